@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Headline benchmark: particle flight+scatter steps/s of the EMC timestep on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload at N=1 (BASELINE.json configs[1]): bulk velocity-field sweep, 24 field points
+log-spaced 0.1-50 kV/cm along -z, 10^6 electrons per field point batched as ONE 2.4e7-particle
+ensemble (EMC_FIELD_GROUPS), GaAs parameters / dt / Gamma / tables exactly as init_.py and
+scatter_.calc_scatter_table give them.  A "step" of the bench is one timestep of the whole
+ensemble = one launch of the fused flight/scatter kernel with the observables of
+main_.py:394-403 reduced in the same launch.  The metric counts flight segments
+(carrier_drift calls, each ending in a scatter event or the end of the timestep).
+N > 1: every rank owns its own 2.4e7-particle slice (Philox keyed by global particle id),
+no data-path collective (this configuration has no Poisson coupling) -> weak scaling.
+
+Printed JSON (one line, rank 0): see the contract in the task description; extra keys
+`roofline`, `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`, `coupled`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_FIELDS = 24
+PER_FIELD = 1_000_000
+SEED = 12345
+ALGO_BYTES_PER_PARTICLE_STEP = 120      # read+write 7 f64 + 1 i32 of state
+METRIC = "particle flight+scatter steps/sec"
+UNIT = "steps/s"
+
+
+def field_points():
+    """24 field points log-spaced 0.1 .. 50 kV/cm along -z (V/cm)."""
+    mags = np.logspace(np.log10(100.0), np.log10(50000.0), N_FIELDS)
+    return np.stack([np.zeros(N_FIELDS), np.zeros(N_FIELDS), -mags], axis=1)
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: bulk velocity-field sweep, 24 field points 0.1-50 kV/cm, "
+                        "1e6 electrons per point batched (2.4e7 particles per GPU), dt=2fs, Gamma=4e14/s",
+            "particles_per_gpu": N_FIELDS * PER_FIELD, "field_points": N_FIELDS,
+            "global_particles": N_FIELDS * PER_FIELD * n_gpus,
+            "parallelism": "particle slices per rank, no data-path collective",
+            "l2_policy": "inputs larger than L2 (1.44 GB of particle state per GPU vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:      # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:      # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:      # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """dram bytes per launch of the flight kernel from the committed ncu summary, if any."""
+    p = os.path.join(ROOT, "profiles", "flight_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:      # noqa: BLE001
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------
+def oracle_for_bench(n_per_field):
+    import helpers
+    o = helpers.make_oracle()
+    o.set_field_groups(field_points(), n_per_field)
+    return o
+
+
+def cpu_port_run(n_per_field, steps, warmup, threads, budget_s=None):
+    """The oracle (C port of the reference's loop, OpenMP over particles) on a bounded sample
+    of the same workload: 24 field groups x n_per_field particles."""
+    import oracle as orc
+    o = oracle_for_bench(n_per_field)
+    n = N_FIELDS * n_per_field
+    st = o.init_ensemble(n, SEED, 0)
+    for s in range(warmup):
+        o.timestep(st, orc.philox_stream(SEED, s, 0), threads=threads)
+    seg, t0, done = 0, time.perf_counter(), 0
+    for s in range(warmup, warmup + steps):
+        seg += o.timestep(st, orc.philox_stream(SEED, s, 0), threads=threads)["n_segments"]
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return seg / dt, dt, done, n
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python original cannot
+    travel to the GPU box and runs ~1e3 steps/s/core) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_per_field = 100_000
+    value, dt, done, n = cpu_port_run(n_per_field, args.steps, args.warmup, threads)
+    sample = "%d particles (24 field groups x %d), %d timesteps" % (n, n_per_field, done)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from monte_carlo_carrier_transport_b200 import abi, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = N_FIELDS * PER_FIELD
+    ctx = engine.Context(device=local)             # init_ / scatter_ module state -> EmcParams + tables
+    ctx.set_field_groups(field_points(), PER_FIELD)
+    # global particle id = rank*n + i; field group = (global id / PER_FIELD) % 24 is arranged by
+    # giving every rank the same 24 groups: the group index uses the LOCAL offset
+    ens = engine.Ensemble(ctx, n, pid_offset=0)
+    ens.init(SEED + rank)
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    for s in range(warmup):
+        ens.step(s, SEED + rank, field_mode=abi.FIELD_GROUPS)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    obs_keep = torch.zeros((steps, 11), dtype=torch.int64, device=ctx.device)
+    launches0 = ctx.launch_count()
+    barrier()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(steps):
+        ev[s][0].record()
+        ens.step(warmup + s, SEED + rank, field_mode=abi.FIELD_GROUPS)
+        ev[s][1].record()
+        obs_keep[s].copy_(ens.obs, non_blocking=True)
+    t_stop.record()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    elapsed_ms = t_start.elapsed_time(t_stop)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    raw = obs_keep.cpu().numpy()
+    segments = int(raw[:, 9].sum())
+    events = int(raw[:, 10].sum())
+    faults = int(raw[-1, 8])
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end-to-end arm: the caller holds HOST arrays (the reference's coords/valley/dtau) ----
+    co, val, dtau = None, None, None
+    hs = engine.HostStepper(ctx, n)
+    # start the host copy from the current device state
+    out = torch.empty((n, 6), dtype=torch.float64, device=ctx.device)
+    p = ens._ptrs()
+    ctx.check(ctx.lib.emc_soa_to_aos(ctx.h, *p[:6], n, out.data_ptr(), ctx.stream))
+    hs.coords_t.copy_(out)
+    hs.valley_t.copy_(ens.valley)
+    hs.dtau_t.copy_(ens.state[6])
+    del out
+    torch.cuda.synchronize()
+    e2e_steps = max(3, min(steps, 10))
+    hs.step(10_000, SEED + rank, field_mode=abi.FIELD_GROUPS)          # warm-up (allocations, pinning)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    seg_e2e = 0
+    for s in range(e2e_steps):
+        seg_e2e += hs.step(10_001 + s, SEED + rank, field_mode=abi.FIELD_GROUPS)["n_segments"]
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # ---- max over ranks, totals over ranks ---------------------------------------------------
+    t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=ctx.device)
+    c = torch.tensor([segments, seg_e2e, events, faults], dtype=torch.int64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms, kernel_ms = (float(v) for v in t.cpu())
+    segments, seg_e2e, events, faults = (int(v) for v in c.cpu())
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = ALGO_BYTES_PER_PARTICLE_STEP * n / (kernel_ms * 1e-3) / 1e9
+        threads = os.cpu_count() or 1
+        cpu_value, cpu_dt, cpu_steps, cpu_n = cpu_port_run(100_000, 40, 2, threads, budget_s=12.0)
+        line = {
+            "metric": METRIC, "value": segments / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": elapsed_ms / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "particle_timesteps_per_s": world * n * steps / (elapsed_ms * 1e-3),
+            "segments_per_particle_timestep": segments / (world * n * steps),
+            "events_per_particle_timestep": events / (world * n * steps), "faulted_particles": faults,
+            "roofline": {"bound": "hbm", "kernel": "flight_scatter_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
+                         "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n},
+            "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d particles (24 field groups x 100000), %d timesteps, %.1f s"
+                                       % (cpu_n, cpu_steps, cpu_dt)},
+            "e2e": {"value": seg_e2e / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": hs.h2d_bytes,
+                    "d2h_bytes_per_step": hs.d2h_bytes,
+                    "api": "engine.HostStepper.step: pinned host (N,6) coords + valley + dtau in, same out"},
+            "gpu_launches": int(launches), "clocks": clk,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,231 @@
+/*
+ * emc.h -- C-ABI of the B200-native ensemble Monte Carlo hot path.
+ *
+ * This is the drop-in boundary for the particle loop of
+ * edsolibet/Monte_Carlo_Carrier_Transport.  The reference has no FFI layer: its
+ * boundary is the Python function surface of main_.py / scatter_.py /
+ * poisson_.py, so every entry point below names the reference function (file:line
+ * into the reference repository) whose work it replaces.  The reference-side
+ * binding (a ctypes stub) is shown in INTEGRATION.md and shipped as
+ * monte_carlo_carrier_transport_b200/abi.py.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes and POD structs only; no C++ or torch types.
+ *   - every function returns an int status: 0 = ok, < 0 = EMC_ERR_* (never throws);
+ *     emc_last_error() returns the message of the last failure.
+ *   - "device pointer" arguments point into memory owned by the CALLER (torch
+ *     tensors in the Python host); the library never allocates particle-sized
+ *     memory.  All launches are asynchronous on the caller's stream
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream) unless a
+ *     function returns a value to the HOST, in which case it synchronises that
+ *     stream before returning.
+ *   - one EmcCtx per (process, device); not thread-safe without external locking
+ *     (the reference is single-threaded).
+ *   - particle state is structure-of-arrays float64: kx ky kz [1/m], x y z [m],
+ *     dtau [s] (time left of the current free flight, main_.py:337,391) and an
+ *     int32 valley (0 = Gamma, 1 = L, 2 = X).  A particle the reference would have
+ *     raised on (scatter_.py:45,47,1079, NaN propagation) gets
+ *     valley = -(1 + EMC_FAULT_*) and is frozen; faults are counted in EmcObs.
+ */
+#ifndef EMC_H
+#define EMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMC_ABI_VERSION 1
+#define EMC_MAX_MECH 16
+
+/* status codes */
+enum {
+    EMC_OK = 0,
+    EMC_ERR_INVALID = -1,      /* bad argument */
+    EMC_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+    EMC_ERR_NO_TABLES = -3,    /* emc_upload_tables has not been called */
+    EMC_ERR_DIVERGED = -4,     /* SOR update >= 1e3, the reference's "Too large du" (poisson_.py:78-80) */
+    EMC_ERR_UNSUPPORTED = -5
+};
+
+/* polar-angle samplers (scatter_.py:795-889) */
+enum { EMC_SAMPLER_SELF = 0, EMC_SAMPLER_ISO = 1, EMC_SAMPLER_POP_ABS = 2,
+       EMC_SAMPLER_POP_EMS = 3, EMC_SAMPLER_ION = 4 };
+
+/* per-particle fault codes (valley = -(1+code)) */
+enum { EMC_FAULT_NAN = 0,        /* scatter_.py:45  "Nan energy" */
+       EMC_FAULT_ZERO_E = 1,     /* scatter_.py:47  zero energy */
+       EMC_FAULT_NO_MECH = 2,    /* no column with cum > r2 (cannot happen: last column is 1) */
+       EMC_FAULT_DOMAIN = 3,     /* NaN final state (arcsin/arccos/sqrt domain), the reference propagates NaN */
+       EMC_FAULT_NEG_ENERGY = 4, /* E0 + dE < 0 -> sqrt(negative) at scatter_.py:1071 */
+       EMC_FAULT_ZERO_K = 5,     /* scatter_.py:1079 exact-zero component */
+       EMC_FAULT_STREAM = 6 };   /* replay stream exhausted */
+
+/* charge assignment schemes */
+enum { EMC_DEPOSIT_NGP = 0,      /* poisson_.py:30-38 (inclusive box test, face hits count twice) */
+       EMC_DEPOSIT_CIC = 1 };    /* the commented weight at poisson_.py:34, 2^-32 fixed point */
+
+/* Poisson sweep orders */
+enum { EMC_SOR_LEXICOGRAPHIC = 0, /* poisson_.py:74 order, executed as hyperplane wavefronts: bit-identical iterates */
+       EMC_SOR_RED_BLACK = 1 };   /* same fixed point, parallel colouring (the fast path) */
+
+/* field sources of the flight kernel */
+enum { EMC_FIELD_CONSTANT = 0,   /* dev.elec_field, main_.py:367,373,388 */
+       EMC_FIELD_GROUPS = 1,     /* particle i uses field_groups[(pid_offset+i)/group_size] (velocity-field sweeps) */
+       EMC_FIELD_MESH = 2 };     /* nearest-cell gather from the Poisson field (poisson_.py:88-96), V/m */
+
+/* Physical / numerical parameters: a snapshot of init_.Parameters, init_.GaAs and
+ * init_.Device (init_.py:58-157). */
+typedef struct EmcParams {
+    double dt;            /* init_.py:60  */
+    double gamma;         /* init_.py:83  GaAs.tot_scat (self-scattering ceiling) */
+    double hbar;          /* init_.py:68  */
+    double q;             /* init_.py:67  */
+    double mass[3];       /* init_.py:87  */
+    double nonparab[3];   /* init_.py:89  */
+    double tot_dim[3];    /* init_.py:147 */
+    double efield[3];     /* init_.py:133, V/cm */
+    double e_phonon;      /* init_.py:79  */
+    double ion_eb;        /* scatter_.py:868-869  q/(2*eps_0*b), b = (1/(2*dope))**(1/3) */
+    double kT;            /* init_.py:64 */
+    double mean_energy;   /* init_.py:145 (in units of kT) */
+    /* mesh (init_.py:135-150) */
+    int32_t seg[3];       /* cells per axis */
+    int32_t pad_;
+    double dl[3];         /* cell size */
+    double rho_background;/* init_.py:189-191: -dope*prod(dl)*1e6 per cell */
+    double rho_increment; /* poisson_.py:36: dope*vol*1e6/num_carr per super-particle */
+    double eps_s;         /* GaAs.eps_0, the permittivity used at poisson_.py:76 */
+    double surf_val;      /* Dirichlet value of the z-min face, poisson_.py:51-52 */
+} EmcParams;
+
+/* Ensemble observables of one timestep (main_.py:394-403), as raw sums so that
+ * ranks can be combined with an integer/double all-reduce. */
+typedef struct EmcObs {
+    double sum_z, sum_vz, sum_e;   /* main_.py:398-400 numerators */
+    double sum_vz2, sum_e2;        /* for the standard errors */
+    int64_t n_valley[3];           /* main_.py:401-403 */
+    int64_t n_fault;               /* frozen particles */
+    int64_t n_segments;            /* carrier_drift calls: the "flight+scatter steps" of the headline metric */
+    int64_t n_events;              /* scatter_.scatter calls */
+} EmcObs;
+
+typedef struct EmcCtx EmcCtx;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int emc_abi_version(void);
+/* Creates a context on CUDA device `device`.  Fails (EMC_ERR_CUDA) when no device exists:
+ * there is no CPU fallback. */
+int emc_create(const EmcParams *params, int device, EmcCtx **out);
+void emc_destroy(EmcCtx *ctx);
+/* message of the last failure on ctx (or of the last failed emc_create when ctx == NULL) */
+const char *emc_last_error(const EmcCtx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t emc_launch_count(const EmcCtx *ctx);
+
+/* ---- tables: scatter_.calc_scatter_table (scatter_.py:954-984) + scatter_mech (:892-951) -- */
+/* HOST pointers.  ek: energy grid (n_energy), must be np.linspace(0, e_max, n_energy)
+ * (init_.py:160-166).  cum[v]: row-major (n_energy, n_mech[v]) cumulative table of valley v.
+ * dE/trans/sampler: [3][EMC_MAX_MECH] mechanism metadata.  The tables are copied to the
+ * device (2.7 MB, L2-resident). */
+int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy,
+                      const double *cum0, const double *cum1, const double *cum2,
+                      const int32_t n_mech[3], const double *dE, const int32_t *trans,
+                      const int32_t *sampler);
+
+/* constant field (V/cm) used by EMC_FIELD_CONSTANT; replaces EmcParams.efield */
+int emc_set_efield(EmcCtx *ctx, const double efield[3]);
+/* EMC_FIELD_GROUPS table: HOST pointer to n_groups x 3 doubles (V/cm) */
+int emc_set_field_groups(EmcCtx *ctx, const double *efields, int32_t n_groups, int64_t group_size);
+
+/* ---- ensemble initialisation: init_.init_coords (init_.py:194-234) + main_.py:53,337 ------ */
+/* Device pointers.  Philox4x32-10 keyed by `seed`, counter (draw/2, 0xFFFFFFFF, pid). */
+int emc_init_ensemble(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y,
+                      double *z, double *dtau, int32_t *valley, int64_t n, uint64_t seed,
+                      uint64_t pid_offset, void *stream);
+
+/* ---- the particle loop of one timestep: main_.py:360-397 --------------------------------- */
+/* free_flight (main_.py:114) + carrier_drift/cyclic_boundary/specular_refl (:125-213) +
+ * scatter_.scatter (scatter_.py:986-1099), fused, one call per timestep for the whole
+ * ensemble.  Random numbers: in-kernel Philox4x32-10, key = seed, counter =
+ * (draw/2, step, pid_offset+i).  field_mode selects EMC_FIELD_*; ex/ey/ez are the padded
+ * (nx+2,ny+2,nz+2) field arrays of emc_field (only for EMC_FIELD_MESH, else NULL).
+ * obs (device pointer to one EmcObs, may be NULL): if given, the observables of
+ * main_.py:394-403 are reduced in the same kernel and written there.
+ * mesh (device int64[nx*ny*nz], may be NULL): if given, the end-of-step NGP charge
+ * assignment (poisson_.py:30-38) is fused into the kernel (atomically ADDED to mesh). */
+int emc_flight_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y,
+                       double *z, double *dtau, int32_t *valley, int64_t n,
+                       int32_t field_mode, const double *ex, const double *ey, const double *ez,
+                       uint64_t seed, uint64_t pid_offset, uint32_t step,
+                       EmcObs *obs, int64_t *mesh, void *stream);
+
+/* Replay mode: the same loop, but every np.random.uniform() of the reference is read from a
+ * per-particle sequential stream: uniforms is a device (n, stride) row-major array, cursor a
+ * device int32[n] read position that the call advances. */
+int emc_flight_scatter_replay(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x,
+                              double *y, double *z, double *dtau, int32_t *valley, int64_t n,
+                              int32_t field_mode, const double *ex, const double *ey,
+                              const double *ez, uint64_t pid_offset,
+                              const double *uniforms, int64_t stride, int32_t *cursor,
+                              EmcObs *obs, int64_t *mesh, void *stream);
+
+/* main_.py:394-403 without stepping.  out is a HOST pointer; synchronises the stream. */
+int emc_observables(EmcCtx *ctx, const double *kx, const double *ky, const double *kz,
+                    const double *z, const int32_t *valley, int64_t n, EmcObs *out, void *stream);
+
+/* ---- single-function batches (the reference's per-particle signatures, n particles) -------- */
+/* scatter_.calc_energy (scatter_.py:19-54): e_np[n], idx[n], fault[n] (-1 = ok) */
+int emc_calc_energy(EmcCtx *ctx, const double *kx, const double *ky, const double *kz,
+                    const int32_t *valley, int64_t n, double *e_np, int32_t *idx,
+                    int32_t *fault, void *stream);
+/* main_.free_flight (main_.py:114-123): out[i] = (-1/g0)*log(r[i]) */
+int emc_free_flight(EmcCtx *ctx, double g0, const double *r, int64_t n, double *out, void *stream);
+/* main_.carrier_drift (main_.py:179-213) with per-particle field (n x 3, V/cm), flight time
+ * and effective mass (the reference passes mat.mass[valley]); state updated in place */
+int emc_carrier_drift(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y,
+                      double *z, const double *mass, const double *efield3, const double *dt2,
+                      int64_t n, void *stream);
+/* scatter_.scatter (scatter_.py:986-1099) with explicit uniforms u (n x 3: r2, azimuth,
+ * polar).  k and valley updated in place unless the particle faults; mech[n], n_draws[n]
+ * (2 for self-scattering, else 3) and fault[n] (-1 = ok) are outputs. */
+int emc_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, int32_t *valley,
+                const double *u3, int64_t n, int32_t *mech, int32_t *n_draws, int32_t *fault,
+                void *stream);
+
+/* ---- layout helpers for callers that hold the reference's (N,6) array (main_.py:51-52) ----- */
+int emc_aos_to_soa(EmcCtx *ctx, const double *coords6, int64_t n, double *kx, double *ky,
+                   double *kz, double *x, double *y, double *z, void *stream);
+int emc_soa_to_aos(EmcCtx *ctx, const double *kx, const double *ky, const double *kz,
+                   const double *x, const double *y, const double *z, int64_t n,
+                   double *coords6, void *stream);
+
+/* ---- charge assignment: poisson_.get_near (poisson_.py:30-44; twin main_.py:242-261) ------- */
+/* ADDS to mesh (device int64[nx*ny*nz], z fastest like rho.reshape(tot_seg), poisson_.py:42):
+ * NGP adds 1 per hit cell, CIC adds llrint(w * 2^32).  Integer, hence bit-exact and
+ * independent of the order particles are visited in (and of the number of ranks). */
+int emc_deposit(EmcCtx *ctx, const double *x, const double *y, const double *z, int64_t n,
+                int64_t *mesh, int32_t scheme, void *stream);
+/* rho_pad (device, (nx+2,ny+2,nz+2), zero halo as np.pad at poisson_.py:53).  NGP: background
+ * then `count` sequential += increment (poisson_.py:27,36: bit-identical to the reference's
+ * accumulation).  CIC: background + increment * mesh/2^32. */
+int emc_mesh_to_rho(EmcCtx *ctx, const int64_t *mesh, int32_t scheme, double *rho_pad,
+                    void *stream);
+
+/* ---- Poisson: poisson_.py:47-84 (twin main_.py:283-315) ------------------------------------ */
+/* u_pad: device (nx+2,ny+2,nz+2), holds the initial guess INCLUDING boundary values
+ * (poisson_.py:47-52) and receives the solution.  Iterates until RMS(update) <= tol or
+ * max_sweeps.  sweeps_out / err_out (HOST, may be NULL) receive the sweep count and the
+ * last RMS update; err_hist (HOST, max_sweeps doubles, may be NULL) the whole history.
+ * Synchronises the stream. */
+int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad, double omega0, double tol,
+                    int32_t max_sweeps, int32_t order, int32_t *sweeps_out, double *err_out,
+                    double *err_hist, void *stream);
+/* E = -central difference on interior cells (poisson_.py:88-96); padded outputs, V/m */
+int emc_field(EmcCtx *ctx, const double *u_pad, double *ex, double *ey, double *ez, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMC_H */

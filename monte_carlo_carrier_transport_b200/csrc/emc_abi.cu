@@ -1,0 +1,405 @@
+// emc_abi.cu -- the extern "C" boundary declared in include/emc.h.
+// Argument validation, context lifetime, table upload; every compute entry point is a thin
+// wrapper over a kernel launcher in emc_flight.cu / emc_mesh.cu.  No exception crosses the ABI.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "emc_host.h"
+
+using namespace emc;
+
+struct EmcCtx {
+    Ctx c;
+};
+
+static std::string g_create_error;
+
+#define CTX_OR_FAIL(ctx)                                       \
+    if (!(ctx)) return EMC_ERR_INVALID;                        \
+    Ctx *c = &(ctx)->c;                                        \
+    {                                                          \
+        cudaError_t e__ = cudaSetDevice(c->device);            \
+        if (e__ != cudaSuccess) return fail_cuda(c, e__, "cudaSetDevice"); \
+    }
+
+static int fail(Ctx *c, int code, const char *msg)
+{
+    c->last_error = msg;
+    return code;
+}
+
+static int fail_cuda(Ctx *c, cudaError_t e, const char *where)
+{
+    c->last_error = std::string(where) + ": " + cudaGetErrorString(e);
+    return EMC_ERR_CUDA;
+}
+
+static void fill_devconst(Ctx *c)
+{
+    const EmcParams &p = c->params;
+    DevConst &d = c->dc;
+    d.dt = p.dt;
+    d.neg_inv_gamma = -1 / p.gamma;             // main_.py:122 (-1/G0)
+    d.hbar = p.hbar;
+    d.q = p.q;
+    d.half_q = 0.5 * p.q;
+    d.hbar2 = p.hbar * p.hbar;
+    for (int v = 0; v < 3; ++v) {
+        d.mass[v] = p.mass[v];
+        d.den[v] = 2 * p.mass[v] * p.q;         // (2*m)*q
+        d.four_a[v] = 4 * p.nonparab[v];
+        d.two_a[v] = 2 * p.nonparab[v];
+        d.hbar_over_m[v] = p.hbar / p.mass[v];
+        d.tot_dim[v] = p.tot_dim[v];
+        d.efield[v] = p.efield[v];
+        d.seg[v] = p.seg[v];
+        d.dl[v] = p.dl[v];
+    }
+    d.e_phonon = p.e_phonon;
+    d.ion_eb = p.ion_eb;
+}
+
+extern "C" int emc_abi_version(void) { return EMC_ABI_VERSION; }
+
+extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
+{
+    if (!params || !out) { g_create_error = "null argument"; return EMC_ERR_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        g_create_error = std::string("no CUDA device (there is no CPU fallback): ") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return EMC_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return EMC_ERR_INVALID; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return EMC_ERR_CUDA;
+    }
+    for (int a = 0; a < 3; ++a)
+        if (params->seg[a] < 1 || !(params->dl[a] > 0) || !(params->tot_dim[a] > 0) || !(params->mass[a] > 0)) {
+            g_create_error = "seg/dl/tot_dim/mass must be positive";
+            return EMC_ERR_INVALID;
+        }
+    if (!(params->gamma > 0) || !(params->dt > 0)) { g_create_error = "gamma and dt must be positive"; return EMC_ERR_INVALID; }
+    EmcCtx *h = new (std::nothrow) EmcCtx();
+    if (!h) { g_create_error = "out of host memory"; return EMC_ERR_INVALID; }
+    Ctx *c = &h->c;
+    c->params = *params;
+    c->device = device;
+    std::memset(&c->dc, 0, sizeof(c->dc));
+    std::memset(&c->mech, 0, sizeof(c->mech));
+    fill_devconst(c);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) goto fail_cuda_create;
+    c->sm_count = prop.multiProcessorCount;
+    {
+        int per_sm = 4;
+        const char *env = std::getenv("EMC_BLOCKS_PER_SM");
+        if (env && std::atoi(env) > 0) per_sm = std::atoi(env);
+        c->max_grid = c->sm_count * per_sm;
+        const char *ex = std::getenv("EMC_EXACT_LIBM");
+        c->exact_libm = ex && std::atoi(ex) != 0;
+    }
+    if ((e = cudaMalloc(&c->partials, sizeof(ObsPartial) * (size_t)c->max_grid)) != cudaSuccess) goto fail_cuda_create;
+    if ((e = cudaMalloc(&c->ticket, sizeof(unsigned int))) != cudaSuccess) goto fail_cuda_create;
+    if ((e = cudaMemset(c->ticket, 0, sizeof(unsigned int))) != cudaSuccess) goto fail_cuda_create;
+    if ((e = cudaMalloc(&c->d_obs, sizeof(EmcObs))) != cudaSuccess) goto fail_cuda_create;
+    if ((e = cudaMalloc(&c->d_sor_scalars, sizeof(double) * 8)) != cudaSuccess) goto fail_cuda_create;
+    if ((e = cudaMalloc(&c->d_sor_flags, sizeof(int32_t) * 4)) != cudaSuccess) goto fail_cuda_create;
+    if ((e = cudaMalloc(&c->d_sor_partials, sizeof(double) * 4096)) != cudaSuccess) goto fail_cuda_create;
+    *out = h;
+    return EMC_OK;
+fail_cuda_create:
+    g_create_error = std::string("CUDA: ") + cudaGetErrorString(e);
+    emc_destroy(h);
+    return EMC_ERR_CUDA;
+}
+
+extern "C" void emc_destroy(EmcCtx *ctx)
+{
+    if (!ctx) return;
+    Ctx *c = &ctx->c;
+    cudaSetDevice(c->device);
+    for (int v = 0; v < 3; ++v)
+        if (c->d_cum[v]) cudaFree(c->d_cum[v]);
+    if (c->d_groups) cudaFree(c->d_groups);
+    if (c->partials) cudaFree(c->partials);
+    if (c->ticket) cudaFree(c->ticket);
+    if (c->d_obs) cudaFree(c->d_obs);
+    if (c->d_sor_scalars) cudaFree(c->d_sor_scalars);
+    if (c->d_sor_flags) cudaFree(c->d_sor_flags);
+    if (c->d_sor_partials) cudaFree(c->d_sor_partials);
+    if (c->d_err_hist) cudaFree(c->d_err_hist);
+    delete ctx;
+}
+
+extern "C" const char *emc_last_error(const EmcCtx *ctx)
+{
+    return ctx ? ctx->c.last_error.c_str() : g_create_error.c_str();
+}
+
+extern "C" int64_t emc_launch_count(const EmcCtx *ctx) { return ctx ? ctx->c.launches : 0; }
+
+extern "C" int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy, const double *cum0,
+                                 const double *cum1, const double *cum2, const int32_t n_mech[3],
+                                 const double *dE, const int32_t *trans, const int32_t *sampler)
+{
+    CTX_OR_FAIL(ctx);
+    if (!ek || !cum0 || !cum1 || !cum2 || !n_mech || !dE || !trans || !sampler || n_energy < 2)
+        return fail(c, EMC_ERR_INVALID, "emc_upload_tables: null argument or n_energy < 2");
+    // the kernel regenerates the grid as i*step (np.linspace with start 0): verify that is what we were given
+    const double step = ek[1] - ek[0];
+    if (!(step > 0) || ek[0] != 0.0) return fail(c, EMC_ERR_UNSUPPORTED, "energy grid must start at 0 and increase");
+    for (int32_t i = 0; i < n_energy - 1; ++i)
+        if (ek[i] != (double)i * step)
+            return fail(c, EMC_ERR_UNSUPPORTED, "energy grid is not np.linspace(0, e_max, n) (init_.py:160-166)");
+    const double *cum[3] = {cum0, cum1, cum2};
+    for (int v = 0; v < 3; ++v) {
+        if (n_mech[v] < 1 || n_mech[v] > EMC_MAX_MECH) return fail(c, EMC_ERR_INVALID, "n_mech out of range");
+        for (int j = 0; j < n_mech[v]; ++j) {
+            const int t = trans[v * EMC_MAX_MECH + j], s = sampler[v * EMC_MAX_MECH + j];
+            if (t < 0 || t > 2 || s < 0 || s > EMC_SAMPLER_ION)
+                return fail(c, EMC_ERR_INVALID, "mechanism metadata out of range");
+        }
+    }
+    for (int v = 0; v < 3; ++v) {
+        const size_t bytes = sizeof(double) * (size_t)n_energy * (size_t)n_mech[v];
+        if (c->d_cum[v]) { cudaFree(c->d_cum[v]); c->d_cum[v] = nullptr; }
+        cudaError_t e = cudaMalloc(&c->d_cum[v], bytes);
+        if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(table)");
+        e = cudaMemcpy(c->d_cum[v], cum[v], bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(table)");
+        c->dc.cum[v] = c->d_cum[v];
+        c->dc.n_mech[v] = n_mech[v];
+        for (int j = 0; j < EMC_MAX_MECH; ++j) {
+            c->mech.dE[v][j] = dE[v * EMC_MAX_MECH + j];
+            c->mech.trans[v][j] = trans[v * EMC_MAX_MECH + j];
+            c->mech.sampler[v][j] = sampler[v * EMC_MAX_MECH + j];
+        }
+    }
+    c->dc.n_energy = n_energy;
+    c->dc.ek_step = step;
+    c->dc.e_max = ek[n_energy - 1];
+    c->have_tables = true;
+    return EMC_OK;
+}
+
+extern "C" int emc_set_efield(EmcCtx *ctx, const double efield[3])
+{
+    CTX_OR_FAIL(ctx);
+    if (!efield) return fail(c, EMC_ERR_INVALID, "emc_set_efield: null");
+    for (int a = 0; a < 3; ++a) c->params.efield[a] = c->dc.efield[a] = efield[a];
+    return EMC_OK;
+}
+
+extern "C" int emc_set_field_groups(EmcCtx *ctx, const double *efields, int32_t n_groups, int64_t group_size)
+{
+    CTX_OR_FAIL(ctx);
+    if (!efields || n_groups < 1 || group_size < 1) return fail(c, EMC_ERR_INVALID, "emc_set_field_groups: bad argument");
+    if (c->d_groups) { cudaFree(c->d_groups); c->d_groups = nullptr; }
+    cudaError_t e = cudaMalloc(&c->d_groups, sizeof(double) * 3 * (size_t)n_groups);
+    if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(groups)");
+    e = cudaMemcpy(c->d_groups, efields, sizeof(double) * 3 * (size_t)n_groups, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(groups)");
+    c->dc.field_groups = c->d_groups;
+    c->dc.n_groups = n_groups;
+    c->dc.group_size = group_size;
+    return EMC_OK;
+}
+
+static int check_state(Ctx *c, const void *kx, const void *ky, const void *kz, const void *x, const void *y,
+                       const void *z, const void *dtau, const void *valley, int64_t n)
+{
+    if (n < 0) return fail(c, EMC_ERR_INVALID, "n < 0");
+    if (n > 0 && (!kx || !ky || !kz || !x || !y || !z || !dtau || !valley))
+        return fail(c, EMC_ERR_INVALID, "null particle-state pointer");
+    return EMC_OK;
+}
+
+extern "C" int emc_init_ensemble(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                                 double *dtau, int32_t *valley, int64_t n, uint64_t seed, uint64_t pid_offset,
+                                 void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    int r = check_state(c, kx, ky, kz, x, y, z, dtau, valley, n);
+    if (r) return r;
+    if (n == 0) return EMC_OK;
+    cudaError_t e = launch_init_ensemble(c, kx, ky, kz, x, y, z, dtau, valley, n, seed, pid_offset,
+                                         (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "init_ensemble launch");
+}
+
+static int flight_common(Ctx *c, FlightArgs &A, bool replay, int32_t field_mode, const double *ex, const double *ey,
+                         const double *ez, void *stream)
+{
+    if (!c->have_tables) return fail(c, EMC_ERR_NO_TABLES, "emc_upload_tables has not been called");
+    if (field_mode == EMC_FIELD_MESH && (!ex || !ey || !ez)) return fail(c, EMC_ERR_INVALID, "EMC_FIELD_MESH needs ex, ey, ez");
+    if (field_mode == EMC_FIELD_GROUPS && !c->dc.field_groups)
+        return fail(c, EMC_ERR_INVALID, "EMC_FIELD_GROUPS needs emc_set_field_groups");
+    if (field_mode < 0 || field_mode > EMC_FIELD_MESH) return fail(c, EMC_ERR_INVALID, "unknown field_mode");
+    A.ex = ex; A.ey = ey; A.ez = ez;
+    if (A.n == 0) return EMC_OK;
+    cudaError_t e = launch_flight(c, A, replay, field_mode, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "flight_scatter launch");
+}
+
+extern "C" int emc_flight_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                                  double *dtau, int32_t *valley, int64_t n, int32_t field_mode, const double *ex,
+                                  const double *ey, const double *ez, uint64_t seed, uint64_t pid_offset,
+                                  uint32_t step, EmcObs *obs, int64_t *mesh, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    int r = check_state(c, kx, ky, kz, x, y, z, dtau, valley, n);
+    if (r) return r;
+    FlightArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.kx = kx; A.ky = ky; A.kz = kz; A.x = x; A.y = y; A.z = z; A.dtau = dtau; A.valley = valley; A.n = n;
+    A.seed = seed; A.pid_offset = pid_offset; A.step = step;
+    A.obs = obs; A.mesh = mesh;
+    return flight_common(c, A, false, field_mode, ex, ey, ez, stream);
+}
+
+extern "C" int emc_flight_scatter_replay(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y,
+                                         double *z, double *dtau, int32_t *valley, int64_t n, int32_t field_mode,
+                                         const double *ex, const double *ey, const double *ez, uint64_t pid_offset,
+                                         const double *uniforms, int64_t stride, int32_t *cursor, EmcObs *obs,
+                                         int64_t *mesh, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    int r = check_state(c, kx, ky, kz, x, y, z, dtau, valley, n);
+    if (r) return r;
+    if (n > 0 && (!uniforms || !cursor || stride < 1 || stride > 0x7fffffff))
+        return fail(c, EMC_ERR_INVALID, "replay needs uniforms, cursor and 1 <= stride < 2^31");
+    FlightArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.kx = kx; A.ky = ky; A.kz = kz; A.x = x; A.y = y; A.z = z; A.dtau = dtau; A.valley = valley; A.n = n;
+    A.uniforms = uniforms; A.stride = stride; A.cursor = cursor; A.pid_offset = pid_offset;
+    A.obs = obs; A.mesh = mesh;
+    return flight_common(c, A, true, field_mode, ex, ey, ez, stream);
+}
+
+extern "C" int emc_observables(EmcCtx *ctx, const double *kx, const double *ky, const double *kz, const double *z,
+                               const int32_t *valley, int64_t n, EmcObs *out, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!out || n < 0 || (n > 0 && (!kx || !ky || !kz || !z || !valley)))
+        return fail(c, EMC_ERR_INVALID, "emc_observables: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = launch_observables(c, kx, ky, kz, z, valley, n, c->d_obs, st);
+    if (e != cudaSuccess) return fail_cuda(c, e, "observables launch");
+    if ((e = cudaMemcpyAsync(out, c->d_obs, sizeof(EmcObs), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+        return fail_cuda(c, e, "observables copy");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail_cuda(c, e, "observables sync");
+    return EMC_OK;
+}
+
+extern "C" int emc_calc_energy(EmcCtx *ctx, const double *kx, const double *ky, const double *kz,
+                               const int32_t *valley, int64_t n, double *e_np, int32_t *idx, int32_t *fault,
+                               void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->have_tables) return fail(c, EMC_ERR_NO_TABLES, "emc_upload_tables has not been called");
+    if (n < 0 || (n > 0 && (!kx || !ky || !kz || !valley || !e_np || !idx || !fault)))
+        return fail(c, EMC_ERR_INVALID, "emc_calc_energy: bad argument");
+    if (n == 0) return EMC_OK;
+    cudaError_t e = launch_calc_energy(c, kx, ky, kz, valley, n, e_np, idx, fault, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "calc_energy launch");
+}
+
+extern "C" int emc_free_flight(EmcCtx *ctx, double g0, const double *r, int64_t n, double *out, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (n < 0 || (n > 0 && (!r || !out))) return fail(c, EMC_ERR_INVALID, "emc_free_flight: bad argument");
+    if (n == 0) return EMC_OK;
+    cudaError_t e = launch_free_flight(c, g0, r, n, out, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "free_flight launch");
+}
+
+extern "C" int emc_carrier_drift(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                                 const double *mass, const double *efield3, const double *dt2, int64_t n,
+                                 void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (n < 0 || (n > 0 && (!kx || !ky || !kz || !x || !y || !z || !mass || !efield3 || !dt2)))
+        return fail(c, EMC_ERR_INVALID, "emc_carrier_drift: bad argument");
+    if (n == 0) return EMC_OK;
+    cudaError_t e = launch_carrier_drift(c, kx, ky, kz, x, y, z, mass, efield3, dt2, n, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "carrier_drift launch");
+}
+
+extern "C" int emc_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, int32_t *valley, const double *u3,
+                           int64_t n, int32_t *mech, int32_t *n_draws, int32_t *fault, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->have_tables) return fail(c, EMC_ERR_NO_TABLES, "emc_upload_tables has not been called");
+    if (n < 0 || (n > 0 && (!kx || !ky || !kz || !valley || !u3 || !mech || !n_draws || !fault)))
+        return fail(c, EMC_ERR_INVALID, "emc_scatter: bad argument");
+    if (n == 0) return EMC_OK;
+    cudaError_t e = launch_scatter(c, kx, ky, kz, valley, u3, n, mech, n_draws, fault, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "scatter launch");
+}
+
+extern "C" int emc_aos_to_soa(EmcCtx *ctx, const double *coords6, int64_t n, double *kx, double *ky, double *kz,
+                              double *x, double *y, double *z, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (n < 0 || (n > 0 && (!coords6 || !kx || !ky || !kz || !x || !y || !z)))
+        return fail(c, EMC_ERR_INVALID, "emc_aos_to_soa: bad argument");
+    if (((uintptr_t)coords6 & 15) != 0) return fail(c, EMC_ERR_INVALID, "coords6 must be 16-byte aligned");
+    if (n == 0) return EMC_OK;
+    cudaError_t e = launch_aos_to_soa(c, coords6, n, kx, ky, kz, x, y, z, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "aos_to_soa launch");
+}
+
+extern "C" int emc_soa_to_aos(EmcCtx *ctx, const double *kx, const double *ky, const double *kz, const double *x,
+                              const double *y, const double *z, int64_t n, double *coords6, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (n < 0 || (n > 0 && (!coords6 || !kx || !ky || !kz || !x || !y || !z)))
+        return fail(c, EMC_ERR_INVALID, "emc_soa_to_aos: bad argument");
+    if (((uintptr_t)coords6 & 15) != 0) return fail(c, EMC_ERR_INVALID, "coords6 must be 16-byte aligned");
+    if (n == 0) return EMC_OK;
+    cudaError_t e = launch_soa_to_aos(c, kx, ky, kz, x, y, z, n, coords6, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "soa_to_aos launch");
+}
+
+extern "C" int emc_deposit(EmcCtx *ctx, const double *x, const double *y, const double *z, int64_t n, int64_t *mesh,
+                           int32_t scheme, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (n < 0 || !mesh || (n > 0 && (!x || !y || !z))) return fail(c, EMC_ERR_INVALID, "emc_deposit: bad argument");
+    if (scheme != EMC_DEPOSIT_NGP && scheme != EMC_DEPOSIT_CIC) return fail(c, EMC_ERR_INVALID, "unknown deposit scheme");
+    if (n == 0) return EMC_OK;
+    cudaError_t e = launch_deposit(c, x, y, z, n, mesh, scheme, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "deposit launch");
+}
+
+extern "C" int emc_mesh_to_rho(EmcCtx *ctx, const int64_t *mesh, int32_t scheme, double *rho_pad, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!mesh || !rho_pad) return fail(c, EMC_ERR_INVALID, "emc_mesh_to_rho: null");
+    if (scheme != EMC_DEPOSIT_NGP && scheme != EMC_DEPOSIT_CIC) return fail(c, EMC_ERR_INVALID, "unknown deposit scheme");
+    cudaError_t e = launch_mesh_to_rho(c, mesh, scheme, rho_pad, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "mesh_to_rho launch");
+}
+
+extern "C" int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad, double omega0, double tol,
+                               int32_t max_sweeps, int32_t order, int32_t *sweeps_out, double *err_out,
+                               double *err_hist, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!u_pad || !rho_pad) return fail(c, EMC_ERR_INVALID, "emc_poisson_sor: null");
+    return run_poisson_sor(c, u_pad, rho_pad, omega0, tol, max_sweeps, order, sweeps_out, err_out, err_hist,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int emc_field(EmcCtx *ctx, const double *u_pad, double *ex, double *ey, double *ez, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!u_pad || !ex || !ey || !ez) return fail(c, EMC_ERR_INVALID, "emc_field: null");
+    cudaError_t e = launch_field(c, u_pad, ex, ey, ez, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "field launch");
+}

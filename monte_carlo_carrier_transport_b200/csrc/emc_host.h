@@ -1,0 +1,92 @@
+// emc_host.h -- host-side context and launcher prototypes shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "emc_device.cuh"
+
+namespace emc {
+
+constexpr int FLIGHT_THREADS = 256;
+constexpr int SMEM_MESH_BYTES = 96 * 1024;     // NGP counts privatised in shared memory up to this size
+
+struct ObsPartial {
+    double d[5];
+    long long c[6];
+};
+
+// kernel arguments of the timestep kernel (device pointers are the caller's)
+struct FlightArgs {
+    double *kx, *ky, *kz, *x, *y, *z, *dtau;
+    int32_t *valley;
+    int64_t n;
+    // random stream
+    const double *uniforms;      // replay
+    int64_t stride;
+    int32_t *cursor;
+    uint64_t seed, pid_offset;   // philox
+    uint32_t step;
+    // EMC_FIELD_MESH
+    const double *ex, *ey, *ez;
+    // fused epilogues
+    EmcObs *obs;
+    ObsPartial *partials;
+    unsigned int *ticket;
+    int64_t *mesh;
+    int32_t smem_cells;
+};
+
+struct Ctx {
+    EmcParams params;
+    DevConst dc;
+    MechMeta mech;
+    int device = 0;
+    int sm_count = 0;
+    int max_grid = 0;             // persistent grid: sm_count * resident blocks
+    bool have_tables = false;
+    bool exact_libm = false;      // EMC_EXACT_LIBM=1: compose acos/asin/atan exactly like the reference
+    double *d_cum[3] = {nullptr, nullptr, nullptr};
+    double *d_groups = nullptr;
+    ObsPartial *partials = nullptr;
+    unsigned int *ticket = nullptr;
+    EmcObs *d_obs = nullptr;      // scratch for emc_observables
+    // Poisson scratch
+    double *d_sor_scalars = nullptr;   // [0] err, [1] omega, ...
+    double *d_err_hist = nullptr;
+    int err_hist_cap = 0;
+    double *d_sor_partials = nullptr;
+    int32_t *d_sor_flags = nullptr;
+    int64_t launches = 0;
+    std::string last_error;
+};
+
+// emc_flight.cu
+cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, cudaStream_t st);
+cudaError_t launch_observables(Ctx *ctx, const double *kx, const double *ky, const double *kz, const double *z,
+                               const int32_t *valley, int64_t n, EmcObs *out_dev, cudaStream_t st);
+cudaError_t launch_init_ensemble(Ctx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                                 double *dtau, int32_t *valley, int64_t n, uint64_t seed, uint64_t pid_offset,
+                                 cudaStream_t st);
+cudaError_t launch_calc_energy(Ctx *ctx, const double *kx, const double *ky, const double *kz,
+                               const int32_t *valley, int64_t n, double *e_np, int32_t *idx, int32_t *fault,
+                               cudaStream_t st);
+cudaError_t launch_free_flight(Ctx *ctx, double g0, const double *r, int64_t n, double *out, cudaStream_t st);
+cudaError_t launch_carrier_drift(Ctx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                                 const double *mass, const double *ef3, const double *dt2, int64_t n,
+                                 cudaStream_t st);
+cudaError_t launch_scatter(Ctx *ctx, double *kx, double *ky, double *kz, int32_t *valley, const double *u3,
+                           int64_t n, int32_t *mech, int32_t *n_draws, int32_t *fault, cudaStream_t st);
+cudaError_t launch_aos_to_soa(Ctx *ctx, const double *c6, int64_t n, double *kx, double *ky, double *kz, double *x,
+                              double *y, double *z, cudaStream_t st);
+cudaError_t launch_soa_to_aos(Ctx *ctx, const double *kx, const double *ky, const double *kz, const double *x,
+                              const double *y, const double *z, int64_t n, double *c6, cudaStream_t st);
+
+// emc_mesh.cu
+cudaError_t launch_deposit(Ctx *ctx, const double *x, const double *y, const double *z, int64_t n, int64_t *mesh,
+                           int scheme, cudaStream_t st);
+cudaError_t launch_mesh_to_rho(Ctx *ctx, const int64_t *mesh, int scheme, double *rho_pad, cudaStream_t st);
+cudaError_t launch_field(Ctx *ctx, const double *u_pad, double *ex, double *ey, double *ez, cudaStream_t st);
+// returns 0 / EMC_ERR_*; fills sweeps/err; synchronises
+int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega0, double tol, int max_sweeps,
+                    int order, int32_t *sweeps_out, double *err_out, double *err_hist, cudaStream_t st);
+
+}  // namespace emc

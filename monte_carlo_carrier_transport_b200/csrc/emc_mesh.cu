@@ -1,0 +1,458 @@
+// emc_mesh.cu -- charge assignment (poisson_.py:30-44), rho assembly (poisson_.py:27,36,42,53),
+// Poisson SOR (poisson_.py:47-84) and field (poisson_.py:88-96) on the device-resident mesh.
+// Mesh layout everywhere: C order of (nx, ny, nz) / padded (nx+2, ny+2, nz+2), z fastest, like
+// rho.reshape(dev.tot_seg) in the reference.  Compiled with -fmad=false.
+#include <cooperative_groups.h>
+#include <cmath>
+#include <vector>
+#include "emc_host.h"
+
+namespace cg = cooperative_groups;
+
+namespace emc {
+
+// ------------------------------------------------------------------------------------------
+// charge assignment
+// ------------------------------------------------------------------------------------------
+// cloud-in-cell weights on one axis: the two nearest centres, w = 1 - |centre - r|/dl
+// (the commented line poisson_.py:34)
+__device__ __forceinline__ void axis_cic(double r, double dl, int j[2], double w[2])
+{
+    const double t = r / dl - 0.5;
+    const double f = floor(t);
+    const double w1 = t - f;
+    j[0] = (int)f;
+    j[1] = j[0] + 1;
+    w[0] = 1.0 - w1;
+    w[1] = w1;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(256)
+deposit_ngp_kernel(const __grid_constant__ DevConst P, const double *__restrict__ x, const double *__restrict__ y,
+                   const double *__restrict__ z, int64_t n, unsigned long long *mesh, int cells)
+{
+    extern __shared__ unsigned int scount[];
+    if (SMEM) {
+        for (int t = threadIdx.x; t < cells; t += blockDim.x) scount[t] = 0u;
+        __syncthreads();
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int hx[3], hy[3], hz[3];
+        const int nx = axis_hits(x[i], P.seg[0], P.dl[0], hx);
+        const int ny = axis_hits(y[i], P.seg[1], P.dl[1], hy);
+        const int nz = axis_hits(z[i], P.seg[2], P.dl[2], hz);
+        for (int a = 0; a < nx; ++a)
+            for (int b = 0; b < ny; ++b)
+                for (int c = 0; c < nz; ++c) {
+                    const int64_t cell = ((int64_t)hx[a] * P.seg[1] + hy[b]) * P.seg[2] + hz[c];
+                    if (SMEM) atomicAdd(&scount[cell], 1u);
+                    else atomicAdd(mesh + cell, 1ull);
+                }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < cells; t += blockDim.x) {
+            const unsigned int v = scount[t];
+            if (v) atomicAdd(mesh + t, (unsigned long long)v);
+        }
+    }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(256)
+deposit_cic_kernel(const __grid_constant__ DevConst P, const double *__restrict__ x, const double *__restrict__ y,
+                   const double *__restrict__ z, int64_t n, unsigned long long *mesh, int cells)
+{
+    extern __shared__ unsigned long long sfx[];
+    if (SMEM) {
+        for (int t = threadIdx.x; t < cells; t += blockDim.x) sfx[t] = 0ull;
+        __syncthreads();
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int jx[2], jy[2], jz[2];
+        double wx[2], wy[2], wz[2];
+        axis_cic(x[i], P.dl[0], jx, wx);
+        axis_cic(y[i], P.dl[1], jy, wy);
+        axis_cic(z[i], P.dl[2], jz, wz);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (jx[a] < 0 || jx[a] >= P.seg[0] || jy[b] < 0 || jy[b] >= P.seg[1] || jz[c] < 0 ||
+                        jz[c] >= P.seg[2])
+                        continue;
+                    const double w = wx[a] * wy[b] * wz[c];
+                    const unsigned long long q = (unsigned long long)__double2ll_rn(w * 4294967296.0);
+                    const int64_t cell = ((int64_t)jx[a] * P.seg[1] + jy[b]) * P.seg[2] + jz[c];
+                    if (SMEM) atomicAdd(&sfx[cell], q);
+                    else atomicAdd(mesh + cell, q);
+                }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < cells; t += blockDim.x) {
+            const unsigned long long v = sfx[t];
+            if (v) atomicAdd(mesh + t, v);
+        }
+    }
+}
+
+cudaError_t launch_deposit(Ctx *ctx, const double *x, const double *y, const double *z, int64_t n, int64_t *mesh,
+                           int scheme, cudaStream_t st)
+{
+    const int64_t cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];
+    const int64_t blocks_needed = (n + 255) / 256;
+    int grid = (int)(blocks_needed < (int64_t)ctx->max_grid ? blocks_needed : ctx->max_grid);
+    if (grid < 1) grid = 1;
+    unsigned long long *m = reinterpret_cast<unsigned long long *>(mesh);
+    ctx->launches++;
+    if (scheme == EMC_DEPOSIT_NGP) {
+        if (cells * 4 <= SMEM_MESH_BYTES)
+            deposit_ngp_kernel<true><<<grid, 256, (size_t)cells * 4, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
+        else
+            deposit_ngp_kernel<false><<<grid, 256, 0, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
+    } else {
+        if (cells * 8 <= SMEM_MESH_BYTES)
+            deposit_cic_kernel<true><<<grid, 256, (size_t)cells * 8, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
+        else
+            deposit_cic_kernel<false><<<grid, 256, 0, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
+    }
+    return cudaGetLastError();
+}
+
+// rho_pad: zero halo (np.pad, poisson_.py:53); interior = background + charge
+__global__ void mesh_to_rho_kernel(const __grid_constant__ DevConst P, const long long *__restrict__ mesh, int scheme,
+                                   double background, double increment, double *rho_pad)
+{
+    const int nx = P.seg[0], ny = P.seg[1], nz = P.seg[2];
+    const int64_t total = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= total) return;
+    const int k = (int)(c % (nz + 2));
+    const int j = (int)((c / (nz + 2)) % (ny + 2));
+    const int i = (int)(c / ((int64_t)(nz + 2) * (ny + 2)));
+    if (i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz) { rho_pad[c] = 0.0; return; }
+    const long long m = mesh[((int64_t)(i - 1) * ny + (j - 1)) * nz + (k - 1)];
+    double r = background;                                   // poisson_.py:27
+    if (scheme == EMC_DEPOSIT_NGP) {
+        for (long long t = 0; t < m; ++t) r += increment;    // poisson_.py:36, one += per hit, in sequence
+    } else {
+        r = background + increment * ((double)m / 4294967296.0);
+    }
+    rho_pad[c] = r;
+}
+
+cudaError_t launch_mesh_to_rho(Ctx *ctx, const int64_t *mesh, int scheme, double *rho_pad, cudaStream_t st)
+{
+    const int64_t total = (int64_t)(ctx->dc.seg[0] + 2) * (ctx->dc.seg[1] + 2) * (ctx->dc.seg[2] + 2);
+    ctx->launches++;
+    mesh_to_rho_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+        ctx->dc, reinterpret_cast<const long long *>(mesh), scheme, ctx->params.rho_background,
+        ctx->params.rho_increment, rho_pad);
+    return cudaGetLastError();
+}
+
+// E = -central difference on interior cells (poisson_.py:88-96), zero halo
+__global__ void field_kernel(const __grid_constant__ DevConst P, const double *__restrict__ u, double *ex,
+                             double *ey, double *ez)
+{
+    const int nx = P.seg[0], ny = P.seg[1], nz = P.seg[2];
+    const int64_t sy = nz + 2, sx = (int64_t)(ny + 2) * (nz + 2);
+    const int64_t total = (int64_t)(nx + 2) * sx;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= total) return;
+    const int k = (int)(c % (nz + 2));
+    const int j = (int)((c / (nz + 2)) % (ny + 2));
+    const int i = (int)(c / sx);
+    if (i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz) {
+        ex[c] = 0.0; ey[c] = 0.0; ez[c] = 0.0;
+        return;
+    }
+    ex[c] = -0.5 * (u[c + sx] - u[c - sx]) / P.dl[0];      // :94
+    ey[c] = -0.5 * (u[c + sy] - u[c - sy]) / P.dl[1];      // :95
+    ez[c] = -0.5 * (u[c + 1] - u[c - 1]) / P.dl[2];        // :96
+}
+
+cudaError_t launch_field(Ctx *ctx, const double *u_pad, double *ex, double *ey, double *ez, cudaStream_t st)
+{
+    const int64_t total = (int64_t)(ctx->dc.seg[0] + 2) * (ctx->dc.seg[1] + 2) * (ctx->dc.seg[2] + 2);
+    ctx->launches++;
+    field_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->dc, u_pad, ex, ey, ez);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Poisson SOR
+// ------------------------------------------------------------------------------------------
+struct SorConst {
+    int nx, ny, nz;
+    double xy, xz, e;       // poisson_.py:56-57,61
+    double dl0sq;           // dl[0]*dl[0]     (poisson_.py:76)
+    double eps_s;
+    double pch2_quarter;    // 0.25*(p*p), p = 0.5*sum(cos(pi/n)) (poisson_.py:68,81)
+    double omega0, tol;
+    int max_sweeps;
+};
+
+// one Gauss-Seidel/SOR cell update, poisson_.py:58-60,76-77.  Returns u_new - u_old.
+__device__ __forceinline__ double sor_update(const SorConst &S, double *u, const double *rho, int64_t c, int64_t sx,
+                                             int64_t sy, double relx, bool &diverged)
+{
+    const double uc = u[c];
+    double sum = S.e * uc;
+    sum += u[c + sx];
+    sum += u[c - sx];
+    sum += S.xy * u[c + sy];
+    sum += S.xy * u[c - sy];
+    sum += S.xz * u[c + 1];
+    sum += S.xz * u[c - 1];
+    const double du = (sum - S.dl0sq * rho[c] / S.eps_s) * relx / S.e;
+    const double un = uc - du;
+    u[c] = un;
+    if (fabs(du) >= 1e3) diverged = true;       // poisson_.py:78-80
+    return un - uc;
+}
+
+__device__ __forceinline__ double block_sum(double v, double *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < nwarp; ++w) t += scratch[w];
+        scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// Lexicographic order (poisson_.py:74: k outer, j, i inner) executed as hyperplane wavefronts
+// h = i+j+k: a cell's (i-1, j-1, k-1) neighbours lie on plane h-1 (already updated, as in the
+// sequential sweep) and its (+1) neighbours on plane h+1 (still old), and cells of one plane
+// are mutually independent -- so every iterate is bit-identical to the sequential loop.
+// One CTA; the whole solve (all sweeps) is one launch.  SMEM: u and rho live in shared memory.
+template <bool SMEM>
+__global__ void __launch_bounds__(1024)
+sor_lex_kernel(const __grid_constant__ SorConst S, double *u_g, const double *rho_g, double *err_hist,
+               double *scalars, int32_t *flags)
+{
+    extern __shared__ double sm[];
+    __shared__ double scratch[33];
+    __shared__ int s_div;
+    const int nx = S.nx, ny = S.ny, nz = S.nz;
+    const int64_t sy = nz + 2, sx = (int64_t)(ny + 2) * (nz + 2);
+    const int64_t total = (int64_t)(nx + 2) * sx;
+    double *u = u_g;
+    const double *rho = rho_g;
+    if (SMEM) {
+        double *su = sm, *srho = sm + total;
+        for (int64_t t = threadIdx.x; t < total; t += blockDim.x) { su[t] = u_g[t]; srho[t] = rho_g[t]; }
+        u = su;
+        rho = srho;
+    }
+    if (threadIdx.x == 0) s_div = 0;
+    __syncthreads();
+    double relx = S.omega0;          // poisson_.py:66
+    double err = 1;
+    int num = 0;
+    bool diverged = false;
+    while (err > S.tol && num < S.max_sweeps) {      // poisson_.py:69
+        double acc = 0.0;
+        for (int h = 3; h <= nx + ny + nz; ++h) {
+            const int ilo = max(1, h - ny - nz), ihi = min(nx, h - 2);
+            const int pairs = (ihi - ilo + 1) * ny;
+            for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+                const int i = ilo + p / ny, j = 1 + p % ny, k = h - i - j;
+                if (k >= 1 && k <= nz) {
+                    const double d = sor_update(S, u, rho, i * sx + j * sy + k, sx, sy, relx, diverged);
+                    acc += d * d;
+                }
+            }
+            __syncthreads();
+        }
+        relx = 1 / (1 - S.pch2_quarter * relx);      // poisson_.py:81
+        const double ssq = block_sum(acc, scratch);
+        err = sqrt(ssq / (double)total);             // poisson_.py:82 (RMS over the padded array)
+        if (threadIdx.x == 0) err_hist[num] = err;
+        num += 1;
+        if (diverged) s_div = 1;
+        __syncthreads();
+        if (s_div) break;
+    }
+    if (SMEM) {
+        for (int64_t t = threadIdx.x; t < total; t += blockDim.x) u_g[t] = u[t];
+    }
+    if (threadIdx.x == 0) {
+        scalars[0] = err;
+        scalars[1] = relx;
+        flags[0] = num;
+        flags[1] = s_div;
+    }
+}
+
+// Red-black ordering: colour = (i+j+k) & 1.  Cooperative persistent grid, two grid syncs per
+// sweep; omega is updated once per sweep and the stopping rule is the reference's RMS update.
+__global__ void __launch_bounds__(256)
+sor_rb_kernel(const __grid_constant__ SorConst S, double *u, const double *__restrict__ rho, double *err_hist,
+              double *scalars, int32_t *flags, double *partials)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double scratch[33];
+    const int nx = S.nx, ny = S.ny, nz = S.nz;
+    const int64_t sy = nz + 2, sx = (int64_t)(ny + 2) * (nz + 2);
+    const int64_t total = (int64_t)(nx + 2) * sx;
+    const int hz = (nz + 1) >> 1;                       // k slots per (i,j) column and colour
+    const int64_t work = (int64_t)nx * ny * hz;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double relx = S.omega0;
+    double err = 1;
+    int num = 0;
+    bool diverged = false;
+    int any_div = 0;
+    while (err > S.tol && num < S.max_sweeps) {
+        double acc = 0.0;
+        for (int colour = 0; colour < 2; ++colour) {
+            for (int64_t t = gtid; t < work; t += gstride) {
+                const int kk = (int)(t % hz);
+                const int j = 1 + (int)((t / hz) % ny);
+                const int i = 1 + (int)(t / ((int64_t)hz * ny));
+                const int k = 1 + 2 * kk + (((i + j + 1) & 1) != colour ? 1 : 0);
+                if (k <= nz) {
+                    const double d = sor_update(S, u, rho, i * sx + j * sy + k, sx, sy, relx, diverged);
+                    acc += d * d;
+                }
+            }
+            if (colour == 0) grid.sync();
+        }
+        relx = 1 / (1 - S.pch2_quarter * relx);
+        const double bs = block_sum(acc, scratch);
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = bs;
+            if (diverged) atomicExch(&flags[1], 1);
+        }
+        grid.sync();
+        // every block folds the partials in the same fixed order -> identical err everywhere
+        double v = 0.0;
+        if (threadIdx.x < 32) {
+            for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) v += __ldcg(&partials[b]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (threadIdx.x == 0) {
+                scratch[32] = v;
+                scratch[31] = (double)__ldcg(&flags[1]);
+            }
+        }
+        __syncthreads();
+        err = sqrt(scratch[32] / (double)total);
+        any_div = scratch[31] != 0.0;
+        __syncthreads();
+        if (gtid == 0) err_hist[num] = err;
+        num += 1;
+        if (any_div) break;
+    }
+    if (gtid == 0) {
+        scalars[0] = err;
+        scalars[1] = relx;
+        flags[0] = num;
+    }
+}
+
+int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega0, double tol, int max_sweeps,
+                    int order, int32_t *sweeps_out, double *err_out, double *err_hist, cudaStream_t st)
+{
+    const int nx = ctx->dc.seg[0], ny = ctx->dc.seg[1], nz = ctx->dc.seg[2];
+    const double *dl = ctx->dc.dl;
+    SorConst S;
+    S.nx = nx; S.ny = ny; S.nz = nz;
+    S.xy = (dl[0] / dl[1]) * (dl[0] / dl[1]);            // poisson_.py:56 (x/y)**2
+    S.xz = (dl[0] / dl[2]) * (dl[0] / dl[2]);
+    S.e = -2 * (1 + S.xy + S.xz);
+    S.dl0sq = dl[0] * dl[0];
+    S.eps_s = ctx->params.eps_s;
+    const double pch = 0.5 * std::cos(M_PI / nx) + 0.5 * std::cos(M_PI / ny) + 0.5 * std::cos(M_PI / nz);
+    S.pch2_quarter = 0.25 * (pch * pch);
+    S.omega0 = omega0; S.tol = tol; S.max_sweeps = max_sweeps;
+    if (max_sweeps < 1) { ctx->last_error = "max_sweeps < 1"; return EMC_ERR_INVALID; }
+
+    cudaError_t e;
+    if (ctx->err_hist_cap < max_sweeps) {
+        if (ctx->d_err_hist) cudaFree(ctx->d_err_hist);
+        ctx->d_err_hist = nullptr;
+        if ((e = cudaMalloc(&ctx->d_err_hist, sizeof(double) * (size_t)max_sweeps)) != cudaSuccess) goto cuda_fail;
+        ctx->err_hist_cap = max_sweeps;
+    }
+    if ((e = cudaMemsetAsync(ctx->d_sor_flags, 0, 4 * sizeof(int32_t), st)) != cudaSuccess) goto cuda_fail;
+    {
+        const int64_t total = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
+        ctx->launches++;
+        if (order == EMC_SOR_LEXICOGRAPHIC) {
+            const size_t need = (size_t)total * 2 * sizeof(double);
+            if (need <= 200 * 1024) {
+                if ((e = cudaFuncSetAttribute(sor_lex_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)need)) != cudaSuccess) goto cuda_fail;
+                sor_lex_kernel<true><<<1, 1024, need, st>>>(S, u_pad, rho_pad, ctx->d_err_hist, ctx->d_sor_scalars,
+                                                           ctx->d_sor_flags);
+            } else {
+                sor_lex_kernel<false><<<1, 1024, 0, st>>>(S, u_pad, rho_pad, ctx->d_err_hist, ctx->d_sor_scalars,
+                                                          ctx->d_sor_flags);
+            }
+            e = cudaGetLastError();
+        } else if (order == EMC_SOR_RED_BLACK) {
+            int per_sm = 0;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_kernel, 256, 0)) != cudaSuccess)
+                goto cuda_fail;
+            if (per_sm > 4) per_sm = 4;
+            const int64_t work = (int64_t)nx * ny * ((nz + 1) / 2);
+            int grid = ctx->sm_count * per_sm;
+            const int64_t want = (work + 255) / 256;
+            if (want < grid) grid = (int)want;
+            if (grid < 1) grid = 1;
+            if (grid > 4096) grid = 4096;        // d_sor_partials capacity
+            double *eh = ctx->d_err_hist, *sc = ctx->d_sor_scalars, *pt = ctx->d_sor_partials;
+            int32_t *fl = ctx->d_sor_flags;
+            void *args[] = {(void *)&S, (void *)&u_pad, (void *)&rho_pad, (void *)&eh, (void *)&sc, (void *)&fl,
+                            (void *)&pt};
+            e = cudaLaunchCooperativeKernel((void *)sor_rb_kernel, dim3(grid), dim3(256), args, 0, st);
+        } else {
+            ctx->last_error = "unknown SOR order";
+            return EMC_ERR_INVALID;
+        }
+        if (e != cudaSuccess) goto cuda_fail;
+    }
+    {
+        double scal[2];
+        int32_t fl[2];
+        if ((e = cudaMemcpyAsync(scal, ctx->d_sor_scalars, sizeof(scal), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            goto cuda_fail;
+        if ((e = cudaMemcpyAsync(fl, ctx->d_sor_flags, sizeof(fl), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            goto cuda_fail;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) goto cuda_fail;
+        if (sweeps_out) *sweeps_out = fl[0];
+        if (err_out) *err_out = scal[0];
+        if (err_hist && fl[0] > 0) {
+            if ((e = cudaMemcpy(err_hist, ctx->d_err_hist, sizeof(double) * (size_t)fl[0], cudaMemcpyDeviceToHost)) !=
+                cudaSuccess)
+                goto cuda_fail;
+        }
+        if (fl[1]) {
+            ctx->last_error = "Too large du (poisson_.py:78-80)";
+            return EMC_ERR_DIVERGED;
+        }
+    }
+    return EMC_OK;
+cuda_fail:
+    ctx->last_error = std::string("CUDA: ") + cudaGetErrorString(e);
+    return EMC_ERR_CUDA;
+}
+
+}  // namespace emc

@@ -244,6 +244,28 @@ static int scatter_stream(const OrcParams *p, double coord[6], int32_t *val, Cur
     return scatter_core(p, coord, val, mech, e_np, r_az, r_pol);
 }
 
+/* field seen by particle i at position r (V/cm) */
+static void field_at(const OrcParams *p, const OrcStream *s, int64_t i, const double coord[6], double ef[3])
+{
+    if (p->field_mode == 1) {
+        int64_t g = (int64_t)((s->pid_offset + (uint64_t)i) / (uint64_t)p->group_size);
+        if (g >= p->n_groups) g = p->n_groups - 1;
+        for (int a = 0; a < 3; ++a) ef[a] = p->field_groups[3 * g + a];
+    } else if (p->field_mode == 2) {
+        int c[3];
+        for (int a = 0; a < 3; ++a) {
+            int j = (int)floor(coord[3 + a] / p->dl[a]);
+            if (j < 0) j = 0;
+            if (j > p->seg[a] - 1) j = p->seg[a] - 1;
+            c[a] = j + 1;
+        }
+        int64_t idx = ((int64_t)c[0] * (p->seg[1] + 2) + c[1]) * (p->seg[2] + 2) + c[2];
+        ef[0] = p->ex[idx] * 1e-2; ef[1] = p->ey[idx] * 1e-2; ef[2] = p->ez[idx] * 1e-2;
+    } else {
+        for (int a = 0; a < 3; ++a) ef[a] = p->efield[a];
+    }
+}
+
 static void obs_zero(OrcObs *o) { memset(o, 0, sizeof(*o)); }
 
 static void obs_add(OrcObs *a, const OrcObs *b)
@@ -276,12 +298,14 @@ static void step_particle(const OrcParams *p, double coord[6], double *dtau, int
     if (*valley < 0) return;                      /* frozen after a fault */
     double dt = p->dt;
     double dte = *dtau;                           /* :361 */
+    double ef[3];
+    field_at(p, c->s, c->i, coord, ef);
     if (dte >= dt) {                              /* :363 */
-        orc_carrier_drift(p, coord, p->efield, dt, p->mass[*valley]);     /* :367 */
+        orc_carrier_drift(p, coord, ef, dt, p->mass[*valley]);     /* :367 */
         o->n_segments++;
     } else {
         double dt2 = dte;                         /* :370 */
-        orc_carrier_drift(p, coord, p->efield, dt2, p->mass[*valley]);    /* :373 */
+        orc_carrier_drift(p, coord, ef, dt2, p->mass[*valley]);    /* :373 */
         o->n_segments++;
         while (dte < dt) {                        /* :375 */
             double dte2 = dte;                    /* :376 */
@@ -293,7 +317,8 @@ static void step_particle(const OrcParams *p, double coord[6], double *dtau, int
             if (c->overflow) { *valley = -(1 + ORC_FAULT_STREAM); *dtau = dte; return; }
             double dtp = dt - dte2;               /* :381 */
             dt2 = (dt3 <= dtp) ? dt3 : dtp;       /* :382-385 */
-            orc_carrier_drift(p, coord, p->efield, dt2, p->mass[*valley]);/* :388 */
+            if (p->field_mode == 2) field_at(p, c->s, c->i, coord, ef);
+            orc_carrier_drift(p, coord, ef, dt2, p->mass[*valley]);/* :388 */
             o->n_segments++;
             dte = dte2 + dt3;                     /* :389 */
         }
@@ -330,6 +355,52 @@ void orc_timestep(const OrcParams *p, int64_t n, double *kx, double *ky, double 
         obs_add(&total, &local);
     }
     if (obs) *obs = total;
+}
+
+/* ------------------------------------------------------------------ */
+/* init_coords: init_.py:194-234; valley 0 main_.py:53; dtau main_.py:337
+ * The reference draws from numpy's global MT19937 stream (all x, all y, all z,
+ * then all energies, then two normals per particle), which a counter-based
+ * per-particle generator cannot reproduce draw for draw; the SAME DISTRIBUTIONS are
+ * sampled per particle from Philox (step word 0xFFFFFFFF), draws in this order:
+ *   0,1,2  x, y, z = box * u                               (init_.py:198-200)
+ *   3..6   n1,n2 = BoxMuller(u3,u4); n3,_ = BoxMuller(u5,u6);
+ *          E = mean*kT + 1e-7*sqrt(n1^2+n2^2+n3^2)        (scipy maxwell == chi(3), init_.py:207)
+ *   7,8    alpha, beta = 2*pi*BoxMuller(u7,u8)             (Normal(0, 2*pi), init_.py:216-217)
+ *   9      dtau = (-1/G0)*log(u9)                          (main_.py:337)
+ * BoxMuller(a,b) = sqrt(-2 log(1-a)) * (cos 2 pi b, sin 2 pi b).                  */
+/* ------------------------------------------------------------------ */
+static void box_muller(double ua, double ub, double *n0, double *n1)
+{
+    double rad = sqrt(-2 * log(1 - ua));
+    *n0 = rad * cos(2 * M_PI * ub);
+    *n1 = rad * sin(2 * M_PI * ub);
+}
+
+void orc_init_ensemble(const OrcParams *p, int64_t n, double *kx, double *ky, double *kz,
+                       double *x, double *y, double *z, double *dtau, int32_t *valley,
+                       uint64_t seed, uint64_t pid_offset)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        double u[10];
+        for (uint32_t d = 0; d < 10; ++d)
+            u[d] = orc_philox_uniform(seed, pid_offset + (uint64_t)i, 0xFFFFFFFFu, d);
+        x[i] = p->tot_dim[0] * u[0];
+        y[i] = p->tot_dim[1] * u[1];
+        z[i] = p->tot_dim[2] * u[2];
+        double n1, n2, n3, n4, na, nb;
+        box_muller(u[3], u[4], &n1, &n2);
+        box_muller(u[5], u[6], &n3, &n4);
+        double e = p->mean_energy * p->kT + 1E-7 * sqrt(n1 * n1 + n2 * n2 + n3 * n3);
+        double k = sqrt(2 * p->mass[0] * p->q * e / (p->hbar * p->hbar));    /* init_.py:215 */
+        box_muller(u[7], u[8], &na, &nb);
+        double alpha = 2 * M_PI * na, beta = 2 * M_PI * nb;
+        kx[i] = k * cos(alpha) * sin(beta);       /* init_.py:218-220 */
+        ky[i] = k * sin(alpha) * sin(beta);
+        kz[i] = k * cos(beta);
+        dtau[i] = (-1 / p->gamma) * log(u[9]);
+        valley[i] = 0;
+    }
 }
 
 void orc_observables(const OrcParams *p, int64_t n, const double *kx, const double *ky,
@@ -417,6 +488,13 @@ void orc_counts_to_rho(int64_t n_cells, const int64_t *counts, double background
         for (int64_t k = 0; k < counts[c]; ++k) r += increment;   /* poisson_.py:36 */
         rho[c] = r;
     }
+}
+
+void orc_fx_to_rho(int64_t n_cells, const int64_t *mesh_fx, double background,
+                   double increment, double *rho)
+{
+    for (int64_t c = 0; c < n_cells; ++c)
+        rho[c] = background + increment * ((double)mesh_fx[c] / 4294967296.0);
 }
 
 /* ------------------------------------------------------------------ */

@@ -49,6 +49,18 @@ typedef struct OrcParams {
     double  mech_dE[3][ORC_MAX_MECH];
     int32_t mech_trans[3][ORC_MAX_MECH];
     int32_t mech_sampler[3][ORC_MAX_MECH];
+    /* field source of carrier_drift (extensions beyond the reference's constant dev.elec_field):
+       0 constant `efield`; 1 per-group constant: particle pid uses field_groups[pid/group_size];
+       2 nearest-cell gather from a padded (nx+2,ny+2,nz+2) mesh field in V/m (poisson_.py:88-96) */
+    int32_t field_mode;
+    int32_t n_groups;
+    int64_t group_size;
+    const double *field_groups;
+    int32_t seg[3];
+    int32_t pad_;
+    double dl[3];
+    const double *ex, *ey, *ez;
+    double kT, mean_energy;   /* init_.py:64,145 (ensemble initialisation) */
 } OrcParams;
 
 typedef struct OrcObs {
@@ -87,6 +99,12 @@ void   orc_timestep(const OrcParams *p, int64_t n, double *kx, double *ky, doubl
                     double *x, double *y, double *z, double *dtau, int32_t *valley,
                     OrcStream *s, OrcObs *obs, int n_threads);
 
+/* init_.init_coords (init_.py:194-234) + valley 0 (main_.py:53) + first free flights
+   (main_.py:337) with the Philox draw layout documented in emc_oracle.c */
+void   orc_init_ensemble(const OrcParams *p, int64_t n, double *kx, double *ky, double *kz,
+                         double *x, double *y, double *z, double *dtau, int32_t *valley,
+                         uint64_t seed, uint64_t pid_offset);
+
 /* observables only (main_.py:394-403) */
 void   orc_observables(const OrcParams *p, int64_t n, const double *kx, const double *ky,
                        const double *kz, const double *z, const int32_t *valley, OrcObs *obs);
@@ -101,6 +119,10 @@ void   orc_deposit_cic(int64_t n, const double *x, const double *y, const double
 /* rho[c] = background, then `counts[c]` sequential `+= increment` (poisson_.py:27,36) */
 void   orc_counts_to_rho(int64_t n_cells, const int64_t *counts, double background,
                          double increment, double *rho);
+
+/* CIC fixed point -> rho: background + increment * mesh/2^32 */
+void   orc_fx_to_rho(int64_t n_cells, const int64_t *mesh_fx, double background,
+                     double increment, double *rho);
 
 /* lexicographic Gauss-Seidel/SOR (poisson_.py:55-84) on padded arrays (nx+2,ny+2,nz+2),
    C order (z fastest).  Returns sweeps done; err_hist gets RMS update per sweep. */

@@ -41,6 +41,11 @@ class OrcParams(C.Structure):
         ("mech_dE", (C.c_double * ORC_MAX_MECH) * 3),
         ("mech_trans", (C.c_int32 * ORC_MAX_MECH) * 3),
         ("mech_sampler", (C.c_int32 * ORC_MAX_MECH) * 3),
+        ("field_mode", C.c_int32), ("n_groups", C.c_int32), ("group_size", C.c_int64),
+        ("field_groups", C.POINTER(C.c_double)),
+        ("seg", C.c_int32 * 3), ("pad_", C.c_int32), ("dl", C.c_double * 3),
+        ("ex", C.POINTER(C.c_double)), ("ey", C.POINTER(C.c_double)), ("ez", C.POINTER(C.c_double)),
+        ("kT", C.c_double), ("mean_energy", C.c_double),
     ]
 
 
@@ -88,6 +93,9 @@ def lib():
         L.orc_scatter.argtypes = [C.POINTER(OrcParams), dp, ip, dp, ip, ip]
         L.orc_timestep.argtypes = [C.POINTER(OrcParams), C.c_int64] + [dp] * 7 + [
             ip, C.POINTER(OrcStream), C.POINTER(OrcObs), C.c_int]
+        L.orc_init_ensemble.argtypes = [C.POINTER(OrcParams), C.c_int64] + [dp] * 7 + [
+            ip, C.c_uint64, C.c_uint64]
+        L.orc_fx_to_rho.argtypes = [C.c_int64, lp, C.c_double, C.c_double, dp]
         L.orc_observables.argtypes = [C.POINTER(OrcParams), C.c_int64, dp, dp, dp, dp, ip,
                                       C.POINTER(OrcObs)]
         L.orc_deposit_ngp.argtypes = [C.c_int64, dp, dp, dp, ip, dp, lp]
@@ -141,12 +149,37 @@ class Oracle:
         p.e_phonon, p.ion_eb = phys["e_phonon"], phys["ion_eb"]
         p.n_energy = len(self.ek)
         p.ek = _dp(self.ek)
+        p.kT, p.mean_energy = phys.get("kT", 0.02585), phys.get("mean_energy", 0.1)
+        p.field_mode = 0
         self.p = p
         self.L = lib()
+        self._keep = {}
 
     def set_efield(self, ef):
         for v in range(3):
             self.p.efield[v] = float(ef[v])
+
+    def set_field_groups(self, efields, group_size):
+        ef = np.ascontiguousarray(efields, dtype=np.float64)
+        self._keep["groups"] = ef
+        self.p.field_mode, self.p.n_groups, self.p.group_size = 1, ef.shape[0], int(group_size)
+        self.p.field_groups = _dp(ef)
+
+    def set_field_mesh(self, seg, dl, ex, ey, ez):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (ex, ey, ez)]
+        self._keep["mesh"] = arrs
+        self.p.field_mode = 2
+        for a in range(3):
+            self.p.seg[a], self.p.dl[a] = int(seg[a]), float(dl[a])
+        self.p.ex, self.p.ey, self.p.ez = (_dp(a) for a in arrs)
+
+    def init_ensemble(self, n, seed, pid_offset=0):
+        st = {k: np.zeros(n, dtype=np.float64) for k in ("kx", "ky", "kz", "x", "y", "z", "dtau")}
+        st["valley"] = np.zeros(n, dtype=np.int32)
+        self.L.orc_init_ensemble(C.byref(self.p), n, *[_dp(st[k]) for k in
+                                                       ("kx", "ky", "kz", "x", "y", "z", "dtau")],
+                                 _ip(st["valley"]), seed, pid_offset)
+        return st
 
     # -- single-particle functions (the reference's own signatures) ----------------
     def calc_energy(self, k, val):
@@ -240,6 +273,13 @@ def counts_to_rho(counts, background, increment):
     counts = np.ascontiguousarray(counts, dtype=np.int64)
     rho = np.empty(len(counts), dtype=np.float64)
     lib().orc_counts_to_rho(len(counts), _lp(counts), background, increment, _dp(rho))
+    return rho
+
+
+def fx_to_rho(mesh_fx, background, increment):
+    mesh_fx = np.ascontiguousarray(mesh_fx, dtype=np.int64)
+    rho = np.empty(len(mesh_fx), dtype=np.float64)
+    lib().orc_fx_to_rho(len(mesh_fx), _lp(mesh_fx), background, increment, _dp(rho))
     return rho
 
 

@@ -1,0 +1,528 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle and with the golden vectors
+recorded from the unmodified reference.  Needs a B200: every test is marked ``gpu``.
+
+Bars (north_star): bit-exact for everything built from IEEE + - * / sqrt and for all
+integer / index work (energy index, mechanism choice, valley, draw counts, charge counts,
+rho, lexicographic SOR iterates, field); 1e-9 relative for per-particle trajectories that
+pass through libm transcendentals (CUDA's and glibc's differ in the last ulp).
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TRAJ_RTOL = 1e-9          # north_star: per-particle trajectories within 1e-9 relative error
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("the gpu-marked tests need a CUDA device (no CPU fallback exists)")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ctx(torch_mod):
+    from monte_carlo_carrier_transport_b200 import engine
+    g = helpers.golden_params()
+    p = engine.params_from_dict(g["phys"], g["device"])
+    c = engine.Context(p, device=0, tables=helpers.host_tables())
+    yield c
+    c.close()
+
+
+def dev(torch, a, dtype=None):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+
+
+def k_err(got, ref):
+    """max |dk| / |k_ref| over particles"""
+    kn = np.linalg.norm(ref, axis=1, keepdims=True)
+    return float(np.max(np.abs(got - ref) / kn)) if len(ref) else 0.0
+
+
+# ------------------------------------------------------------------------------------------
+def test_loaded_native_library(ctx):
+    assert ctx.lib.emc_abi_version() == 1
+    assert os.path.basename(ctx.lib._name) == "libemc_b200.so"
+
+
+def test_free_flight_kat(ctx, torch_mod):
+    torch = torch_mod
+    k = helpers.golden_npz("kat")
+    r = dev(torch, k["ff_r1"])
+    out = torch.empty_like(r)
+    ctx.check(ctx.lib.emc_free_flight(ctx.h, float(k["ff_g0"]), r.data_ptr(), len(r), out.data_ptr(), ctx.stream))
+    assert np.max(helpers.rel_err(out.cpu().numpy(), k["ff_out"])) <= 4.5e-16      # log: <= 2 ulp
+
+
+def test_carrier_drift_kat_bit_exact(ctx, torch_mod):
+    torch = torch_mod
+    k = helpers.golden_npz("kat")
+    g = helpers.golden_params()
+    cd = dev(torch, k["cd_in"].T.copy())
+    mass = dev(torch, np.array(g["phys"]["mass"])[k["cd_val"]])
+    ef, dt2 = dev(torch, k["cd_ef"]), dev(torch, k["cd_dt"])
+    n = cd.shape[1]
+    ctx.check(ctx.lib.emc_carrier_drift(ctx.h, *[cd[i].data_ptr() for i in range(6)], mass.data_ptr(),
+                                        ef.data_ptr(), dt2.data_ptr(), n, ctx.stream))
+    assert np.array_equal(cd.cpu().numpy().T, k["cd_out"])
+
+
+def test_calc_energy_kat_bit_exact(ctx, torch_mod):
+    torch = torch_mod
+    k = helpers.golden_npz("kat")
+    kk = dev(torch, k["ce_k"].T.copy())
+    val = dev(torch, k["ce_val"], np.int32)
+    n = kk.shape[1]
+    e = torch.empty(n, dtype=torch.float64, device="cuda")
+    idx = torch.empty(n, dtype=torch.int32, device="cuda")
+    fl = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.check(ctx.lib.emc_calc_energy(ctx.h, kk[0].data_ptr(), kk[1].data_ptr(), kk[2].data_ptr(),
+                                      val.data_ptr(), n, e.data_ptr(), idx.data_ptr(), fl.data_ptr(), ctx.stream))
+    assert (fl.cpu().numpy() == -1).all()
+    assert np.array_equal(e.cpu().numpy(), k["ce_e"])
+    assert np.array_equal(idx.cpu().numpy(), k["ce_idx"])
+
+
+def test_calc_energy_edge_cases(ctx, torch_mod, oracle):
+    """Grid ends, midpoints between grid energies (ties -> lower index), > 2 eV clamp, zero k, NaN."""
+    torch = torch_mod
+    g = helpers.golden_params()["phys"]
+    ek = helpers.host_tables()[0]
+    rng = np.random.RandomState(5)
+    targets = np.concatenate([ek[[1, 2, 3, 5000, 9998, 9999]], (ek[:-1] + ek[1:])[rng.randint(0, 9998, 200)] / 2,
+                              [2.0, 2.1, 5.0, 1e-9, 1e-7], rng.uniform(0, 2.2, 2000)])
+    v = rng.randint(0, 3, len(targets))
+    a, m = np.array(g["nonparab"])[v], np.array(g["mass"])[v]
+    E = targets * (1 + a * targets)                               # invert E_np -> parabolic E
+    kmag = np.sqrt(2 * m * g["q"] * E) / g["hbar"]
+    d = rng.normal(size=(len(targets), 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = kmag[:, None] * d
+    k = np.vstack([k, [[0, 0, 0], [np.nan, 1e8, 1e8]]])
+    v = np.concatenate([v, [0, 1]])
+    n = len(k)
+    kk, val = dev(torch, k.T.copy()), dev(torch, v, np.int32)
+    e = torch.empty(n, dtype=torch.float64, device="cuda")
+    idx = torch.empty(n, dtype=torch.int32, device="cuda")
+    fl = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.check(ctx.lib.emc_calc_energy(ctx.h, kk[0].data_ptr(), kk[1].data_ptr(), kk[2].data_ptr(),
+                                      val.data_ptr(), n, e.data_ptr(), idx.data_ptr(), fl.data_ptr(), ctx.stream))
+    e, idx, fl = e.cpu().numpy(), idx.cpu().numpy(), fl.cpu().numpy()
+    for i in range(n):
+        eo, io, fo = oracle.calc_energy(k[i], int(v[i]))
+        assert fl[i] == fo, i
+        if fo == -1:
+            assert e[i] == eo and idx[i] == io, (i, e[i], eo, idx[i], io)
+    assert fl[-2] == 1 and fl[-1] == 0
+
+
+def run_scatter(ctx, torch, k_in, val_in, u3):
+    n = len(k_in)
+    kk = dev(torch, np.asarray(k_in).T.copy())
+    val = dev(torch, val_in, np.int32)
+    u = dev(torch, u3)
+    mech = torch.empty(n, dtype=torch.int32, device="cuda")
+    nd = torch.empty(n, dtype=torch.int32, device="cuda")
+    fl = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.check(ctx.lib.emc_scatter(ctx.h, kk[0].data_ptr(), kk[1].data_ptr(), kk[2].data_ptr(), val.data_ptr(),
+                                  u.data_ptr(), n, mech.data_ptr(), nd.data_ptr(), fl.data_ptr(), ctx.stream))
+    return kk.cpu().numpy().T, val.cpu().numpy(), mech.cpu().numpy(), nd.cpu().numpy(), fl.cpu().numpy()
+
+
+def test_scatter_kat(ctx, torch_mod):
+    """scatter_.scatter on 3000 pinned-uniform cases recorded from the reference."""
+    k = helpers.golden_npz("kat")
+    kout, vout, mech, nd, fl = run_scatter(ctx, torch_mod, k["sc_in"][:, :3], k["sc_val"], k["sc_u"])
+    ref_bad = (k["sc_vout"] == -1) | np.isnan(k["sc_out"]).any(axis=1)
+    assert np.array_equal(fl >= 0, ref_bad)            # faults exactly where the reference raised / went NaN
+    ok = ~ref_bad
+    assert np.array_equal(mech[ok], k["sc_mech"][ok])
+    assert np.array_equal(nd[ok], k["sc_nd"][ok])
+    assert np.array_equal(vout[ok], k["sc_vout"][ok])
+    assert k_err(kout[ok], k["sc_out"][ok, :3]) < TRAJ_RTOL
+    # a faulted particle keeps its input state
+    assert np.array_equal(kout[~ok], k["sc_in"][~ok, :3])
+
+
+def test_scatter_vs_oracle_dense(ctx, torch_mod, oracle):
+    """20000 random events over all valleys / energies, against the oracle (incl. fault codes)."""
+    g = helpers.golden_params()["phys"]
+    rng = np.random.RandomState(77)
+    n = 20000
+    v = rng.randint(0, 3, n)
+    E = 10 ** rng.uniform(-3.5, 0.3, n)
+    kmag = np.sqrt(2 * np.array(g["mass"])[v] * g["q"] * E) / g["hbar"]
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = kmag[:, None] * d
+    u = rng.random_sample((n, 3))
+    u[::3, 0] *= 0.3
+    kout, vout, mech, nd, fl = run_scatter(ctx, torch_mod, k, v, u)
+    worst = 0.0
+    for i in range(n):
+        c, vo, mo, ndo, fo = oracle.scatter(np.concatenate([k[i], [0, 0, 0]]), int(v[i]), u[i])
+        assert fl[i] == fo, (i, fl[i], fo)
+        assert nd[i] == ndo and mech[i] == mo, i
+        if fo == -1:
+            assert vout[i] == vo
+            worst = max(worst, float(np.max(np.abs(kout[i] - c[:3])) / np.linalg.norm(c[:3])))
+    assert worst < TRAJ_RTOL, worst
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["c1", "hot"])
+def test_replay_golden_trajectories(ctx, torch_mod, case):
+    """The reference's own functions driven over main_.py:360-397 with a per-particle uniform
+    stream, vs the fused CUDA kernel reading the same stream (replay mode)."""
+    torch = torch_mod
+    from monte_carlo_carrier_transport_b200 import engine
+    meta = json.load(open(os.path.join(helpers.GOLDEN, "replay.json")))["cases"][case]
+    r = helpers.golden_npz("replay")
+    N, L = meta["N"], meta["L"]
+    U = np.random.RandomState(meta["seed"] + 1000).random_sample((N, L))
+    ctx.set_efield(meta["efield"])
+    ens = engine.Ensemble(ctx, N).load(r[case + "_coords0"], r[case + "_valley0"], r[case + "_dtau0"])
+    Ud = dev(torch, U[:, 1:].copy())
+    cursor = torch.zeros(N, dtype=torch.int32, device="cuda")
+    fault_step = r[case + "_fault_step"]
+    n_seg = n_ev = 0
+    for s in range(meta["steps"]):
+        ens.step_replay(Ud, cursor)
+        o = ens.last_obs()
+        n_seg += o["n_segments"]
+        n_ev += o["n_events"]
+        if s in meta["snaps"]:
+            co, val, dtau = ens.coords()
+            assert np.array_equal(val < 0, (fault_step >= 0) & (fault_step <= s)), s
+            ok = val >= 0
+            ref = r["%s_coords_s%d" % (case, s)]
+            assert np.array_equal(val[ok], r["%s_valley_s%d" % (case, s)][ok])
+            assert k_err(co[ok, :3], ref[ok, :3]) < TRAJ_RTOL, s
+            dims = np.array(ctx.params.tot_dim[:])
+            assert np.max(np.abs(co[ok, 3:] - ref[ok, 3:]) / dims) < TRAJ_RTOL, s
+            assert np.max(helpers.rel_err(dtau[ok], r["%s_dtau_s%d" % (case, s)][ok])) < 1e-7, s
+    ok = ens.valley.cpu().numpy() >= 0
+    assert np.array_equal(cursor.cpu().numpy()[ok] + 1, r[case + "_cursor_end"][ok])
+    if not (fault_step >= 0).any():
+        assert (n_seg, n_ev) == (meta["n_segments"], meta["n_events"])
+    ctx.set_efield(helpers.golden_params()["phys"]["efield"])
+
+
+def hot_ensemble(n, seed, phys):
+    rng = np.random.RandomState(seed)
+    v = rng.randint(0, 3, n).astype(np.int32)
+    E = 10 ** rng.uniform(-2.5, -0.1, n)
+    kmag = np.sqrt(2 * np.array(phys["mass"])[v] * phys["q"] * E) / phys["hbar"]
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    coords = np.zeros((n, 6))
+    coords[:, :3] = kmag[:, None] * d
+    coords[:, 3:] = rng.uniform(0, 1, (n, 3)) * np.array(phys["tot_dim"])
+    dtau = -np.log(rng.random_sample(n)) / phys["gamma"]
+    return coords, v, dtau
+
+
+def compare_states(st, co, val, dtau, dims, tol=TRAJ_RTOL):
+    assert np.array_equal(st["valley"], val)
+    ok = val >= 0
+    ref = helpers.coords_from_state(st)
+    assert k_err(co[ok, :3], ref[ok, :3]) < tol
+    assert np.max(np.abs(co[ok, 3:] - ref[ok, 3:]) / dims) < tol
+    # dtau = (-1/G) log(u) - remaining time: absolute scale is the mean flight time
+    assert np.max(np.abs(dtau[ok] - st["dtau"][ok])) < 1e-9 * 2.5e-15
+
+
+@pytest.mark.parametrize("efield", [[0, 0, -5000], [3000, -2000, -50000]])
+def test_philox_timesteps_vs_oracle(ctx, torch_mod, efield):
+    """Free-running (in-kernel Philox) mode: the oracle consumes the identical counter-based
+    stream, so trajectories must agree particle by particle, step by step."""
+    from monte_carlo_carrier_transport_b200 import engine
+    g = helpers.golden_params()["phys"]
+    n, steps, seed, off = 20000, 12, 9001, 123456789012
+    coords, v, dtau = hot_ensemble(n, 31, g)
+    o = helpers.make_oracle(efield=efield)
+    st = helpers.state_from_coords(coords, v, dtau)
+    ctx.set_efield(efield)
+    ens = engine.Ensemble(ctx, n, pid_offset=off).load(coords, v, dtau)
+    dims = np.array(g["tot_dim"])
+    for s in range(steps):
+        ens.step(s, seed)
+        og = ens.last_obs()
+        oo = o.timestep(st, orc.philox_stream(seed, s, off), threads=8)
+        assert og["n_segments"] == oo["n_segments"] and og["n_events"] == oo["n_events"], s
+        assert og["n_valley"] == oo["n_valley"] and og["n_fault"] == oo["n_fault"], s
+        for key in ("sum_z", "sum_vz", "sum_e", "sum_vz2", "sum_e2"):
+            assert abs(og[key] - oo[key]) <= 1e-9 * abs(oo[key]), (s, key)
+        if s in (0, 5, steps - 1):
+            compare_states(st, *ens.coords(), dims)
+    ctx.set_efield(g["efield"])
+
+
+def test_field_groups_mode_vs_oracle(ctx, torch_mod):
+    """Velocity-field sweep batching: particle i uses field_groups[(pid_offset+i)/group_size]."""
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    g = helpers.golden_params()["phys"]
+    n, gs = 6000, 1000
+    fields = np.array([[0, 0, -100.0], [0, 0, -1000.0], [0, 0, -5000.0], [500, 0, -20000.0],
+                       [0, 0, -50000.0], [0, -300, -30000.0]])
+    coords, v, dtau = hot_ensemble(n, 32, g)
+    o = helpers.make_oracle()
+    o.set_field_groups(fields, gs)
+    ctx.set_field_groups(fields, gs)
+    st = helpers.state_from_coords(coords, v, dtau)
+    ens = engine.Ensemble(ctx, n).load(coords, v, dtau)
+    for s in range(6):
+        ens.step(s, 17, field_mode=abi.FIELD_GROUPS)
+        o.timestep(st, orc.philox_stream(17, s, 0), threads=4)
+    compare_states(st, *ens.coords(), np.array(g["tot_dim"]))
+
+
+def test_observables_kernel(ctx, torch_mod, oracle):
+    from monte_carlo_carrier_transport_b200 import engine
+    g = helpers.golden_params()["phys"]
+    n = 100003
+    coords, v, dtau = hot_ensemble(n, 33, g)
+    v[::97] = -3                                     # frozen particles are counted, not averaged
+    ens = engine.Ensemble(ctx, n).load(coords, v, dtau)
+    og = ens.observables()
+    oo = oracle.observables(helpers.state_from_coords(coords, v, dtau))
+    assert og["n_valley"] == oo["n_valley"] and og["n_fault"] == oo["n_fault"]
+    for key in ("sum_z", "sum_vz", "sum_e", "sum_vz2", "sum_e2"):
+        assert abs(og[key] - oo[key]) <= 1e-11 * abs(oo[key]), key
+    # run-to-run determinism of the fixed-order reduction
+    assert ens.observables() == og
+
+
+def test_init_ensemble_vs_oracle(ctx, torch_mod, oracle):
+    from monte_carlo_carrier_transport_b200 import engine
+    n, seed, off = 50000, 4242, 7 << 33
+    ens = engine.Ensemble(ctx, n, pid_offset=off).init(seed)
+    co, val, dtau = ens.coords()
+    st = oracle.init_ensemble(n, seed, off)
+    assert (val == 0).all()
+    assert np.array_equal(co[:, 3:], helpers.coords_from_state(st)[:, 3:])       # box * u: exact
+    assert k_err(co[:, :3], helpers.coords_from_state(st)[:, :3]) < 1e-7         # sincos of N(0, 2 pi) angles
+    assert np.max(helpers.rel_err(dtau, st["dtau"])) < 1e-14
+    # init_.init_coords semantics: |k| from E ~ 0.1 kT (+1e-7 chi_3), positions uniform in the box
+    g = helpers.golden_params()["phys"]
+    E = (np.linalg.norm(co[:, :3], axis=1) * g["hbar"]) ** 2 / (2 * g["mass"][0] * g["q"])
+    assert abs(E.mean() - (0.1 * g["kT"] + 1e-7 * 1.5958)) < 2e-9
+    assert np.all((co[:, 3:] >= 0) & (co[:, 3:] <= np.array(g["tot_dim"])))
+    assert abs(dtau.mean() * g["gamma"] - 1) < 0.02
+
+
+def test_aos_soa_roundtrip(ctx, torch_mod):
+    from monte_carlo_carrier_transport_b200 import engine
+    rng = np.random.RandomState(3)
+    for n in (1, 31, 1000, 65537):
+        coords = rng.normal(size=(n, 6))
+        ens = engine.Ensemble(ctx, n).load(coords, np.zeros(n, np.int32), np.ones(n))
+        co, val, dtau = ens.coords()
+        assert np.array_equal(co, coords) and (dtau == 1).all()
+
+
+def test_empty_ensemble_is_a_noop(ctx, torch_mod):
+    from monte_carlo_carrier_transport_b200 import engine
+    ens = engine.Ensemble(ctx, 0)
+    ens.step(0, 1)
+    ens.init(1)
+
+
+def test_host_stepper_matches_device_path(ctx, torch_mod):
+    """The host-array (pinned, chunked, overlapped) timestep gives the same result as the
+    device-resident one: same Philox keys (global particle id), any chunking."""
+    from monte_carlo_carrier_transport_b200 import engine
+    g = helpers.golden_params()["phys"]
+    n = 50001
+    coords, v, dtau = hot_ensemble(n, 34, g)
+    ens = engine.Ensemble(ctx, n).load(coords, v, dtau)
+    hs = engine.HostStepper(ctx, n, chunk=7000)
+    hs.coords[:], hs.valley[:], hs.dtau[:] = coords, v, dtau
+    tot = None
+    for s in range(3):
+        ens.step(s, 99)
+        tot = hs.step(s, 99)
+    co, val, dt_ = ens.coords()
+    assert np.array_equal(hs.coords, co) and np.array_equal(hs.valley, val) and np.array_equal(hs.dtau, dt_)
+    od = ens.last_obs()
+    assert tot["n_segments"] == od["n_segments"] and tot["n_valley"] == od["n_valley"]
+    assert abs(tot["sum_e"] - od["sum_e"]) < 1e-10 * abs(od["sum_e"])
+
+
+# ------------------------------------------------------------------------------------------
+def poisson_inputs():
+    p = helpers.golden_npz("poisson")
+    D = helpers.golden_params()["phys"]["tot_dim"]
+    rng = np.random.RandomState(int(p["seed"]))
+    pos = rng.uniform(0, 1, (int(p["n"]), 3)) * np.array(D)
+    pos[:6] = p["special"]
+    return p, pos
+
+
+def test_ngp_deposit_bit_exact_vs_reference(ctx, torch_mod):
+    """poisson_.py's rho for 10^4 particles incl. face/edge/corner hits (double counting)."""
+    from monte_carlo_carrier_transport_b200 import poisson_
+    p, pos = poisson_inputs()
+    res = poisson_.solve(pos, u0=p["u0"], ctx=ctx)
+    assert np.array_equal(res["counts"], orc.deposit_ngp(pos[:, 0], pos[:, 1], pos[:, 2], p["seg"], p["dl"]))
+    assert np.array_equal(res["rho"], p["rho"].ravel())
+    # ... and the whole script: lexicographic SOR iterates and field are bit-identical
+    assert res["sweeps"] == len(p["err_hist"])
+    assert np.array_equal(res["u_"], p["u_final"])
+    assert np.max(helpers.rel_err(res["err_hist"], p["err_hist"])) < 1e-10
+    assert np.array_equal(res["ef_x"], p["ef_x"]) and np.array_equal(res["ef_y"], p["ef_y"])
+    assert np.array_equal(res["ef_z"], p["ef_z"])
+
+
+def test_red_black_sor_same_fixed_point(ctx, torch_mod):
+    from monte_carlo_carrier_transport_b200 import abi, poisson_
+    p, pos = poisson_inputs()
+    lex = poisson_.solve(pos, u0=p["u0"], ctx=ctx, tol=1e-13, order=abi.SOR_LEXICOGRAPHIC)
+    rb = poisson_.solve(pos, u0=p["u0"], ctx=ctx, tol=1e-13, order=abi.SOR_RED_BLACK)
+    assert np.max(np.abs(lex["u_"] - rb["u_"])) < 1e-10
+    rb6 = poisson_.solve(pos, u0=p["u0"], ctx=ctx, tol=1e-6, order=abi.SOR_RED_BLACK)
+    assert rb6["err"] <= 1e-6 and np.max(np.abs(rb6["u_"] - lex["u_"])) < 2e-5
+    # boundary values untouched
+    assert (rb["u_"][:, :, 0] == 0.6).all() and (rb["u_"][0, :, 1:] == 0).all()
+
+
+def mesh_context(seg, torch):
+    from monte_carlo_carrier_transport_b200 import engine
+    g = helpers.golden_params()
+    device = dict(g["device"])
+    device["seg"] = list(seg)
+    device["dl"] = [g["phys"]["tot_dim"][a] / seg[a] for a in range(3)]
+    p = engine.params_from_dict(g["phys"], device)
+    return engine.Context(p, device=0, tables=helpers.host_tables())
+
+
+@pytest.mark.parametrize("seg", [(16, 3, 12), (256, 1, 192)])
+def test_deposit_and_sor_other_meshes(torch_mod, seg):
+    """3-D mesh (ny > 1) and a mesh too large for shared-memory privatisation / the SMEM solver."""
+    torch = torch_mod
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    c = mesh_context(seg, torch)
+    try:
+        g = helpers.golden_params()["phys"]
+        rng = np.random.RandomState(8)
+        n = 200000
+        dl = np.array(c.params.dl[:])
+        pos = rng.uniform(0, 1, (n, 3)) * np.array(g["tot_dim"])
+        pos[:500] = np.round(pos[:500] / dl) * dl                     # on cell faces / edges / corners
+        coords = np.zeros((n, 6))
+        coords[:, 3:] = pos
+        ens = engine.Ensemble(c, n).load(coords, np.zeros(n, np.int32), np.ones(n))
+        for scheme, ofn in ((abi.DEPOSIT_NGP, orc.deposit_ngp), (abi.DEPOSIT_CIC, orc.deposit_cic)):
+            mesh = engine.Mesh(c, scheme)
+            mesh.deposit(ens)
+            want = ofn(pos[:, 0], pos[:, 1], pos[:, 2], np.array(seg), dl)
+            assert np.array_equal(mesh.counts.cpu().numpy(), want), scheme
+            mesh.to_rho()
+            bg, inc = c.params.rho_background, c.params.rho_increment
+            rho = (orc.counts_to_rho(want, bg, inc) if scheme == abi.DEPOSIT_NGP
+                   else orc.fx_to_rho(want, bg, inc))
+            assert np.array_equal(mesh.rho_pad.cpu().numpy()[1:-1, 1:-1, 1:-1].ravel(), rho), scheme
+        # SOR on the NGP rho: lexicographic wavefronts == the sequential oracle, bit for bit
+        mesh = engine.Mesh(c, abi.DEPOSIT_NGP)
+        mesh.deposit(ens)
+        mesh.to_rho()
+        u0 = rng.random_sample(seg)
+        mesh.set_initial_guess(u0)
+        u_start = mesh.u_pad.cpu().numpy()
+        n_sw, err, hist = mesh.solve(order=abi.SOR_LEXICOGRAPHIC, history=True, max_sweeps=500)
+        uo, no, ho = orc.poisson_sor(np.array(seg), dl, c.params.eps_s, u_start, mesh.rho_pad.cpu().numpy(),
+                                     1.5, 1e-6, 500)
+        assert n_sw == no
+        assert np.array_equal(mesh.u_pad.cpu().numpy(), uo)
+        mesh.field()
+        ex, ey, ez = orc.field(np.array(seg), dl, uo)
+        assert np.array_equal(mesh.ex.cpu().numpy(), ex) and np.array_equal(mesh.ey.cpu().numpy(), ey)
+        assert np.array_equal(mesh.ez.cpu().numpy(), ez)
+        # red-black reaches the same solution
+        mesh.set_initial_guess(u0)
+        mesh.solve(order=abi.SOR_RED_BLACK, tol=1e-12, max_sweeps=5000)
+        u_rb = mesh.u_pad.cpu().numpy()
+        mesh.set_initial_guess(u0)
+        mesh.solve(order=abi.SOR_LEXICOGRAPHIC, tol=1e-12, max_sweeps=5000)
+        assert np.max(np.abs(u_rb - mesh.u_pad.cpu().numpy())) < 1e-8 * max(1.0, np.abs(u_rb).max())
+    finally:
+        c.close()
+
+
+def test_fused_deposit_and_mesh_field_vs_oracle(torch_mod):
+    """Coupled step: flight kernel gathers the mesh field (EMC_FIELD_MESH) and deposits its
+    end-of-step positions in the same launch; both against the oracle."""
+    torch = torch_mod
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    seg = (24, 1, 16)
+    c = mesh_context(seg, torch)
+    try:
+        g = helpers.golden_params()["phys"]
+        n = 30000
+        coords, v, dtau = hot_ensemble(n, 35, g)
+        rng = np.random.RandomState(9)
+        mesh = engine.Mesh(c)
+        pad = c.padded_shape
+        fld = [np.zeros(pad) for _ in range(3)]
+        for f in fld:
+            f[1:-1, 1:-1, 1:-1] = rng.uniform(-5e6, 5e6, seg)           # V/m
+        mesh.ex.copy_(torch.from_numpy(fld[0])); mesh.ey.copy_(torch.from_numpy(fld[1]))
+        mesh.ez.copy_(torch.from_numpy(fld[2]))
+        o = helpers.make_oracle()
+        o.set_field_mesh(seg, c.params.dl[:], *fld)
+        st = helpers.state_from_coords(coords, v, dtau)
+        ens = engine.Ensemble(c, n).load(coords, v, dtau)
+        for s in range(4):
+            mesh.zero_counts()
+            ens.step(s, 5, field_mode=abi.FIELD_MESH, mesh=mesh, deposit=True)
+            o.timestep(st, orc.philox_stream(5, s, 0), threads=4)
+        co, val, dt_ = ens.coords()
+        compare_states(st, co, val, dt_, np.array(g["tot_dim"]))
+        # fused deposit == standalone deposit of the same positions == oracle on the GPU positions
+        fused = mesh.counts.cpu().numpy().copy()
+        mesh.zero_counts()
+        mesh.deposit(ens)
+        assert np.array_equal(fused, mesh.counts.cpu().numpy())
+        assert np.array_equal(fused, orc.deposit_ngp(co[:, 3], co[:, 4], co[:, 5], np.array(seg),
+                                                     np.array(c.params.dl[:])))
+    finally:
+        c.close()
+
+
+def test_error_paths(ctx, torch_mod):
+    """Bad arguments come back as negative status + message, never a crash."""
+    from monte_carlo_carrier_transport_b200 import abi
+    lib = ctx.lib
+    assert lib.emc_deposit(ctx.h, None, None, None, 10, None, 0, None) == abi.ERR_INVALID
+    assert b"emc_deposit" in lib.emc_last_error(ctx.h)
+    t = torch_mod.zeros(8, dtype=torch_mod.float64, device="cuda")
+    assert lib.emc_deposit(ctx.h, t.data_ptr(), t.data_ptr(), t.data_ptr(), 8, t.data_ptr(), 7, None) == abi.ERR_INVALID
+    bad = np.linspace(0, 2, 100) ** 2
+    with pytest.raises(abi.EmcError) as ei:
+        ek, tabs, mech = helpers.host_tables()
+        ctx.upload_tables(bad, [tb[:100] for tb in tabs], mech)
+    assert ei.value.status == abi.ERR_UNSUPPORTED
+    ctx.upload_tables(*helpers.host_tables())         # restore
+
+
+def test_sor_divergence_is_reported(torch_mod):
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    c = mesh_context((8, 1, 8), torch_mod)
+    try:
+        mesh = engine.Mesh(c)
+        mesh.rho_pad.fill_(1e30)
+        with pytest.raises(abi.EmcError) as ei:
+            mesh.solve(order=abi.SOR_LEXICOGRAPHIC, max_sweeps=50)
+        assert ei.value.status == abi.ERR_DIVERGED
+    finally:
+        c.close()
