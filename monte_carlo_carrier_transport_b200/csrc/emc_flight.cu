@@ -9,10 +9,20 @@ namespace emc {
 // ------------------------------------------------------------------------------------------
 // block-level reduction of the observables
 // ------------------------------------------------------------------------------------------
+// per-lane accumulators: doubles for the sums, 32-bit counters (a lane sees far fewer than 2^32
+// particles per launch); widened to 64 bit in the block reduction
 struct ObsAcc {
-    double d[5];       // sum_z, sum_vz, sum_e, sum_vz2, sum_e2
-    long long c[6];    // n_valley[3], n_fault, n_segments, n_events
+    double d[5];        // sum_z, sum_vz, sum_e, sum_vz2, sum_e2
+    unsigned int c[6];  // n_valley[3], n_fault, n_segments, n_events
 };
+
+__device__ __forceinline__ void obs_zero(ObsAcc &a)
+{
+#pragma unroll
+    for (int k = 0; k < 5; ++k) a.d[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a.c[k] = 0u;
+}
 
 __device__ __forceinline__ void obs_particle(const DevConst &P, ObsAcc &a, double kx, double ky, double kz,
                                              double z, int val)
@@ -27,27 +37,37 @@ __device__ __forceinline__ void obs_particle(const DevConst &P, ObsAcc &a, doubl
     a.d[2] += enp;
     a.d[3] += vz * vz;
     a.d[4] += enp * enp;
-    a.c[val]++;
+    a.c[0] += (val == 0);
+    a.c[1] += (val == 1);
+    a.c[2] += (val == 2);
 }
 
 // Deterministic two-level reduction: warp shuffles, then shared memory, one partial per block;
 // the last block to finish (ticket) folds the partials in a fixed order, so the result does
 // not depend on block scheduling.
-__device__ void obs_block_reduce_and_finish(ObsAcc &a, ObsPartial *partials, unsigned int *ticket, EmcObs *out)
+__device__ void obs_block_reduce_and_finish(const ObsAcc &acc, ObsPartial *partials, unsigned int *ticket, EmcObs *out)
 {
     __shared__ ObsPartial warp_part[32];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    double d[5];
+    long long c[6];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) d[k] = acc.d[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c[k] = (long long)acc.c[k];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) a.d[k] += __shfl_down_sync(0xffffffffu, a.d[k], off);
+        for (int k = 0; k < 5; ++k) d[k] += __shfl_down_sync(0xffffffffu, d[k], off);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a.c[k] += __shfl_down_sync(0xffffffffu, a.c[k], off);
+        for (int k = 0; k < 6; ++k) c[k] += __shfl_down_sync(0xffffffffu, c[k], off);
     }
     if (lane == 0) {
-        for (int k = 0; k < 5; ++k) warp_part[warp].d[k] = a.d[k];
-        for (int k = 0; k < 6; ++k) warp_part[warp].c[k] = a.c[k];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) warp_part[warp].d[k] = d[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) warp_part[warp].c[k] = c[k];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -64,7 +84,7 @@ __device__ void obs_block_reduce_and_finish(ObsAcc &a, ObsPartial *partials, uns
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // fixed-order fold: thread t owns value t (11 values), walks the blocks in index order
+    // fixed-order fold: thread k owns value k (11 values) and walks the blocks in index order
     if (threadIdx.x < 11) {
         const int k = threadIdx.x;
         if (k < 5) {
@@ -74,7 +94,7 @@ __device__ void obs_block_reduce_and_finish(ObsAcc &a, ObsPartial *partials, uns
         } else {
             long long s = 0;
             for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[b].c[k - 5]);
-            out->n_valley[0 + (k - 5)] = s;      // n_valley[3], n_fault, n_segments, n_events are contiguous
+            (&out->n_valley[0])[k - 5] = s;      // n_valley[3], n_fault, n_segments, n_events are contiguous
         }
     }
     if (threadIdx.x == 0) *ticket = 0u;
@@ -98,24 +118,54 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 
 // ------------------------------------------------------------------------------------------
 // the timestep kernel
+//
+// Work decomposition.  Events per particle-timestep are Poisson(Gamma*dt = 0.8): 45 % of the
+// particles need no scatter event, 36 % one, the tail is unbounded.  One thread per particle
+// therefore runs the (fp64-heavy, ~1400 instruction) event body with a third of the lanes
+// active (measured 10/32, profiles/r1a_baseline_flight_ncu.txt).  Instead each WARP owns a
+// contiguous slice of the ensemble and a small queue in shared memory:
+//   refill phase  all 32 lanes load the next 32 particles (fully coalesced 256-B rows per
+//                 state array), do the first flight segment, retire the particles whose free
+//                 flight outlasts the timestep and push the others into the queue, compacted
+//                 with ballot/popc;
+//   event phase   32 lanes pop 32 queued particles, each does ONE scatter event + the flight
+//                 that follows, retires finished particles (store, observables, charge
+//                 deposit) and pushes the still-pending ones back.
+// Both phases run with all lanes active except while the slice drains.  A particle's
+// trajectory depends only on its own state and its own (counter-based) random stream, so the
+// regrouping changes no result.
 // ------------------------------------------------------------------------------------------
+constexpr int QCAP = 64;                     // <= 31 left over + 32 pushed
+struct WarpQueue {
+    double kx[QCAP], ky[QCAP], kz[QCAP], x[QCAP], y[QCAP], z[QCAP], dte[QCAP];
+    int32_t val[QCAP];
+    uint32_t off[QCAP];                      // particle index relative to the warp's slice
+    uint32_t s0[QCAP], s1[QCAP], s2[QCAP];   // random-stream state
+    int32_t grp[QCAP];                       // EMC_FIELD_GROUPS: field group of the particle
+};
+
+struct Particle {
+    double kx, ky, kz, x, y, z, dte;
+    int32_t val;
+    uint32_t off;
+    int32_t grp;
+};
+
 template <int FIELD>
-__device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A, int64_t i, double x, double y,
-                                         double z, double &efx, double &efy, double &efz)
+__device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A, const Particle &p,
+                                         double &efx, double &efy, double &efz)
 {
     if (FIELD == EMC_FIELD_CONSTANT) {
         efx = P.efield[0]; efy = P.efield[1]; efz = P.efield[2];
     } else if (FIELD == EMC_FIELD_GROUPS) {
-        int64_t g = (int64_t)((A.pid_offset + (uint64_t)i) / (uint64_t)P.group_size);
-        if (g >= P.n_groups) g = P.n_groups - 1;
-        efx = __ldg(P.field_groups + 3 * g);
-        efy = __ldg(P.field_groups + 3 * g + 1);
-        efz = __ldg(P.field_groups + 3 * g + 2);
+        efx = __ldg(P.field_groups + 3 * p.grp);
+        efy = __ldg(P.field_groups + 3 * p.grp + 1);
+        efz = __ldg(P.field_groups + 3 * p.grp + 2);
     } else {
         // nearest-cell gather from the padded (nx+2,ny+2,nz+2) field of emc_field, V/m -> V/cm
-        const int ci = axis_cell(x, P.seg[0], P.dl[0]) + 1;
-        const int cj = axis_cell(y, P.seg[1], P.dl[1]) + 1;
-        const int ck = axis_cell(z, P.seg[2], P.dl[2]) + 1;
+        const int ci = axis_cell(p.x, P.seg[0], P.dl[0]) + 1;
+        const int cj = axis_cell(p.y, P.seg[1], P.dl[1]) + 1;
+        const int ck = axis_cell(p.z, P.seg[2], P.dl[2]) + 1;
         const int64_t c = ((int64_t)ci * (P.seg[1] + 2) + cj) * (P.seg[2] + 2) + ck;
         efx = __ldg(A.ex + c) * 1e-2;
         efy = __ldg(A.ey + c) * 1e-2;
@@ -123,51 +173,46 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
     }
 }
 
-// main_.py:360-391 for one particle.  Returns with the state updated; counts segments/events.
-template <class Stream, int FIELD, bool EXACT>
-__device__ __forceinline__ void step_particle(const DevConst &P, const MechMeta &M, const FlightArgs &A, int64_t i,
-                                              double &kx, double &ky, double &kz, double &x, double &y, double &z,
-                                              double &dtau, int &val, Stream &rng, long long &n_seg,
-                                              long long &n_ev)
+// retire a particle: write its state back, add it to the observables and the charge mesh
+template <bool REPLAY>
+__device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, int64_t i, const Particle &p,
+                                       uint32_t cursor, ObsAcc &acc, unsigned int *smesh)
 {
-    if (val < 0) return;                          // frozen after a fault
-    const double dt = P.dt;
-    double dte = dtau;                            // :361
-    double efx, efy, efz;
-    field_at<FIELD>(P, A, i, x, y, z, efx, efy, efz);
-    if (dte >= dt) {                              // :363
-        carrier_drift(P, kx, ky, kz, x, y, z, efx, efy, efz, dt, P.mass[val]);        // :367
-        n_seg++;
-    } else {
-        carrier_drift(P, kx, ky, kz, x, y, z, efx, efy, efz, dte, P.mass[val]);       // :373
-        n_seg++;
-        while (dte < dt) {                        // :375
-            const double dte2 = dte;              // :376
-            int f = scatter_event<EXACT>(P, M, kx, ky, kz, val, rng);                 // :378
-            if (rng.overflow()) f = EMC_FAULT_STREAM;
-            if (f >= 0) { val = -(1 + f); dtau = dte; return; }
-            n_ev++;
-            const double dt3 = P.neg_inv_gamma * log(rng.next());                    // :379
-            if (rng.overflow()) { val = -(1 + EMC_FAULT_STREAM); dtau = dte; return; }
-            const double dtp = dt - dte2;         // :381
-            const double dt2 = (dt3 <= dtp) ? dt3 : dtp;                              // :382-385
-            if (FIELD == EMC_FIELD_MESH) field_at<FIELD>(P, A, i, x, y, z, efx, efy, efz);
-            carrier_drift(P, kx, ky, kz, x, y, z, efx, efy, efz, dt2, P.mass[val]);  // :388
-            n_seg++;
-            dte = dte2 + dt3;                     // :389
-        }
+    A.kx[i] = p.kx; A.ky[i] = p.ky; A.kz[i] = p.kz;
+    A.x[i] = p.x; A.y[i] = p.y; A.z[i] = p.z;
+    A.dtau[i] = p.dte;
+    A.valley[i] = p.val;
+    if (REPLAY) A.cursor[i] = (int32_t)cursor;
+    if (A.obs) obs_particle(P, acc, p.kx, p.ky, p.kz, p.z, p.val);
+    if (A.mesh) {
+        if (A.smem_cells > 0)
+            deposit_ngp_particle(P, p.x, p.y, p.z, [&](int64_t c) { atomicAdd(&smesh[c], 1u); });
+        else
+            deposit_ngp_particle(P, p.x, p.y, p.z, [&](int64_t c) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(A.mesh) + c, 1ull); });
     }
-    dte -= dt;                                    // :390
-    dtau = dte;                                   // :391
+}
+
+__device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particle &p, uint32_t s0, uint32_t s1,
+                                           uint32_t s2)
+{
+    Q.kx[slot] = p.kx; Q.ky[slot] = p.ky; Q.kz[slot] = p.kz;
+    Q.x[slot] = p.x; Q.y[slot] = p.y; Q.z[slot] = p.z;
+    Q.dte[slot] = p.dte;
+    Q.val[slot] = p.val; Q.off[slot] = p.off; Q.grp[slot] = p.grp;
+    Q.s0[slot] = s0; Q.s1[slot] = s1; Q.s2[slot] = s2;
 }
 
 template <class Stream, int FIELD, bool EXACT>
-__global__ void __launch_bounds__(FLIGHT_THREADS)
+__global__ void __launch_bounds__(FLIGHT_THREADS, 2)
 flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg,
                       const __grid_constant__ FlightArgs A)
 {
+    constexpr bool REPLAY = Stream::is_replay;
     __shared__ MechMeta M;
-    extern __shared__ unsigned int smesh[];       // privatised NGP counts (when A.smem_cells > 0)
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    WarpQueue *queues = reinterpret_cast<WarpQueue *>(dyn_smem);
+    unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + sizeof(WarpQueue) * (FLIGHT_THREADS / 32));
     {
         const int nw = sizeof(MechMeta) / 4;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&Mg);
@@ -178,38 +223,119 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     __syncthreads();
 
     ObsAcc acc;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) acc.d[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) acc.c[k] = 0;
+    obs_zero(acc);
 
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += stride) {
-        double kx = A.kx[i], ky = A.ky[i], kz = A.kz[i];
-        double x = A.x[i], y = A.y[i], z = A.z[i];
-        double dtau = A.dtau[i];
-        int val = A.valley[i];
-        Stream rng;
-        if constexpr (Stream::is_replay) rng.init(A.uniforms, A.stride, i, A.cursor[i]);
-        else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step);
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    WarpQueue &Q = queues[warp];
+    const int64_t total_warps = (int64_t)gridDim.x * (FLIGHT_THREADS / 32);
+    const int64_t gw = (int64_t)blockIdx.x * (FLIGHT_THREADS / 32) + warp;
+    const int64_t slice = (((A.n + total_warps - 1) / total_warps) + 31) & ~(int64_t)31;
+    int64_t wstart = gw * slice;
+    if (wstart > A.n) wstart = A.n;
+    const int64_t wend = (wstart + slice < A.n) ? wstart + slice : A.n;
+    int64_t next = wstart;
+    int qn = 0;                                   // queue length (warp-uniform)
+    const double dt = P.dt;
 
-        step_particle<Stream, FIELD, EXACT>(P, M, A, i, kx, ky, kz, x, y, z, dtau, val, rng, acc.c[4], acc.c[5]);
-
-        A.kx[i] = kx; A.ky[i] = ky; A.kz[i] = kz;
-        A.x[i] = x; A.y[i] = y; A.z[i] = z;
-        A.dtau[i] = dtau;
-        A.valley[i] = val;
-        if constexpr (Stream::is_replay) A.cursor[i] = rng.pos;
-
-        if (A.obs) obs_particle(P, acc, kx, ky, kz, z, val);
-        if (A.mesh) {
-            if (A.smem_cells > 0)
-                deposit_ngp_particle(P, x, y, z, [&](int64_t c) { atomicAdd(&smesh[c], 1u); });
-            else
-                deposit_ngp_particle(P, x, y, z, [&](int64_t c) {
-                    atomicAdd(reinterpret_cast<unsigned long long *>(A.mesh) + c, 1ull); });
+    while (true) {
+        if (qn < 32 && next < wend) {
+            // ---- refill phase: main_.py:361-373 for the next 32 particles -------------------
+            const int64_t i = next + lane;
+            next += 32;
+            bool pend = false;
+            Particle p;
+            uint32_t s0 = 0;
+            if (i < wend) {
+                p.kx = A.kx[i]; p.ky = A.ky[i]; p.kz = A.kz[i];
+                p.x = A.x[i]; p.y = A.y[i]; p.z = A.z[i];
+                p.dte = A.dtau[i];
+                p.val = A.valley[i];
+                p.off = (uint32_t)(i - wstart);
+                p.grp = 0;
+                if (REPLAY) s0 = (uint32_t)A.cursor[i];
+                if (p.val >= 0) {
+                    if (FIELD == EMC_FIELD_GROUPS) {
+                        int64_t g = (int64_t)((A.pid_offset + (uint64_t)i) / (uint64_t)P.group_size);
+                        p.grp = (int32_t)(g >= P.n_groups ? P.n_groups - 1 : g);
+                    }
+                    double efx, efy, efz;
+                    field_at<FIELD>(P, A, p, efx, efy, efz);
+                    const double dte = p.dte;                     // :361
+                    if (dte >= dt) {                              // :363
+                        carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt, P.mass[p.val]);   // :367
+                        p.dte = dte - dt;                         // :390-391
+                    } else {
+                        carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dte, P.mass[p.val]);  // :373
+                        pend = true;
+                    }
+                    acc.c[4]++;
+                }
+                if (!pend) retire<REPLAY>(P, A, i, p, s0, acc, smesh);
+            }
+            const unsigned pm = __ballot_sync(FULL, pend);
+            if (pend) queue_push(Q, qn + __popc(pm & lt_mask), p, s0, 0u, 0u);
+            qn += __popc(pm);
+            __syncwarp();
+            continue;
         }
+        if (qn == 0) break;
+        // ---- event phase: one pass of the while-loop body main_.py:375-389 ---------------------
+        const int cnt = qn < 32 ? qn : 32;
+        const bool act = lane < cnt;
+        qn -= cnt;
+        Particle p;
+        uint32_t s0 = 0, s1 = 0, s2 = 0;
+        if (act) {
+            const int slot = qn + lane;
+            p.kx = Q.kx[slot]; p.ky = Q.ky[slot]; p.kz = Q.kz[slot];
+            p.x = Q.x[slot]; p.y = Q.y[slot]; p.z = Q.z[slot];
+            p.dte = Q.dte[slot];
+            p.val = Q.val[slot]; p.off = Q.off[slot]; p.grp = Q.grp[slot];
+            s0 = Q.s0[slot]; s1 = Q.s1[slot]; s2 = Q.s2[slot];
+        }
+        __syncwarp();
+        bool pend = false;
+        if (act) {
+            const int64_t i = wstart + p.off;
+            Stream rng;
+            if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
+            else rng.restore(A.seed, A.pid_offset + (uint64_t)i, A.step, s0, s1, s2);
+            const double dte2 = p.dte;                            // :376
+            int v = p.val;
+            int f = scatter_event<EXACT>(P, M, p.kx, p.ky, p.kz, v, rng);            // :378
+            if (rng.overflow()) f = EMC_FAULT_STREAM;
+            if (f >= 0) {
+                p.val = -(1 + f);                                 // frozen; dtau keeps dte
+            } else {
+                p.val = v;
+                acc.c[5]++;
+                const double dt3 = P.neg_inv_gamma * log(rng.next());                // :379
+                if (rng.overflow()) {
+                    p.val = -(1 + EMC_FAULT_STREAM);
+                } else {
+                    const double dtp = dt - dte2;                 // :381
+                    const double dt2 = (dt3 <= dtp) ? dt3 : dtp;  // :382-385
+                    double efx, efy, efz;
+                    field_at<FIELD>(P, A, p, efx, efy, efz);
+                    carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt2, P.mass[p.val]);     // :388
+                    acc.c[4]++;
+                    const double dte = dte2 + dt3;                // :389
+                    if (dte < dt) { p.dte = dte; pend = true; }   // :375
+                    else p.dte = dte - dt;                        // :390-391
+                }
+            }
+            if constexpr (REPLAY) s0 = (uint32_t)rng.pos;
+            else rng.save(s0, s1, s2);
+            if (!pend) retire<REPLAY>(P, A, i, p, s0, acc, smesh);
+        }
+        const unsigned pm = __ballot_sync(FULL, pend);
+        if (pend) queue_push(Q, qn + __popc(pm & lt_mask), p, s0, s1, s2);
+        qn += __popc(pm);
+        __syncwarp();
     }
+
     if (A.mesh && A.smem_cells > 0) {
         __syncthreads();
         for (int t = threadIdx.x; t < A.smem_cells; t += blockDim.x) {
@@ -223,23 +349,30 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
 template <class Stream, int FIELD>
 static cudaError_t launch_flight_t(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
-    if (ctx->exact_libm)
-        flight_scatter_kernel<Stream, FIELD, true><<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
-    else
-        flight_scatter_kernel<Stream, FIELD, false><<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
+    cudaError_t e;
+    if (ctx->exact_libm) {
+        auto k = flight_scatter_kernel<Stream, FIELD, true>;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
+    } else {
+        auto k = flight_scatter_kernel<Stream, FIELD, false>;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, cudaStream_t st)
 {
+    // one warp needs at least a few refills of work; small ensembles use fewer blocks
     const int64_t blocks_needed = (A.n + FLIGHT_THREADS - 1) / FLIGHT_THREADS;
     int grid = (int)(blocks_needed < (int64_t)ctx->max_grid ? blocks_needed : ctx->max_grid);
     if (grid < 1) grid = 1;
-    size_t smem = 0;
+    size_t smem = sizeof(WarpQueue) * (FLIGHT_THREADS / 32);
     A.smem_cells = 0;
     if (A.mesh) {
         const int64_t cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];
-        if (cells * 4 <= SMEM_MESH_BYTES) { A.smem_cells = (int)cells; smem = (size_t)cells * 4; }
+        if (cells * 4 <= SMEM_MESH_BYTES) { A.smem_cells = (int)cells; smem += (size_t)cells * 4; }
     }
     A.partials = ctx->partials;
     A.ticket = ctx->ticket;
