@@ -50,12 +50,17 @@ static void fill_devconst(Ctx *c)
         d.den[v] = 2 * p.mass[v] * p.q;         // (2*m)*q
         d.four_a[v] = 4 * p.nonparab[v];
         d.two_a[v] = 2 * p.nonparab[v];
-        d.hbar_over_m[v] = p.hbar / p.mass[v];
+        d.r_den[v] = 1 / d.den[v];
+        d.r_two_a[v] = 1 / d.two_a[v];
+        d.r_mass[v] = 1 / p.mass[v];
+        d.inv_dl[v] = 1 / p.dl[v];
         d.tot_dim[v] = p.tot_dim[v];
         d.efield[v] = p.efield[v];
         d.seg[v] = p.seg[v];
         d.dl[v] = p.dl[v];
     }
+    d.r_hbar = 1 / p.hbar;
+    d.r_hbar2 = 1 / d.hbar2;
     d.e_phonon = p.e_phonon;
     d.ion_eb = p.ion_eb;
 }
@@ -148,8 +153,8 @@ extern "C" int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy
                                  const double *dE, const int32_t *trans, const int32_t *sampler)
 {
     CTX_OR_FAIL(ctx);
-    if (!ek || !cum0 || !cum1 || !cum2 || !n_mech || !dE || !trans || !sampler || n_energy < 2)
-        return fail(c, EMC_ERR_INVALID, "emc_upload_tables: null argument or n_energy < 2");
+    if (!ek || !cum0 || !cum1 || !cum2 || !n_mech || !dE || !trans || !sampler || n_energy < 3)
+        return fail(c, EMC_ERR_INVALID, "emc_upload_tables: null argument or n_energy < 3");
     // the kernel regenerates the grid as i*step (np.linspace with start 0): verify that is what we were given
     const double step = ek[1] - ek[0];
     if (!(step > 0) || ek[0] != 0.0) return fail(c, EMC_ERR_UNSUPPORTED, "energy grid must start at 0 and increase");
@@ -182,6 +187,7 @@ extern "C" int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy
     }
     c->dc.n_energy = n_energy;
     c->dc.ek_step = step;
+    c->dc.inv_ek_step = 1 / step;
     c->dc.e_max = ek[n_energy - 1];
     c->have_tables = true;
     return EMC_OK;

@@ -31,7 +31,7 @@ __device__ __forceinline__ void obs_particle(const DevConst &P, ObsAcc &a, doubl
     // main_.py:105,109,394-397
     const double E = energy_parabolic(P, kx, ky, kz, val);
     const double enp = energy_nonparabolic(P, E, val);
-    const double vz = kz * P.hbar / P.mass[val];
+    const double vz = div_const(kz * P.hbar, P.mass[val], P.r_mass[val]);
     a.d[0] += z;
     a.d[1] += vz;
     a.d[2] += enp;
@@ -107,9 +107,9 @@ template <class Add>
 __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x, double y, double z, Add add)
 {
     int hx[3], hy[3], hz[3];
-    const int nx = axis_hits(x, P.seg[0], P.dl[0], hx);
-    const int ny = axis_hits(y, P.seg[1], P.dl[1], hy);
-    const int nz = axis_hits(z, P.seg[2], P.dl[2], hz);
+    const int nx = axis_hits(x, P.seg[0], P.dl[0], P.inv_dl[0], hx);
+    const int ny = axis_hits(y, P.seg[1], P.dl[1], P.inv_dl[1], hy);
+    const int nz = axis_hits(z, P.seg[2], P.dl[2], P.inv_dl[2], hz);
     for (int a = 0; a < nx; ++a)
         for (int b = 0; b < ny; ++b)
             for (int c = 0; c < nz; ++c)
@@ -174,7 +174,7 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
 }
 
 // retire a particle: write its state back, add it to the observables and the charge mesh
-template <bool REPLAY>
+template <bool REPLAY, bool DEPOSIT>
 __device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, int64_t i, const Particle &p,
                                        uint32_t cursor, ObsAcc &acc, unsigned int *smesh)
 {
@@ -184,7 +184,7 @@ __device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, i
     A.valley[i] = p.val;
     if (REPLAY) A.cursor[i] = (int32_t)cursor;
     if (A.obs) obs_particle(P, acc, p.kx, p.ky, p.kz, p.z, p.val);
-    if (A.mesh) {
+    if (DEPOSIT) {
         if (A.smem_cells > 0)
             deposit_ngp_particle(P, p.x, p.y, p.z, [&](int64_t c) { atomicAdd(&smesh[c], 1u); });
         else
@@ -203,7 +203,7 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
     Q.s0[slot] = s0; Q.s1[slot] = s1; Q.s2[slot] = s2;
 }
 
-template <class Stream, int FIELD, bool EXACT>
+template <class Stream, int FIELD, bool EXACT, bool DEPOSIT>
 __global__ void __launch_bounds__(FLIGHT_THREADS, 2)
 flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg,
                       const __grid_constant__ FlightArgs A)
@@ -239,15 +239,30 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     int qn = 0;                                   // queue length (warp-uniform)
     const double dt = P.dt;
 
+    // EMC_FIELD_GROUPS: group index / remainder of the slice's next particle, advanced without
+    // a 64-bit division per particle
+    int64_t grp_next = 0, grp_rem = 0;
+    if (FIELD == EMC_FIELD_GROUPS) {
+        const uint64_t g0 = A.pid_offset + (uint64_t)wstart;
+        grp_next = (int64_t)(g0 / (uint64_t)P.group_size);
+        grp_rem = (int64_t)(g0 % (uint64_t)P.group_size);
+    }
+
+    // The two phases share ONE copy of the flight segment, the retirement and the queue push
+    // (the kernel has to stay inside the 32 KB instruction cache).
     while (true) {
-        if (qn < 32 && next < wend) {
-            // ---- refill phase: main_.py:361-373 for the next 32 particles -------------------
-            const int64_t i = next + lane;
-            next += 32;
-            bool pend = false;
-            Particle p;
-            uint32_t s0 = 0;
-            if (i < wend) {
+        const bool refill = (qn < 32 && next < wend);             // warp-uniform
+        if (!refill && qn == 0) break;
+        Particle p;
+        uint32_t s0 = 0, s1 = 0, s2 = 0;
+        int64_t i = 0;
+        bool act, pend = false, fly = false;
+        double dt_seg = 0.0;
+        if (refill) {
+            // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
+            i = next + lane;
+            act = i < wend;
+            if (act) {
                 p.kx = A.kx[i]; p.ky = A.ky[i]; p.kz = A.kz[i];
                 p.x = A.x[i]; p.y = A.y[i]; p.z = A.z[i];
                 p.dte = A.dtau[i];
@@ -255,88 +270,82 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 p.off = (uint32_t)(i - wstart);
                 p.grp = 0;
                 if (REPLAY) s0 = (uint32_t)A.cursor[i];
-                if (p.val >= 0) {
-                    if (FIELD == EMC_FIELD_GROUPS) {
-                        int64_t g = (int64_t)((A.pid_offset + (uint64_t)i) / (uint64_t)P.group_size);
-                        p.grp = (int32_t)(g >= P.n_groups ? P.n_groups - 1 : g);
-                    }
-                    double efx, efy, efz;
-                    field_at<FIELD>(P, A, p, efx, efy, efz);
+                if (FIELD == EMC_FIELD_GROUPS) {
+                    int64_t g = grp_next, r = grp_rem + lane;
+                    while (r >= P.group_size) { r -= P.group_size; ++g; }
+                    p.grp = (int32_t)(g >= P.n_groups ? P.n_groups - 1 : g);
+                }
+                if (p.val >= 0) {                                 // else frozen after a fault
                     const double dte = p.dte;                     // :361
-                    if (dte >= dt) {                              // :363
-                        carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt, P.mass[p.val]);   // :367
-                        p.dte = dte - dt;                         // :390-391
-                    } else {
-                        carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dte, P.mass[p.val]);  // :373
-                        pend = true;
-                    }
-                    acc.c[4]++;
+                    fly = true;
+                    if (dte >= dt) { dt_seg = dt; p.dte = dte - dt; }      // :363-367, :390-391
+                    else { dt_seg = dte; pend = true; }           // :370-373
                 }
-                if (!pend) retire<REPLAY>(P, A, i, p, s0, acc, smesh);
             }
-            const unsigned pm = __ballot_sync(FULL, pend);
-            if (pend) queue_push(Q, qn + __popc(pm & lt_mask), p, s0, 0u, 0u);
-            qn += __popc(pm);
+            next += 32;
+            if (FIELD == EMC_FIELD_GROUPS) {
+                grp_rem += 32;
+                while (grp_rem >= P.group_size) { grp_rem -= P.group_size; ++grp_next; }
+            }
+        } else {
+            // ---- event phase: one pass of the while-loop body main_.py:375-389 -------------------
+            const int cnt = qn < 32 ? qn : 32;
+            act = lane < cnt;
+            qn -= cnt;
+            if (act) {
+                const int slot = qn + lane;
+                p.kx = Q.kx[slot]; p.ky = Q.ky[slot]; p.kz = Q.kz[slot];
+                p.x = Q.x[slot]; p.y = Q.y[slot]; p.z = Q.z[slot];
+                p.dte = Q.dte[slot];
+                p.val = Q.val[slot]; p.off = Q.off[slot]; p.grp = Q.grp[slot];
+                s0 = Q.s0[slot]; s1 = Q.s1[slot]; s2 = Q.s2[slot];
+            }
             __syncwarp();
-            continue;
-        }
-        if (qn == 0) break;
-        // ---- event phase: one pass of the while-loop body main_.py:375-389 ---------------------
-        const int cnt = qn < 32 ? qn : 32;
-        const bool act = lane < cnt;
-        qn -= cnt;
-        Particle p;
-        uint32_t s0 = 0, s1 = 0, s2 = 0;
-        if (act) {
-            const int slot = qn + lane;
-            p.kx = Q.kx[slot]; p.ky = Q.ky[slot]; p.kz = Q.kz[slot];
-            p.x = Q.x[slot]; p.y = Q.y[slot]; p.z = Q.z[slot];
-            p.dte = Q.dte[slot];
-            p.val = Q.val[slot]; p.off = Q.off[slot]; p.grp = Q.grp[slot];
-            s0 = Q.s0[slot]; s1 = Q.s1[slot]; s2 = Q.s2[slot];
-        }
-        __syncwarp();
-        bool pend = false;
-        if (act) {
-            const int64_t i = wstart + p.off;
-            Stream rng;
-            if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
-            else rng.restore(A.seed, A.pid_offset + (uint64_t)i, A.step, s0, s1, s2);
-            const double dte2 = p.dte;                            // :376
-            int v = p.val;
-            int f = scatter_event<EXACT>(P, M, p.kx, p.ky, p.kz, v, rng);            // :378
-            if (rng.overflow()) f = EMC_FAULT_STREAM;
-            if (f >= 0) {
-                p.val = -(1 + f);                                 // frozen; dtau keeps dte
-            } else {
-                p.val = v;
-                acc.c[5]++;
-                const double dt3 = P.neg_inv_gamma * log(rng.next());                // :379
-                if (rng.overflow()) {
-                    p.val = -(1 + EMC_FAULT_STREAM);
+            if (act) {
+                i = wstart + p.off;
+                Stream rng;
+                if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
+                else rng.restore(A.seed, A.pid_offset + (uint64_t)i, A.step, s0, s1, s2);
+                const double dte2 = p.dte;                        // :376
+                int v = p.val;
+                int f = scatter_event<EXACT>(P, M, p.kx, p.ky, p.kz, v, rng);        // :378
+                if (rng.overflow()) f = EMC_FAULT_STREAM;
+                if (f >= 0) {
+                    p.val = -(1 + f);                             // frozen; dtau keeps dte
                 } else {
-                    const double dtp = dt - dte2;                 // :381
-                    const double dt2 = (dt3 <= dtp) ? dt3 : dtp;  // :382-385
-                    double efx, efy, efz;
-                    field_at<FIELD>(P, A, p, efx, efy, efz);
-                    carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt2, P.mass[p.val]);     // :388
-                    acc.c[4]++;
-                    const double dte = dte2 + dt3;                // :389
-                    if (dte < dt) { p.dte = dte; pend = true; }   // :375
-                    else p.dte = dte - dt;                        // :390-391
+                    p.val = v;
+                    acc.c[5]++;
+                    const double dt3 = P.neg_inv_gamma * log(rng.next());            // :379
+                    if (rng.overflow()) {
+                        p.val = -(1 + EMC_FAULT_STREAM);
+                    } else {
+                        const double dtp = dt - dte2;             // :381
+                        dt_seg = (dt3 <= dtp) ? dt3 : dtp;        // :382-385
+                        fly = true;
+                        const double dte = dte2 + dt3;            // :389
+                        if (dte < dt) { p.dte = dte; pend = true; }        // :375
+                        else p.dte = dte - dt;                    // :390-391
+                    }
                 }
+                if constexpr (REPLAY) s0 = (uint32_t)rng.pos;
+                else rng.save(s0, s1, s2);
             }
-            if constexpr (REPLAY) s0 = (uint32_t)rng.pos;
-            else rng.save(s0, s1, s2);
-            if (!pend) retire<REPLAY>(P, A, i, p, s0, acc, smesh);
         }
+        if (fly) {                                                // :367 / :373 / :388
+            double efx, efy, efz;
+            field_at<FIELD>(P, A, p, efx, efy, efz);
+            const double dtm = div_const(dt_seg, P.mass[p.val], P.r_mass[p.val]);
+            carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
+            acc.c[4]++;
+        }
+        if (act && !pend) retire<REPLAY, DEPOSIT>(P, A, i, p, s0, acc, smesh);
         const unsigned pm = __ballot_sync(FULL, pend);
         if (pend) queue_push(Q, qn + __popc(pm & lt_mask), p, s0, s1, s2);
         qn += __popc(pm);
         __syncwarp();
     }
 
-    if (A.mesh && A.smem_cells > 0) {
+    if (DEPOSIT && A.smem_cells > 0) {
         __syncthreads();
         for (int t = threadIdx.x; t < A.smem_cells; t += blockDim.x) {
             const unsigned int v = smesh[t];
@@ -346,20 +355,24 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     if (A.obs) obs_block_reduce_and_finish(acc, A.partials, A.ticket, A.obs);
 }
 
+template <class Stream, int FIELD, bool EXACT, bool DEPOSIT>
+static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
+{
+    auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
+    return cudaGetLastError();
+}
+
 template <class Stream, int FIELD>
 static cudaError_t launch_flight_t(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
-    cudaError_t e;
-    if (ctx->exact_libm) {
-        auto k = flight_scatter_kernel<Stream, FIELD, true>;
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
-    } else {
-        auto k = flight_scatter_kernel<Stream, FIELD, false>;
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
-    }
-    return cudaGetLastError();
+    if (ctx->exact_libm)
+        return A.mesh ? launch_flight_k<Stream, FIELD, true, true>(ctx, A, grid, smem, st)
+                      : launch_flight_k<Stream, FIELD, true, false>(ctx, A, grid, smem, st);
+    return A.mesh ? launch_flight_k<Stream, FIELD, false, true>(ctx, A, grid, smem, st)
+                  : launch_flight_k<Stream, FIELD, false, false>(ctx, A, grid, smem, st);
 }
 
 cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, cudaStream_t st)
@@ -513,7 +526,7 @@ __global__ void carrier_drift_kernel(const __grid_constant__ DevConst P, double 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double a = kx[i], b = ky[i], c = kz[i], px = x[i], py = y[i], pz = z[i];
-    carrier_drift(P, a, b, c, px, py, pz, ef3[3 * i], ef3[3 * i + 1], ef3[3 * i + 2], dt2[i], mass[i]);
+    carrier_drift(P, a, b, c, px, py, pz, ef3[3 * i], ef3[3 * i + 1], ef3[3 * i + 2], dt2[i], dt2[i] / mass[i]);
     kx[i] = a; ky[i] = b; kz[i] = c;
     x[i] = px; y[i] = py; z[i] = pz;
 }

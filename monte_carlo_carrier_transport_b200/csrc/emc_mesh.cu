@@ -40,9 +40,9 @@ deposit_ngp_kernel(const __grid_constant__ DevConst P, const double *__restrict_
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int hx[3], hy[3], hz[3];
-        const int nx = axis_hits(x[i], P.seg[0], P.dl[0], hx);
-        const int ny = axis_hits(y[i], P.seg[1], P.dl[1], hy);
-        const int nz = axis_hits(z[i], P.seg[2], P.dl[2], hz);
+        const int nx = axis_hits(x[i], P.seg[0], P.dl[0], P.inv_dl[0], hx);
+        const int ny = axis_hits(y[i], P.seg[1], P.dl[1], P.inv_dl[1], hy);
+        const int nz = axis_hits(z[i], P.seg[2], P.dl[2], P.inv_dl[2], hz);
         for (int a = 0; a < nx; ++a)
             for (int b = 0; b < ny; ++b)
                 for (int c = 0; c < nz; ++c) {
