@@ -22,7 +22,7 @@ ERR_INVALID, ERR_CUDA, ERR_NO_TABLES, ERR_DIVERGED, ERR_UNSUPPORTED = -1, -2, -3
 FAULT_NAMES = ["nan", "zero_energy", "no_mechanism", "domain", "negative_energy", "zero_k", "stream"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libemc_b200.so")
+LIB_PATH = os.environ.get("EMC_LIB") or os.path.join(_HERE, "libemc_b200.so")   # EMC_LIB: tuning variants
 
 
 class EmcParams(C.Structure):

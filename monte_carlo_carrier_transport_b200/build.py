@@ -43,14 +43,16 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("EMC_NVCC_EXTRA", "").split()        # tuning variants, e.g. -DEMC_FLIGHT_MIN_BLOCKS=3
+    out = os.environ.get("EMC_LIB_OUT") or LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-8000:]))
     if verbose:
         print(r.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

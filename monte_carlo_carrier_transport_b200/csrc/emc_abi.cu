@@ -101,7 +101,9 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) goto fail_cuda_create;
     c->sm_count = prop.multiProcessorCount;
     {
-        int per_sm = 4;
+        int per_sm = 8;
+        const char *wv = std::getenv("EMC_WAVES");
+        if (wv && std::atoi(wv) > 0) c->waves = std::atoi(wv);
         const char *env = std::getenv("EMC_BLOCKS_PER_SM");
         if (env && std::atoi(env) > 0) per_sm = std::atoi(env);
         c->max_grid = c->sm_count * per_sm;
@@ -170,11 +172,25 @@ extern "C" int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy
                 return fail(c, EMC_ERR_INVALID, "mechanism metadata out of range");
         }
     }
+    // fast mechanism selection needs even-length (16-B aligned) rows of <= 12 columns that are
+    // non-decreasing and NaN-free (choose_mech in emc_device.cuh); anything else is scanned literally
+    int literal = 0;
+    for (int v = 0; v < 3 && !literal; ++v) {
+        if ((n_mech[v] & 1) || n_mech[v] > 12) literal = 1;
+        for (int64_t i = 0; i < n_energy && !literal; ++i) {
+            const double *row = cum[v] + i * n_mech[v];
+            for (int j = 0; j < n_mech[v]; ++j)
+                if (std::isnan(row[j]) || (j > 0 && row[j] < row[j - 1])) { literal = 1; break; }
+        }
+    }
+    c->dc.literal_scan = literal;
     for (int v = 0; v < 3; ++v) {
         const size_t bytes = sizeof(double) * (size_t)n_energy * (size_t)n_mech[v];
         if (c->d_cum[v]) { cudaFree(c->d_cum[v]); c->d_cum[v] = nullptr; }
-        cudaError_t e = cudaMalloc(&c->d_cum[v], bytes);
+        cudaError_t e = cudaMalloc(&c->d_cum[v], bytes + sizeof(double) * EMC_MAX_MECH);   // + one padding row
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(table)");
+        e = cudaMemset(c->d_cum[v], 0, bytes + sizeof(double) * EMC_MAX_MECH);
+        if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemset(table)");
         e = cudaMemcpy(c->d_cum[v], cum[v], bytes, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(table)");
         c->dc.cum[v] = c->d_cum[v];

@@ -135,12 +135,15 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 // trajectory depends only on its own state and its own (counter-based) random stream, so the
 // regrouping changes no result.
 // ------------------------------------------------------------------------------------------
+#ifndef EMC_FLIGHT_MIN_BLOCKS
+#define EMC_FLIGHT_MIN_BLOCKS 2      // resident 256-thread blocks per SM the register allocator must allow
+#endif
 constexpr int QCAP = 64;                     // <= 31 left over + 32 pushed
 struct WarpQueue {
     double kx[QCAP], ky[QCAP], kz[QCAP], x[QCAP], y[QCAP], z[QCAP], dte[QCAP];
     int32_t val[QCAP];
     uint32_t off[QCAP];                      // particle index relative to the warp's slice
-    uint32_t s0[QCAP], s1[QCAP], s2[QCAP];   // random-stream state
+    uint32_t s0[QCAP];                       // random-stream state: Philox event counter / replay cursor
     int32_t grp[QCAP];                       // EMC_FIELD_GROUPS: field group of the particle
 };
 
@@ -193,18 +196,17 @@ __device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, i
     }
 }
 
-__device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particle &p, uint32_t s0, uint32_t s1,
-                                           uint32_t s2)
+__device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particle &p, uint32_t s0)
 {
     Q.kx[slot] = p.kx; Q.ky[slot] = p.ky; Q.kz[slot] = p.kz;
     Q.x[slot] = p.x; Q.y[slot] = p.y; Q.z[slot] = p.z;
     Q.dte[slot] = p.dte;
     Q.val[slot] = p.val; Q.off[slot] = p.off; Q.grp[slot] = p.grp;
-    Q.s0[slot] = s0; Q.s1[slot] = s1; Q.s2[slot] = s2;
+    Q.s0[slot] = s0;
 }
 
 template <class Stream, int FIELD, bool EXACT, bool DEPOSIT>
-__global__ void __launch_bounds__(FLIGHT_THREADS, 2)
+__global__ void __launch_bounds__(FLIGHT_THREADS, EMC_FLIGHT_MIN_BLOCKS)
 flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg,
                       const __grid_constant__ FlightArgs A)
 {
@@ -254,7 +256,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         const bool refill = (qn < 32 && next < wend);             // warp-uniform
         if (!refill && qn == 0) break;
         Particle p;
-        uint32_t s0 = 0, s1 = 0, s2 = 0;
+        uint32_t s0 = 0;
         int64_t i = 0;
         bool act, pend = false, fly = false;
         double dt_seg = 0.0;
@@ -298,14 +300,14 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 p.x = Q.x[slot]; p.y = Q.y[slot]; p.z = Q.z[slot];
                 p.dte = Q.dte[slot];
                 p.val = Q.val[slot]; p.off = Q.off[slot]; p.grp = Q.grp[slot];
-                s0 = Q.s0[slot]; s1 = Q.s1[slot]; s2 = Q.s2[slot];
+                s0 = Q.s0[slot];
             }
             __syncwarp();
             if (act) {
                 i = wstart + p.off;
                 Stream rng;
                 if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
-                else rng.restore(A.seed, A.pid_offset + (uint64_t)i, A.step, s0, s1, s2);
+                else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
                 const double dte2 = p.dte;                        // :376
                 int v = p.val;
                 int f = scatter_event<EXACT>(P, M, p.kx, p.ky, p.kz, v, rng);        // :378
@@ -315,7 +317,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 } else {
                     p.val = v;
                     acc.c[5]++;
-                    const double dt3 = P.neg_inv_gamma * log(rng.next());            // :379
+                    const double dt3 = P.neg_inv_gamma * log(rng.free_flight());     // :379
                     if (rng.overflow()) {
                         p.val = -(1 + EMC_FAULT_STREAM);
                     } else {
@@ -327,8 +329,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                         else p.dte = dte - dt;                    // :390-391
                     }
                 }
-                if constexpr (REPLAY) s0 = (uint32_t)rng.pos;
-                else rng.save(s0, s1, s2);
+                rng.end_event();
+                s0 = rng.state();
             }
         }
         if (fly) {                                                // :367 / :373 / :388
@@ -340,7 +342,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         }
         if (act && !pend) retire<REPLAY, DEPOSIT>(P, A, i, p, s0, acc, smesh);
         const unsigned pm = __ballot_sync(FULL, pend);
-        if (pend) queue_push(Q, qn + __popc(pm & lt_mask), p, s0, s1, s2);
+        if (pend) queue_push(Q, qn + __popc(pm & lt_mask), p, s0);
         qn += __popc(pm);
         __syncwarp();
     }
@@ -361,6 +363,13 @@ static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid
     auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // persistent grid: exactly the blocks that are resident at once (one wave), unless the
+    // ensemble is too small to give every block a full tile
+    int per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FLIGHT_THREADS, smem)) != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int resident = ctx->sm_count * per_sm * ctx->waves;
+    if (grid > resident) grid = resident;
     k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
     return cudaGetLastError();
 }

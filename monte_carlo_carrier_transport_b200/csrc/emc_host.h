@@ -41,7 +41,8 @@ struct Ctx {
     MechMeta mech;
     int device = 0;
     int sm_count = 0;
-    int max_grid = 0;             // persistent grid: sm_count * resident blocks
+    int max_grid = 0;             // upper bound of any persistent grid (partials capacity)
+    int waves = 1;                // flight kernel: grid = resident blocks * waves (EMC_WAVES)
     bool have_tables = false;
     bool exact_libm = false;      // EMC_EXACT_LIBM=1: compose acos/asin/atan exactly like the reference
     double *d_cum[3] = {nullptr, nullptr, nullptr};

@@ -235,6 +235,9 @@ static int scatter_stream(const OrcParams *p, double coord[6], int32_t *val, Cur
     double e_np; int32_t idx;
     int f = orc_calc_energy(p, coord, *val, &e_np, &idx);
     if (f >= 0) return f;
+    /* Philox layout: every event starts on draw index 4e of the (particle, timestep) stream, so
+       that block 2e = (r2, azimuth) and block 2e+1 = (polar, flight) or (flight, unused) */
+    if (c->s->mode == 1) c->draw = (c->draw + 3u) & ~3u;
     double r2 = next_uniform(c);
     int mech = choose_mech(p, *val, idx, r2);
     if (mech < 0) return ORC_FAULT_NO_MECH;
