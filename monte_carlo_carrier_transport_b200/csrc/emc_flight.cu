@@ -123,28 +123,37 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 // particles need no scatter event, 36 % one, the tail is unbounded.  One thread per particle
 // therefore runs the (fp64-heavy, ~1400 instruction) event body with a third of the lanes
 // active (measured 10/32, profiles/r1a_baseline_flight_ncu.txt).  Instead each WARP owns a
-// contiguous slice of the ensemble and a small queue in shared memory:
-//   refill phase  all 32 lanes load the next 32 particles (fully coalesced 256-B rows per
-//                 state array), do the first flight segment, retire the particles whose free
-//                 flight outlasts the timestep and push the others into the queue, compacted
-//                 with ballot/popc;
-//   event phase   32 lanes pop 32 queued particles, each does ONE scatter event + the flight
-//                 that follows, retires finished particles (store, observables, charge
-//                 deposit) and pushes the still-pending ones back.
-// Both phases run with all lanes active except while the slice drains.  A particle's
-// trajectory depends only on its own state and its own (counter-based) random stream, so the
-// regrouping changes no result.
+// contiguous slice of the ensemble and two small queues in shared memory, and every pass of its
+// loop runs ONE of three phases with (nearly) all 32 lanes busy:
+//   refill   load the next 32 particles (fully coalesced 256-B rows per state array), fly the
+//            first segment, retire the particles whose free flight outlasts the timestep and
+//            push the others into the EVENT queue, compacted with ballot/popc;
+//   select   pop 32 particles from the event queue; energy, table row, mechanism choice.
+//            Self-scattering (70-85 % of events) is finished on the spot with the short
+//            closed form (scatter_self); particles that drew a REAL mechanism are parked in the
+//            SCATTER queue with their mechanism, energy and azimuth uniform;
+//   scatter  pop 32 particles from the scatter queue: polar-angle sampler, sincos, rotation.
+// select and scatter share the tail (free-flight draw, flight segment, retirement or push
+// back).  So the divergent branches -- event count, self vs. real mechanism -- are turned into
+// queue traffic instead of idle lanes.  A particle's trajectory depends only on its own state
+// and its own (counter-based) random stream, so the regrouping changes no result.
 // ------------------------------------------------------------------------------------------
 #ifndef EMC_FLIGHT_MIN_BLOCKS
 #define EMC_FLIGHT_MIN_BLOCKS 2      // resident 256-thread blocks per SM the register allocator must allow
 #endif
-constexpr int QCAP = 64;                     // <= 31 left over + 32 pushed
+constexpr int QCAP = 64;                     // a phase runs only if its pushes fit: <= 32 + 32
 struct WarpQueue {
     double kx[QCAP], ky[QCAP], kz[QCAP], x[QCAP], y[QCAP], z[QCAP], dte[QCAP];
     int32_t val[QCAP];
     uint32_t off[QCAP];                      // particle index relative to the warp's slice
     uint32_t s0[QCAP];                       // random-stream state: Philox event counter / replay cursor
     int32_t grp[QCAP];                       // EMC_FIELD_GROUPS: field group of the particle
+};
+struct WarpQueues {
+    WarpQueue ev;                            // particles waiting for their next event
+    WarpQueue sc;                            // mid-event particles that drew a real mechanism ...
+    double sc_enp[QCAP], sc_raz[QCAP];       // ... with E_np (scatter_.py:1069) and the azimuth uniform
+    int32_t sc_mech[QCAP];
 };
 
 struct Particle {
@@ -213,8 +222,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     constexpr bool REPLAY = Stream::is_replay;
     __shared__ MechMeta M;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    WarpQueue *queues = reinterpret_cast<WarpQueue *>(dyn_smem);
-    unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + sizeof(WarpQueue) * (FLIGHT_THREADS / 32));
+    WarpQueues *queues = reinterpret_cast<WarpQueues *>(dyn_smem);
+    unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + sizeof(WarpQueues) * (FLIGHT_THREADS / 32));
     {
         const int nw = sizeof(MechMeta) / 4;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&Mg);
@@ -230,7 +239,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    WarpQueue &Q = queues[warp];
+    WarpQueues &WQ = queues[warp];
     const int64_t total_warps = (int64_t)gridDim.x * (FLIGHT_THREADS / 32);
     const int64_t gw = (int64_t)blockIdx.x * (FLIGHT_THREADS / 32) + warp;
     const int64_t slice = (((A.n + total_warps - 1) / total_warps) + 31) & ~(int64_t)31;
@@ -238,7 +247,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     if (wstart > A.n) wstart = A.n;
     const int64_t wend = (wstart + slice < A.n) ? wstart + slice : A.n;
     int64_t next = wstart;
-    int qn = 0;                                   // queue length (warp-uniform)
+    int qn = 0, qsc = 0;                          // lengths of the event / scatter queues (warp-uniform)
     const double dt = P.dt;
 
     // EMC_FIELD_GROUPS: group index / remainder of the slice's next particle, advanced without
@@ -250,17 +259,31 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         grp_rem = (int64_t)(g0 % (uint64_t)P.group_size);
     }
 
-    // The two phases share ONE copy of the flight segment, the retirement and the queue push
-    // (the kernel has to stay inside the 32 KB instruction cache).
+    // The phases share ONE copy of the event tail, the flight segment, the retirement and the
+    // queue pushes (the kernel has to stay inside the 32 KB instruction cache).
+    enum { PH_REFILL = 0, PH_SELECT = 1, PH_SCATTER = 2 };
     while (true) {
-        const bool refill = (qn < 32 && next < wend);             // warp-uniform
-        if (!refill && qn == 0) break;
+        // warp-uniform phase choice: a full scatter or select pass if one is possible, else
+        // refill, else drain whatever is left.  A pass pops only what its pushes can hold.
+        const int room_ev = QCAP - qn, room_sc = QCAP - qsc;
+        const int n_sc = min(32, min(qsc, room_ev));              // scatter pushes back into ev
+        const int n_sel = min(32, min(qn, room_sc));              // select may push all into sc
+        int phase;
+        if (n_sc == 32) phase = PH_SCATTER;
+        else if (n_sel == 32) phase = PH_SELECT;
+        else if (qn < 32 && next < wend) phase = PH_REFILL;
+        else if (n_sel > 0 && n_sel >= n_sc) phase = PH_SELECT;
+        else if (n_sc > 0) phase = PH_SCATTER;
+        else break;
         Particle p;
+        Stream rng;
         uint32_t s0 = 0;
         int64_t i = 0;
-        bool act, pend = false, fly = false;
+        int mech = 0;
+        double e_np = 0.0, r_az = 0.0;
+        bool act, pend = false, fly = false, park = false, tail = false;
         double dt_seg = 0.0;
-        if (refill) {
+        if (phase == PH_REFILL) {
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
             i = next + lane;
             act = i < wend;
@@ -290,47 +313,70 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 while (grp_rem >= P.group_size) { grp_rem -= P.group_size; ++grp_next; }
             }
         } else {
-            // ---- event phase: one pass of the while-loop body main_.py:375-389 -------------------
-            const int cnt = qn < 32 ? qn : 32;
+            // ---- an event, main_.py:375-389 / scatter_.py:986-1099, in one or two passes ---------
+            const bool sel = (phase == PH_SELECT);
+            WarpQueue &Qp = sel ? WQ.ev : WQ.sc;
+            const int cnt = sel ? n_sel : n_sc;
+            int &qlen = sel ? qn : qsc;
             act = lane < cnt;
-            qn -= cnt;
+            qlen -= cnt;
             if (act) {
-                const int slot = qn + lane;
-                p.kx = Q.kx[slot]; p.ky = Q.ky[slot]; p.kz = Q.kz[slot];
-                p.x = Q.x[slot]; p.y = Q.y[slot]; p.z = Q.z[slot];
-                p.dte = Q.dte[slot];
-                p.val = Q.val[slot]; p.off = Q.off[slot]; p.grp = Q.grp[slot];
-                s0 = Q.s0[slot];
+                const int slot = qlen + lane;
+                p.kx = Qp.kx[slot]; p.ky = Qp.ky[slot]; p.kz = Qp.kz[slot];
+                p.x = Qp.x[slot]; p.y = Qp.y[slot]; p.z = Qp.z[slot];
+                p.dte = Qp.dte[slot];
+                p.val = Qp.val[slot]; p.off = Qp.off[slot]; p.grp = Qp.grp[slot];
+                s0 = Qp.s0[slot];
+                if (!sel) { mech = WQ.sc_mech[slot]; e_np = WQ.sc_enp[slot]; r_az = WQ.sc_raz[slot]; }
             }
             __syncwarp();
             if (act) {
                 i = wstart + p.off;
-                Stream rng;
                 if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
                 else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
-                const double dte2 = p.dte;                        // :376
-                int v = p.val;
-                int f = scatter_event<EXACT>(P, M, p.kx, p.ky, p.kz, v, rng);        // :378
-                if (rng.overflow()) f = EMC_FAULT_STREAM;
-                if (f >= 0) {
-                    p.val = -(1 + f);                             // frozen; dtau keeps dte
-                } else {
-                    p.val = v;
-                    acc.c[5]++;
-                    const double dt3 = P.neg_inv_gamma * log(rng.free_flight());     // :379
-                    if (rng.overflow()) {
-                        p.val = -(1 + EMC_FAULT_STREAM);
-                    } else {
-                        const double dtp = dt - dte2;             // :381
-                        dt_seg = (dt3 <= dtp) ? dt3 : dtp;        // :382-385
-                        fly = true;
-                        const double dte = dte2 + dt3;            // :389
-                        if (dte < dt) { p.dte = dte; pend = true; }        // :375
-                        else p.dte = dte - dt;                    // :390-391
+                int v = p.val, f;
+                if (sel) {
+                    // select pass: energy, table row, r2 / azimuth uniforms, mechanism (:1092, :1029-1034)
+                    f = event_select(P, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech);
+                    if (f < 0) {
+                        if (M.sampler[v][mech] == EMC_SAMPLER_SELF) {
+                            rng.draw_polar(false);                // no polar draw (:889); fetches the flight uniform
+                            f = scatter_self<EXACT>(P, M, p.kx, p.ky, p.kz, v, mech, e_np);
+                            tail = true;
+                        } else {
+                            park = true;                          // real mechanism: finish in a scatter pass
+                            s0 = rng.state();
+                        }
                     }
+                } else {
+                    // scatter pass: polar sampler, rotation (:1059-1089)
+                    const double r_pol = rng.draw_polar(true);
+                    f = scatter_core<EXACT>(P, M, p.kx, p.ky, p.kz, v, mech, e_np, r_az, r_pol);
+                    tail = true;
+                }
+                if (rng.overflow()) { f = EMC_FAULT_STREAM; park = false; }
+                if (f >= 0) { p.val = -(1 + f); tail = false; }  // frozen; dtau keeps dte
+                else p.val = v;
+            }
+            if (tail) {
+                // the event happened: draw the next free flight and fly (main_.py:379-389)
+                acc.c[5]++;
+                const double dte2 = p.dte;                        // :376
+                const double dt3 = P.neg_inv_gamma * log(rng.free_flight());         // :379
+                if (rng.overflow()) {
+                    p.val = -(1 + EMC_FAULT_STREAM);
+                } else {
+                    const double dtp = dt - dte2;                 // :381
+                    dt_seg = (dt3 <= dtp) ? dt3 : dtp;            // :382-385
+                    fly = true;
+                    const double dte = dte2 + dt3;                // :389
+                    if (dte < dt) { p.dte = dte; pend = true; }   // :375
+                    else p.dte = dte - dt;                        // :390-391
                 }
                 rng.end_event();
                 s0 = rng.state();
+            } else if (act && !park && REPLAY) {
+                s0 = rng.state();                                 // faulted: cursor as far as it was read
             }
         }
         if (fly) {                                                // :367 / :373 / :388
@@ -340,10 +386,19 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             acc.c[4]++;
         }
-        if (act && !pend) retire<REPLAY, DEPOSIT>(P, A, i, p, s0, acc, smesh);
+        if (act && !pend && !park) retire<REPLAY, DEPOSIT>(P, A, i, p, s0, acc, smesh);
         const unsigned pm = __ballot_sync(FULL, pend);
-        if (pend) queue_push(Q, qn + __popc(pm & lt_mask), p, s0);
+        if (pend) queue_push(WQ.ev, qn + __popc(pm & lt_mask), p, s0);
         qn += __popc(pm);
+        if (phase == PH_SELECT) {
+            const unsigned km = __ballot_sync(FULL, park);
+            if (park) {
+                const int slot = qsc + __popc(km & lt_mask);
+                queue_push(WQ.sc, slot, p, s0);
+                WQ.sc_mech[slot] = mech; WQ.sc_enp[slot] = e_np; WQ.sc_raz[slot] = r_az;
+            }
+            qsc += __popc(km);
+        }
         __syncwarp();
     }
 
@@ -390,7 +445,7 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     const int64_t blocks_needed = (A.n + FLIGHT_THREADS - 1) / FLIGHT_THREADS;
     int grid = (int)(blocks_needed < (int64_t)ctx->max_grid ? blocks_needed : ctx->max_grid);
     if (grid < 1) grid = 1;
-    size_t smem = sizeof(WarpQueue) * (FLIGHT_THREADS / 32);
+    size_t smem = sizeof(WarpQueues) * (FLIGHT_THREADS / 32);
     A.smem_cells = 0;
     if (A.mesh) {
         const int64_t cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];
