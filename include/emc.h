@@ -218,10 +218,14 @@ int emc_mesh_to_rho(EmcCtx *ctx, const int64_t *mesh, int32_t scheme, double *rh
  * (poisson_.py:47-52) and receives the solution.  Iterates until RMS(update) <= tol or
  * max_sweeps.  sweeps_out / err_out (HOST, may be NULL) receive the sweep count and the
  * last RMS update; err_hist (HOST, max_sweeps doubles, may be NULL) the whole history.
- * Synchronises the stream. */
+ * Synchronises the stream -- unless all three output pointers are NULL: then the solve is
+ * only enqueued (the time loop does not need the counts) and emc_poisson_last reports later. */
 int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad, double omega0, double tol,
                     int32_t max_sweeps, int32_t order, int32_t *sweeps_out, double *err_out,
                     double *err_hist, void *stream);
+/* sweep count / last RMS update / divergence (EMC_ERR_DIVERGED) of the most recent
+ * emc_poisson_sor on this context; synchronises the stream */
+int emc_poisson_last(EmcCtx *ctx, int32_t *sweeps_out, double *err_out, void *stream);
 /* E = -central difference on interior cells (poisson_.py:88-96); padded outputs, V/m */
 int emc_field(EmcCtx *ctx, const double *u_pad, double *ex, double *ey, double *ez, void *stream);
 

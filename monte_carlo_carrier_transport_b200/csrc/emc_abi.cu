@@ -418,6 +418,12 @@ extern "C" int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad
                            (cudaStream_t)stream);
 }
 
+extern "C" int emc_poisson_last(EmcCtx *ctx, int32_t *sweeps_out, double *err_out, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    return poisson_last(c, sweeps_out, err_out, (cudaStream_t)stream);
+}
+
 extern "C" int emc_field(EmcCtx *ctx, const double *u_pad, double *ex, double *ey, double *ez, void *stream)
 {
     CTX_OR_FAIL(ctx);

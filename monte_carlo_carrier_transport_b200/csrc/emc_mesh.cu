@@ -429,7 +429,7 @@ int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega
         }
         if (e != cudaSuccess) goto cuda_fail;
     }
-    {
+    if (sweeps_out || err_out || err_hist) {      // otherwise asynchronous: query with emc_poisson_last
         double scal[2];
         int32_t fl[2];
         if ((e = cudaMemcpyAsync(scal, ctx->d_sor_scalars, sizeof(scal), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
@@ -453,6 +453,26 @@ int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega
 cuda_fail:
     ctx->last_error = std::string("CUDA: ") + cudaGetErrorString(e);
     return EMC_ERR_CUDA;
+}
+
+int poisson_last(Ctx *ctx, int32_t *sweeps_out, double *err_out, cudaStream_t st)
+{
+    double scal[2];
+    int32_t fl[2];
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(scal, ctx->d_sor_scalars, sizeof(scal), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(fl, ctx->d_sor_flags, sizeof(fl), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+        ctx->last_error = std::string("CUDA: ") + cudaGetErrorString(e);
+        return EMC_ERR_CUDA;
+    }
+    if (sweeps_out) *sweeps_out = fl[0];
+    if (err_out) *err_out = scal[0];
+    if (fl[1]) {
+        ctx->last_error = "Too large du (poisson_.py:78-80)";
+        return EMC_ERR_DIVERGED;
+    }
+    return EMC_OK;
 }
 
 }  // namespace emc

@@ -310,9 +310,8 @@ class Mesh:
 
     def allreduce(self, group=None):
         """Sum the integer charge mesh over ranks (NCCL over NVLink; gloo on CPU tests)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.counts, op=dist.ReduceOp.SUM, group=group)
+        from . import parallel
+        parallel.allreduce_counts(self.counts, group)
 
     def to_rho(self):
         c = self.ctx
@@ -331,10 +330,61 @@ class Mesh:
             return n.value, err.value, hist[:n.value].copy()
         return n.value, err.value
 
+    def solve_async(self, omega0: float = 1.5, tol: float = 1e-6, max_sweeps: int = 10000,
+                    order: int = abi.SOR_RED_BLACK):
+        """Enqueue the solve without a host round trip (the time loop); ``last_solve`` reports."""
+        c = self.ctx
+        c.check(c.lib.emc_poisson_sor(c.h, self.u_pad.data_ptr(), self.rho_pad.data_ptr(), omega0, tol,
+                                      max_sweeps, order, None, None, None, c.stream))
+
+    def last_solve(self):
+        """(sweeps, err) of the most recent solve; raises EmcError(ERR_DIVERGED) like poisson_.py:78-80."""
+        c = self.ctx
+        n, err = C.c_int32(0), C.c_double(0.0)
+        c.check(c.lib.emc_poisson_last(c.h, C.byref(n), C.byref(err), c.stream))
+        return n.value, err.value
+
     def field(self):
         c = self.ctx
         c.check(c.lib.emc_field(c.h, self.u_pad.data_ptr(), self.ex.data_ptr(), self.ey.data_ptr(),
                                 self.ez.data_ptr(), c.stream))
+
+
+class CoupledStepper:
+    """Self-consistent timestep (BASELINE configs 3/4): flight in the mesh field with the
+    end-of-step NGP deposit fused into the same kernel -> integer all-reduce of the charge
+    mesh over the ranks -> rho -> red-black SOR (warm-started from the previous potential) ->
+    field.  Everything stays on the device and in stream order; no host synchronisation."""
+
+    def __init__(self, ctx: Context, ens: Ensemble, mesh: Mesh | None = None, seed: int = 12345,
+                 tol: float = 1e-6, max_sweeps: int = 10000, order: int = abi.SOR_RED_BLACK,
+                 group=None):
+        self.ctx, self.ens, self.seed = ctx, ens, seed
+        self.mesh = mesh or Mesh(ctx)
+        self.tol, self.max_sweeps, self.order, self.group = tol, max_sweeps, order, group
+        self.n_steps = 0
+
+    def prime(self):
+        """Field of the initial ensemble (the reference would call poisson() before the loop)."""
+        m = self.mesh
+        m.zero_counts()
+        m.deposit(self.ens)
+        self._solve()
+        return self
+
+    def _solve(self):
+        m = self.mesh
+        m.allreduce(self.group)
+        m.to_rho()
+        m.solve_async(tol=self.tol, max_sweeps=self.max_sweeps, order=self.order)
+        m.field()
+
+    def step(self, observe: bool = True):
+        m = self.mesh
+        m.zero_counts()
+        self.ens.step(self.n_steps, self.seed, field_mode=abi.FIELD_MESH, mesh=m, observe=observe, deposit=True)
+        self._solve()
+        self.n_steps += 1
 
 
 class HostStepper:

@@ -554,3 +554,55 @@ def test_sor_divergence_is_reported(torch_mod):
         assert ei.value.status == abi.ERR_DIVERGED
     finally:
         c.close()
+
+
+def test_coupled_stepper_vs_oracle(torch_mod):
+    """Self-consistent loop (flight in the mesh field + fused deposit -> rho -> SOR -> field),
+    three timesteps, against the same loop run with the oracle.  With the lexicographic sweep
+    order every mesh quantity is bit-identical as long as no particle sits within an ulp of a
+    cell face (none does for this seed)."""
+    torch = torch_mod
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    seg = (24, 1, 16)
+    c = mesh_context(seg, torch)
+    try:
+        g = helpers.golden_params()["phys"]
+        n = 20000
+        coords, v, dtau = hot_ensemble(n, 36, g)
+        dl = np.array(c.params.dl[:])
+        ens = engine.Ensemble(c, n).load(coords, v, dtau)
+        cs = engine.CoupledStepper(c, ens, seed=11, order=abi.SOR_LEXICOGRAPHIC).prime()
+        # oracle side
+        o = helpers.make_oracle()
+        st = helpers.state_from_coords(coords, v, dtau)
+        bg, inc = c.params.rho_background, c.params.rho_increment
+        u = np.zeros(c.padded_shape)
+        u[:, :, 0] = c.params.surf_val
+
+        def oracle_solve(u):
+            cnt = orc.deposit_ngp(st["x"], st["y"], st["z"], np.array(seg), dl)
+            rho = np.pad(orc.counts_to_rho(cnt, bg, inc).reshape(seg), 1)
+            u, nsw, _ = orc.poisson_sor(np.array(seg), dl, c.params.eps_s, u, rho, 1.5, 1e-6, 10000)
+            return cnt, u, nsw, orc.field(np.array(seg), dl, u)
+
+        cnt, u, nsw, fld = oracle_solve(u)
+        assert np.array_equal(cs.mesh.counts.cpu().numpy(), cnt)
+        assert cs.mesh.last_solve()[0] == nsw
+        assert np.array_equal(cs.mesh.u_pad.cpu().numpy(), u)
+        for s in range(3):
+            cs.step()
+            o.set_field_mesh(seg, dl, *fld)
+            o.timestep(st, orc.philox_stream(11, s, 0), threads=4)
+            cnt, u, nsw, fld = oracle_solve(u)
+            assert np.array_equal(cs.mesh.counts.cpu().numpy(), cnt), s
+            assert np.array_equal(cs.mesh.u_pad.cpu().numpy(), u), s
+            assert np.array_equal(cs.mesh.ez.cpu().numpy(), fld[2]), s
+        compare_states(st, *ens.coords(), np.array(g["tot_dim"]))
+        # the fast path (red-black) stays within the solver tolerance of it
+        ens2 = engine.Ensemble(c, n).load(coords, v, dtau)
+        cs2 = engine.CoupledStepper(c, ens2, seed=11, order=abi.SOR_RED_BLACK).prime()
+        for s in range(3):
+            cs2.step()
+        assert np.max(np.abs(cs2.mesh.u_pad.cpu().numpy() - u)) < 1e-4
+    finally:
+        c.close()
