@@ -178,6 +178,69 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+COUPLED_MESH = (1024, 1, 1024)          # BASELINE configs[3]: 1024 x 1024 Poisson mesh (ny = 1 like the reference)
+COUPLED_PER_GPU = 12_500_000            # 1e8 particles over 8 GPUs
+
+
+def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=20, warmup=5):
+    """Metric (ii): ms per coupled MC+Poisson timestep = flight in the mesh field with the NGP
+    deposit fused in -> int64 charge all-reduce (NCCL, world > 1) -> rho -> red-black SOR to the
+    reference's tolerance (warm-started) -> field.  Median over `steps` timesteps, CUDA events."""
+    p = engine.params_from_reference_modules(num_carr=COUPLED_PER_GPU * world)
+    for a in range(3):
+        p.seg[a] = COUPLED_MESH[a]
+        p.dl[a] = p.tot_dim[a] / COUPLED_MESH[a]
+    p.rho_background = -1e16 * p.dl[0] * p.dl[1] * p.dl[2] * 1e6          # init_.py:189-191
+    ctx = engine.Context(p, device=local)
+    n = COUPLED_PER_GPU
+    ens = engine.Ensemble(ctx, n, pid_offset=rank * n).init(SEED + 1)
+    cs = engine.CoupledStepper(ctx, ens, seed=SEED + 1, max_sweeps=200)
+    cs.prime()                                    # cold start: capped, the loop below is warm-started
+    for _ in range(warmup):
+        cs.step()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    stage = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    sweeps = []
+    launches0 = ctx.launch_count()
+    barrier()
+    ev[0].record()
+    for s in range(steps):
+        m = cs.mesh
+        m.zero_counts()
+        ens.step(cs.n_steps, cs.seed, field_mode=abi.FIELD_MESH, mesh=m, observe=True, deposit=False)
+        m.deposit(ens)
+        stage[s][0].record()
+        m.allreduce()
+        stage[s][1].record()
+        m.to_rho()
+        m.solve_async(tol=cs.tol, max_sweeps=cs.max_sweeps, order=cs.order)
+        m.field()
+        stage[s][2].record()
+        cs.n_steps += 1
+        ev[s + 1].record()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    sweeps.append(cs.mesh.last_solve()[0])
+    per = np.array([ev[s].elapsed_time(ev[s + 1]) for s in range(steps)])
+    flight = np.array([ev[s].elapsed_time(stage[s][0]) for s in range(steps)])
+    allred = np.array([stage[s][0].elapsed_time(stage[s][1]) for s in range(steps)])
+    solve = np.array([stage[s][1].elapsed_time(stage[s][2]) for s in range(steps)])
+    t = torch.tensor([np.median(per), np.median(flight), np.median(allred), np.median(solve)],
+                     dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    obs = ens.last_obs()
+    ctx.close()
+    t = [float(v) for v in t.cpu()]
+    return {"metric": "ms per coupled MC+Poisson timestep", "ms_per_timestep": t[0], "flight_deposit_ms": t[1],
+            "charge_allreduce_ms": t[2], "rho_sor_field_ms": t[3], "sor_sweeps_last_step": sweeps[-1],
+            "mesh": "x".join(str(v) for v in COUPLED_MESH), "particles_per_gpu": n, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
+            "sor": "red-black, tol 1e-6 RMS update (poisson_.py:63), warm start from the previous potential",
+            "segments_last_step": obs["n_segments"]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -199,16 +262,16 @@ def run_ours(args):
 
     n = N_FIELDS * PER_FIELD
     ctx = engine.Context(device=local)             # init_ / scatter_ module state -> EmcParams + tables
-    ctx.set_field_groups(field_points(), PER_FIELD)
-    # global particle id = rank*n + i; field group = (global id / PER_FIELD) % 24 is arranged by
-    # giving every rank the same 24 groups: the group index uses the LOCAL offset
-    ens = engine.Ensemble(ctx, n, pid_offset=0)
-    ens.init(SEED + rank)
+    # global particle id = rank*n + i keys the Philox streams (rank-count invariant); every rank
+    # runs the same 24 field points: the group table is tiled once per rank
+    ctx.set_field_groups(np.tile(field_points(), (world, 1)), PER_FIELD)
+    ens = engine.Ensemble(ctx, n, pid_offset=rank * n)
+    ens.init(SEED)
     steps, warmup = args.steps, max(args.warmup, 3)
 
     # ---- device-resident arm ---------------------------------------------------------------
     for s in range(warmup):
-        ens.step(s, SEED + rank, field_mode=abi.FIELD_GROUPS)
+        ens.step(s, SEED, field_mode=abi.FIELD_GROUPS)
     torch.cuda.synchronize()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -221,7 +284,7 @@ def run_ours(args):
     t_start.record()
     for s in range(steps):
         ev[s][0].record()
-        ens.step(warmup + s, SEED + rank, field_mode=abi.FIELD_GROUPS)
+        ens.step(warmup + s, SEED, field_mode=abi.FIELD_GROUPS)
         ev[s][1].record()
         obs_keep[s].copy_(ens.obs, non_blocking=True)
     t_stop.record()
@@ -237,7 +300,7 @@ def run_ours(args):
 
     # ---- end-to-end arm: the caller holds HOST arrays (the reference's coords/valley/dtau) ----
     co, val, dtau = None, None, None
-    hs = engine.HostStepper(ctx, n)
+    hs = engine.HostStepper(ctx, n, pid_offset=rank * n)
     # start the host copy from the current device state
     out = torch.empty((n, 6), dtype=torch.float64, device=ctx.device)
     p = ens._ptrs()
@@ -248,16 +311,20 @@ def run_ours(args):
     del out
     torch.cuda.synchronize()
     e2e_steps = max(3, min(steps, 10))
-    hs.step(10_000, SEED + rank, field_mode=abi.FIELD_GROUPS)          # warm-up (allocations, pinning)
+    hs.step(10_000, SEED, field_mode=abi.FIELD_GROUPS)                 # warm-up (allocations, pinning)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     seg_e2e = 0
     for s in range(e2e_steps):
-        seg_e2e += hs.step(10_001 + s, SEED + rank, field_mode=abi.FIELD_GROUPS)["n_segments"]
+        seg_e2e += hs.step(10_001 + s, SEED, field_mode=abi.FIELD_GROUPS)["n_segments"]
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+
+    h2d_bytes, d2h_bytes = hs.h2d_bytes, hs.d2h_bytes
+    del hs
+    coupled =coupled_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
 
     # ---- max over ranks, totals over ranks ---------------------------------------------------
     t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=ctx.device)
@@ -289,10 +356,10 @@ def run_ours(args):
                              "sample": "%d particles (24 field groups x 100000), %d timesteps, %.1f s"
                                        % (cpu_n, cpu_steps, cpu_dt)},
             "e2e": {"value": seg_e2e / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": hs.h2d_bytes,
-                    "d2h_bytes_per_step": hs.d2h_bytes,
+                    "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes,
                     "api": "engine.HostStepper.step: pinned host (N,6) coords + valley + dtau in, same out"},
-            "gpu_launches": int(launches), "clocks": clk,
+            "gpu_launches": int(launches), "clocks": clk, "coupled": coupled,
         }
         print(json.dumps(line))
     ctx.close()
@@ -306,6 +373,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-coupled", action="store_true", help="skip the coupled MC+Poisson sub-benchmark")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -175,9 +175,9 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
         efz = __ldg(P.field_groups + 3 * p.grp + 2);
     } else {
         // nearest-cell gather from the padded (nx+2,ny+2,nz+2) field of emc_field, V/m -> V/cm
-        const int ci = axis_cell(p.x, P.seg[0], P.dl[0]) + 1;
-        const int cj = axis_cell(p.y, P.seg[1], P.dl[1]) + 1;
-        const int ck = axis_cell(p.z, P.seg[2], P.dl[2]) + 1;
+        const int ci = axis_cell(p.x, P.seg[0], P.dl[0], P.inv_dl[0]) + 1;
+        const int cj = axis_cell(p.y, P.seg[1], P.dl[1], P.inv_dl[1]) + 1;
+        const int ck = axis_cell(p.z, P.seg[2], P.dl[2], P.inv_dl[2]) + 1;
         const int64_t c = ((int64_t)ci * (P.seg[1] + 2) + cj) * (P.seg[2] + 2) + ck;
         efx = __ldg(A.ex + c) * 1e-2;
         efy = __ldg(A.ey + c) * 1e-2;
@@ -449,7 +449,8 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     A.smem_cells = 0;
     if (A.mesh) {
         const int64_t cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];
-        if (cells * 4 <= SMEM_MESH_BYTES) { A.smem_cells = (int)cells; smem += (size_t)cells * 4; }
+        // privatise the counts in shared memory only while two blocks per SM still fit beside the queues
+        if (cells * 4 <= 16 * 1024) { A.smem_cells = (int)cells; smem += (size_t)cells * 4; }
     }
     A.partials = ctx->partials;
     A.ticket = ctx->ticket;
