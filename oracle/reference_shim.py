@@ -36,8 +36,13 @@ def _install_stubs() -> None:
         np.product = np.prod  # type: ignore[attr-defined]
 
     def _stub(name: str) -> types.ModuleType:
+        from unittest import mock
+
         m = types.ModuleType(name)
         m.__dict__["__stub__"] = True
+        # any plotting / spreadsheet call (plt.subplots(), ax.plot(), Workbook() ...) is a no-op:
+        # main_.py:405-434 plots after the time loop and must not abort the run
+        m.__getattr__ = lambda attr: mock.MagicMock(name="%s.%s" % (name, attr))   # PEP 562
         sys.modules[name] = m
         return m
 
@@ -55,6 +60,10 @@ def _install_stubs() -> None:
     mpl = sys.modules["matplotlib"]
     if getattr(mpl, "__stub__", False):
         mpl.pyplot = sys.modules["matplotlib.pyplot"]
+    plt = sys.modules["matplotlib.pyplot"]
+    if getattr(plt, "__stub__", False):
+        from unittest import mock
+        plt.subplots = lambda *a, **k: (mock.MagicMock(), mock.MagicMock())   # main_.py:405 unpacks two
 
 
 _cache: dict[str, types.ModuleType] = {}

@@ -1,0 +1,68 @@
+"""Free-running mode vs the reference's own free-running run (north_star: drift velocity, mean
+energy and valley occupancy within 3 sigma of the ensemble statistical error).
+
+The fixtures tests/golden/free_running_*.json are per-step observables of the UNMODIFIED
+reference (main_.py's loop executed with np.random.seed; tests/golden/generate_golden.py
+free_running / high_field).  The GPU run uses its own (Philox) random stream and the device-side
+ensemble initialiser, with 100x more particles so that its own error is negligible; the two
+trajectories of <v_z>, <E>, <z> and of the valley fractions must be statistically
+indistinguishable at every timestep.  With O(100) correlated comparisons a strict "every |z| < 3"
+would fail by chance one run in four, so the bar is: no |z| above 4.5 and at most 5 % above 3.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(name):
+    p = os.path.join(helpers.GOLDEN, name + ".json")
+    if not os.path.exists(p):
+        pytest.skip("fixture %s.json has not been generated" % name)
+    return json.load(open(p))
+
+
+@pytest.mark.parametrize("name", ["free_running_c1", "free_running_hf"])
+def test_observables_within_three_sigma_of_the_reference(name):
+    import torch
+    from monte_carlo_carrier_transport_b200 import engine
+    assert torch.cuda.is_available()
+    ref = _load(name)
+    g = helpers.golden_params()
+    phys = dict(g["phys"])
+    phys["efield"] = ref["efield"]
+    ctx = engine.Context(engine.params_from_dict(phys, g["device"]), device=0, tables=helpers.host_tables())
+    try:
+        n_ref, pts = ref["num_carr"], ref["pts"]
+        n = 100 * n_ref
+        ens = engine.Ensemble(ctx, n).init(seed=2026)
+        zs, big = [], []
+        L = phys["tot_dim"][2]
+        for c in range(pts):
+            ens.step(c, 2026)
+            o = engine.summarize(ens.last_obs())
+            r = ref["rows"][c]
+            assert o["n_fault"] <= 1e-4 * n
+            z_v = (o["vz"] - r["vz"]) / np.hypot(r["vz_se"], o["vz_se"])
+            z_e = (o["e"] - r["e"]) / np.hypot(r["e_se"], o["e_se"])
+            se_z = L / np.sqrt(12.0) / np.sqrt(n_ref) * 1e9            # <z> of a near-uniform profile, nm
+            z_z = (o["z_nm"] - r["z_nm"]) / se_z
+            zs += [z_v, z_e, z_z]
+            for v in (1, 2):                                           # L and X occupancy
+                p_gpu = o["n_valley"][v] / max(o["n"], 1)
+                se = np.sqrt(max(p_gpu * (1 - p_gpu), 1.0 / n) / n_ref)
+                zs.append((r["n_valley"][v] / n_ref - p_gpu) / se)
+            big.append((c, z_v, z_e, z_z))
+        zs = np.abs(np.array(zs))
+        assert zs.max() < 4.5, (zs.max(), [b for b in big if max(abs(b[1]), abs(b[2]), abs(b[3])) > 3])
+        assert (zs > 3).mean() <= 0.05, (zs > 3).mean()
+        # and the physics the reference shows: Gamma-dominated, energy and drift velocity rising
+        last = engine.summarize(ens.last_obs())
+        assert last["n_valley"][0] > 0.9 * n and last["vz"] > 0
+    finally:
+        ctx.close()
