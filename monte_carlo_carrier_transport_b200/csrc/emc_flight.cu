@@ -139,7 +139,10 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 // and its own (counter-based) random stream, so the regrouping changes no result.
 // ------------------------------------------------------------------------------------------
 #ifndef EMC_FLIGHT_MIN_BLOCKS
-#define EMC_FLIGHT_MIN_BLOCKS 2      // resident 256-thread blocks per SM the register allocator must allow
+// resident blocks per SM the register allocator must allow.  Measured on configs[1] (2.4e7
+// particles): 512 threads x 1 block 1.47 ms, 256 x 2 1.51 ms, 128 x 4 1.54 ms (all 126 registers,
+// 16 warps/SM); 192 x 3 (96 registers, 18 warps, spills) 2.22 ms; 256 x 3 (80 registers) 1.72 ms.
+#define EMC_FLIGHT_MIN_BLOCKS 1
 #endif
 constexpr int QCAP = 64;                     // a phase runs only if its pushes fit: <= 32 + 32
 struct WarpQueue {

@@ -6,7 +6,10 @@
 
 namespace emc {
 
-constexpr int FLIGHT_THREADS = 256;
+#ifndef EMC_FLIGHT_THREADS
+#define EMC_FLIGHT_THREADS 512       // tuning knob (-DEMC_FLIGHT_THREADS=...), multiple of 32
+#endif
+constexpr int FLIGHT_THREADS = EMC_FLIGHT_THREADS;
 constexpr int SMEM_MESH_BYTES = 96 * 1024;     // NGP counts privatised in shared memory up to this size
 
 struct ObsPartial {

@@ -606,3 +606,29 @@ def test_coupled_stepper_vs_oracle(torch_mod):
         assert np.max(np.abs(cs2.mesh.u_pad.cpu().numpy() - u)) < 1e-4
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 511, 513, 4097, 100001])
+def test_ragged_ensemble_sizes_vs_oracle(ctx, torch_mod, n):
+    """Slices that do not fill a warp / a block / the persistent grid, incl. frozen particles."""
+    from monte_carlo_carrier_transport_b200 import engine
+    g = helpers.golden_params()["phys"]
+    coords, v, dtau = hot_ensemble(n, 40 + n % 7, g)
+    v[::5] = np.where(np.arange(n)[::5] % 2 == 0, -4, v[::5])          # some particles already frozen
+    o = helpers.make_oracle(efield=g["efield"])
+    st = helpers.state_from_coords(coords, v, dtau)
+    ens = engine.Ensemble(ctx, n, pid_offset=3).load(coords, v, dtau)
+    for s in range(3):
+        ens.step(s, 55)
+        oo = o.timestep(st, orc.philox_stream(55, s, 3))
+        og = ens.last_obs()
+        for key in ("n_valley", "n_fault", "n_segments", "n_events"):
+            assert og[key] == oo[key], (s, key)
+    co, val, dt_ = ens.coords()
+    assert np.array_equal(val, st["valley"])
+    ok = val >= 0
+    ref = helpers.coords_from_state(st)
+    if ok.any():
+        assert k_err(co[ok, :3], ref[ok, :3]) < 1e-6
+    frozen = ~ok & (v < 0)
+    assert np.array_equal(co[frozen], coords[frozen])                    # frozen on entry: untouched
