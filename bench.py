@@ -164,7 +164,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_per_field = 100_000
+    n_per_field = 500_000
     value, dt, done, n = cpu_port_run(n_per_field, args.steps, args.warmup, threads)
     sample = "%d particles (24 field groups x %d), %d timesteps" % (n, n_per_field, done)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -339,7 +339,7 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         achieved = ALGO_BYTES_PER_PARTICLE_STEP * n / (kernel_ms * 1e-3) / 1e9
         threads = os.cpu_count() or 1
-        cpu_value, cpu_dt, cpu_steps, cpu_n = cpu_port_run(100_000, 40, 2, threads, budget_s=12.0)
+        cpu_value, cpu_dt, cpu_steps, cpu_n = cpu_port_run(500_000, 400, 2, threads, budget_s=12.0)
         line = {
             "metric": METRIC, "value": segments / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": elapsed_ms / steps, "higher_is_better": True,
@@ -353,7 +353,7 @@ def run_ours(args):
                          "peak_source": peak_src, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d particles (24 field groups x 100000), %d timesteps, %.1f s"
+                             "sample": "%d particles (24 field groups x 500000), %d timesteps, %.1f s"
                                        % (cpu_n, cpu_steps, cpu_dt)},
             "e2e": {"value": seg_e2e / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": h2d_bytes,

@@ -384,6 +384,9 @@ void orc_init_ensemble(const OrcParams *p, int64_t n, double *kx, double *ky, do
                        double *x, double *y, double *z, double *dtau, int32_t *valley,
                        uint64_t seed, uint64_t pid_offset)
 {
+#ifdef _OPENMP
+    #pragma omp parallel for schedule(static)
+#endif
     for (int64_t i = 0; i < n; ++i) {
         double u[10];
         for (uint32_t d = 0; d < 10; ++d)
@@ -491,6 +494,30 @@ void orc_counts_to_rho(int64_t n_cells, const int64_t *counts, double background
         for (int64_t k = 0; k < counts[c]; ++k) r += increment;   /* poisson_.py:36 */
         rho[c] = r;
     }
+}
+
+/* Checker for the CUDA path's division by run constants (csrc/emc_device.cuh div_const): the
+   same five operations in C (fma from libm) against the IEEE quotient, on `n` random
+   dividends a = m * 2^e, m in [1,2), e uniform in [e_lo, e_hi].  Returns the mismatches. */
+int64_t orc_div_const_mismatches(double b, int64_t n, uint64_t seed, int e_lo, int e_hi)
+{
+    const double rb = 1 / b;
+    int64_t bad = 0;
+    uint64_t s = seed * 6364136223846793005ull + 1442695040888963407ull;
+    for (int64_t i = 0; i < n; ++i) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        double m = 1.0 + (double)(s >> 11) * (1.0 / 9007199254740992.0);
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        int e = e_lo + (int)((s >> 33) % (uint64_t)(e_hi - e_lo + 1));
+        double a = ldexp((s >> 20) & 1 ? -m : m, e);
+        double q = a * rb;
+        double r = fma(-q, b, a);
+        q = fma(r, rb, q);
+        r = fma(-q, b, a);
+        q = fma(r, rb, q);
+        if (q != a / b) ++bad;
+    }
+    return bad;
 }
 
 void orc_fx_to_rho(int64_t n_cells, const int64_t *mesh_fx, double background,

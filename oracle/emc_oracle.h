@@ -121,6 +121,7 @@ void   orc_counts_to_rho(int64_t n_cells, const int64_t *counts, double backgrou
                          double increment, double *rho);
 
 /* CIC fixed point -> rho: background + increment * mesh/2^32 */
+int64_t orc_div_const_mismatches(double b, int64_t n, uint64_t seed, int e_lo, int e_hi);
 void   orc_fx_to_rho(int64_t n_cells, const int64_t *mesh_fx, double background,
                      double increment, double *rho);
 

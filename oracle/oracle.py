@@ -96,6 +96,8 @@ def lib():
         L.orc_init_ensemble.argtypes = [C.POINTER(OrcParams), C.c_int64] + [dp] * 7 + [
             ip, C.c_uint64, C.c_uint64]
         L.orc_fx_to_rho.argtypes = [C.c_int64, lp, C.c_double, C.c_double, dp]
+        L.orc_div_const_mismatches.restype = C.c_int64
+        L.orc_div_const_mismatches.argtypes = [C.c_double, C.c_int64, C.c_uint64, C.c_int, C.c_int]
         L.orc_observables.argtypes = [C.POINTER(OrcParams), C.c_int64, dp, dp, dp, dp, ip,
                                       C.POINTER(OrcObs)]
         L.orc_deposit_ngp.argtypes = [C.c_int64, dp, dp, dp, ip, dp, lp]
@@ -274,6 +276,10 @@ def counts_to_rho(counts, background, increment):
     rho = np.empty(len(counts), dtype=np.float64)
     lib().orc_counts_to_rho(len(counts), _lp(counts), background, increment, _dp(rho))
     return rho
+
+
+def div_const_mismatches(b, n, seed, e_lo, e_hi):
+    return int(lib().orc_div_const_mismatches(float(b), int(n), int(seed), int(e_lo), int(e_hi)))
 
 
 def fx_to_rho(mesh_fx, background, increment):

@@ -145,6 +145,22 @@ def test_replay_trajectories(case):
         assert (n_seg, n_ev) == (meta["n_segments"], meta["n_events"])
 
 
+def test_division_by_run_constants_is_correctly_rounded():
+    """csrc/emc_device.cuh div_const (reciprocal + two FMA residual corrections) == IEEE '/':
+    the five operations restated in C, 2e6 random dividends per divisor the kernels use, over the
+    exponent ranges those dividends actually span."""
+    g = helpers.golden_params()
+    ph, dev = g["phys"], g["device"]
+    hbar, q = ph["hbar"], ph["q"]
+    divisors = [(hbar, -140, -60), (hbar * hbar, -260, -100)]
+    for v in range(3):
+        divisors += [(2 * ph["mass"][v] * q, -260, -100), (2 * ph["nonparab"][v], -40, 10),
+                     (ph["mass"][v], -120, -20)]
+    divisors += [(d, -80, -10) for d in dev["dl"]]
+    for i, (b, lo, hi) in enumerate(divisors):
+        assert orc.div_const_mismatches(b, 2_000_000, 1000 + i, lo, hi) == 0, b
+
+
 def test_ngp_deposit_and_rho_bit_exact():
     p = helpers.golden_npz("poisson")
     D = helpers.golden_params()["phys"]["tot_dim"]
