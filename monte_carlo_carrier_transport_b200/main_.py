@@ -225,3 +225,40 @@ def run(num_carr=None, pts=None, seed=12345, elec_field=None, coords=None, valle
         if history:
             hist.append(ens.coords())
     return (rows, ens, hist) if history else (rows, ens)
+
+
+# the reference's spreadsheet columns A..G (main_.py:341, 398-403, 448-454)
+SHEET_COLUMNS = ("Time (ps)", "Average z pos. (nm)", "Average velocity (m/s)", "Average energy (eV)",
+                 "Gamma-Valley Population", "L-Valley Population", "X-Valley Population")
+
+
+def sheet_rows(rows):
+    """``run`` rows -> the per-step table the reference writes to its worksheet."""
+    return [(r["t_ps"], r["z_nm"], r["vz"], r["e"], r["n_valley"][0], r["n_valley"][1], r["n_valley"][2])
+            for r in rows]
+
+
+def save_rows(rows, path, num_carr=None, elec_field=None):
+    """Write the per-step table as CSV (``.csv``) or ``.npz`` with the reference's column titles,
+    followed -- like the worksheet's I/J block (main_.py:438-446, 464-469) -- by the run inputs.
+    The reference writes an .xlsx through openpyxl; the same numbers, in a format that needs no
+    extra dependency."""
+    table = sheet_rows(rows)
+    inputs = {"Number of Carriers": int(dev.num_carr if num_carr is None else num_carr),
+              "Electric field (V/cm)": float((dev.elec_field if elec_field is None else elec_field)[2]),
+              "Impurity Doping (cm-3)": float(dev.layers[0].matl.dope),
+              "Time step (ps)": float(param.dt), "Data Points": len(rows),
+              "Simulation Time (ps)": float(param.dt * len(rows))}
+    if str(path).endswith(".npz"):
+        np.savez(path, columns=np.array(SHEET_COLUMNS), table=np.array(table, dtype=np.float64),
+                 **{k.split(" (")[0].replace(" ", "_").lower(): v for k, v in inputs.items()})
+        return path
+    import csv
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(SHEET_COLUMNS)
+        w.writerows(table)
+        w.writerow([])
+        for k, v in inputs.items():
+            w.writerow([k, v])
+    return path
