@@ -171,3 +171,38 @@ def init_coords(layers=None, num_carr=None, mean_nrg=None):
         coords[i, 1] = k * np.sin(alpha) * np.sin(beta)
         coords[i, 2] = k * np.cos(beta)
     return coords
+
+
+class laser:
+    """Excitation pulse parameters, init_.py:236-242 (host-side mirror; photo-excitation is
+    not on the accelerated path: it is inactive in every benchmark configuration and the
+    reference's injection bookkeeping, main_.py:345-358, cannot run once a carrier is drawn
+    beyond the slab -- see DESIGN.md "Out of scope")."""
+
+    laser_ex = 800
+    laser_pow = 0.1E-3
+    laser_std = 0.5E-6
+    laser_t = 100E-15
+    laser_eff = (laser_pow * laser_t / (Parameters.q * (1240 / laser_ex - GaAs.EG))) / 10000
+    t0 = 1.5E-12
+
+
+def init_photoex(layers, num_carr, nrg=1240 / laser.laser_ex - GaAs.EG):
+    """Photo-excited carriers ``(M, 6)``, M <= num_carr (init_.py:244-280): exponential depth
+    profile (carriers drawn beyond the slab are dropped), Gaussian x and y, mono-energetic,
+    ``Normal(0, 2*pi)`` angles; same np.random draw order as the reference."""
+    n = int(num_carr)
+    z = np.random.exponential(min(1 / GaAs.alpha, Device.tot_dim[2]), n)
+    keep = z < Device.tot_dim[2]
+    z = z[keep]
+    x = np.random.normal(0, laser.laser_std, n)[keep]
+    y = np.random.normal(0, laser.laser_std, n)[keep]
+    coords = np.zeros((len(z), 6))
+    for i in range(len(z)):
+        mat = layers[where_am_i(layers, z[i])["current_layer"]].matl
+        k = np.sqrt(2 * mat.mass[0] * Parameters.q * nrg / Parameters.hbar ** 2)
+        alpha = np.random.normal(0, 2 * np.pi)
+        beta = np.random.normal(0, 2 * np.pi)
+        coords[i] = [k * np.cos(alpha) * np.sin(beta), k * np.sin(alpha) * np.sin(beta), k * np.cos(beta),
+                     x[i], y[i], z[i]]
+    return coords

@@ -107,6 +107,14 @@ def test_value_for_value_against_the_reference_modules():
     np.random.seed(99)
     b = ri.init_coords(ri.Device.layers, 300, ri.Device.mean_energy)
     assert np.array_equal(a, b)
+    # laser parameters and photo-excited carriers (host mirrors; not on the accelerated path)
+    for k in ("laser_ex", "laser_pow", "laser_std", "laser_t", "laser_eff", "t0"):
+        assert getattr(init_.laser, k) == getattr(ri.laser, k), k
+    np.random.seed(5)
+    a = init_.init_photoex(init_.Device.layers, 200)
+    np.random.seed(5)
+    b = ri.init_photoex(ri.Device.layers, 200)
+    assert a.shape == b.shape and a.shape[0] < 200 and np.array_equal(a, b)
     # mechanism dictionaries: same order, dE, final valley, sampler
     ma, mb = scatter_.scatter_mech(0), rsc.scatter_mech(0)
     for v in range(3):
