@@ -208,14 +208,14 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
     for s in range(steps):
         m = cs.mesh
         m.zero_counts()
-        ens.step(cs.n_steps, cs.seed, field_mode=abi.FIELD_MESH, mesh=m, observe=True, deposit=False)
+        ens.step(cs.n_steps, cs.seed, field_mode=cs.field_mode, mesh=m, observe=True, deposit=False)
         m.deposit(ens)
         stage[s][0].record()
         m.allreduce()
         stage[s][1].record()
         m.to_rho()
         m.solve_async(tol=cs.tol, max_sweeps=cs.max_sweeps, order=cs.order)
-        m.field()
+        m.field_packed()
         stage[s][2].record()
         cs.n_steps += 1
         ev[s + 1].record()

@@ -73,7 +73,9 @@ enum { EMC_SOR_LEXICOGRAPHIC = 0, /* poisson_.py:74 order, executed as hyperplan
 /* field sources of the flight kernel */
 enum { EMC_FIELD_CONSTANT = 0,   /* dev.elec_field, main_.py:367,373,388 */
        EMC_FIELD_GROUPS = 1,     /* particle i uses field_groups[(pid_offset+i)/group_size] (velocity-field sweeps) */
-       EMC_FIELD_MESH = 2 };     /* nearest-cell gather from the Poisson field (poisson_.py:88-96), V/m */
+       EMC_FIELD_MESH = 2,       /* nearest-cell gather from the Poisson field (poisson_.py:88-96), V/m */
+       EMC_FIELD_MESH_PACKED = 3 }; /* same field, one 32-byte record per cell written by emc_field_packed:
+                                    `ex` points to it, ey = ez = NULL */
 
 /* Physical / numerical parameters: a snapshot of init_.Parameters, init_.GaAs and
  * init_.Device (init_.py:58-157). */
@@ -228,6 +230,11 @@ int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad, double om
 int emc_poisson_last(EmcCtx *ctx, int32_t *sweeps_out, double *err_out, void *stream);
 /* E = -central difference on interior cells (poisson_.py:88-96); padded outputs, V/m */
 int emc_field(EmcCtx *ctx, const double *u_pad, double *ex, double *ey, double *ez, void *stream);
+/* The same field as one record (ex, ey, ez, 0) of four doubles per padded cell, already in the
+ * V/cm carrier_drift expects (main_.py:196: value * 1e-2, the identical multiplication the
+ * gather of EMC_FIELD_MESH applies): two 128-bit loads per flight segment instead of three
+ * scattered 64-bit ones.  e4: device, 4 * (nx+2)(ny+2)(nz+2) doubles, 32-byte aligned. */
+int emc_field_packed(EmcCtx *ctx, const double *u_pad, double *e4, void *stream);
 
 #ifdef __cplusplus
 }

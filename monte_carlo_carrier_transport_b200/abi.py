@@ -15,7 +15,7 @@ EMC_MAX_MECH = 16
 ABI_VERSION = 1
 
 # enums of include/emc.h
-FIELD_CONSTANT, FIELD_GROUPS, FIELD_MESH = 0, 1, 2
+FIELD_CONSTANT, FIELD_GROUPS, FIELD_MESH, FIELD_MESH_PACKED = 0, 1, 2, 3
 DEPOSIT_NGP, DEPOSIT_CIC = 0, 1
 SOR_LEXICOGRAPHIC, SOR_RED_BLACK = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_NO_TABLES, ERR_DIVERGED, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
@@ -82,6 +82,7 @@ SIGNATURES = {
     "emc_mesh_to_rho": (C.c_int, [_vp, _lp, _i32, _dp, _vp]),
     "emc_poisson_sor": (C.c_int, [_vp, _dp, _dp, _f64, _f64, _i32, _i32, C.POINTER(_i32),
                                   C.POINTER(_f64), _dp, _vp]),
+    "emc_field_packed": (C.c_int, [_vp, _dp, _dp, _vp]),
     "emc_poisson_last": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_f64), _vp]),
     "emc_field": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _vp]),
 }

@@ -261,7 +261,9 @@ static int flight_common(Ctx *c, FlightArgs &A, bool replay, int32_t field_mode,
     if (field_mode == EMC_FIELD_MESH && (!ex || !ey || !ez)) return fail(c, EMC_ERR_INVALID, "EMC_FIELD_MESH needs ex, ey, ez");
     if (field_mode == EMC_FIELD_GROUPS && !c->dc.field_groups)
         return fail(c, EMC_ERR_INVALID, "EMC_FIELD_GROUPS needs emc_set_field_groups");
-    if (field_mode < 0 || field_mode > EMC_FIELD_MESH) return fail(c, EMC_ERR_INVALID, "unknown field_mode");
+    if (field_mode == EMC_FIELD_MESH_PACKED && (!ex || ((uintptr_t)ex & 31) != 0))
+        return fail(c, EMC_ERR_INVALID, "EMC_FIELD_MESH_PACKED needs a 32-byte aligned packed field in ex");
+    if (field_mode < 0 || field_mode > EMC_FIELD_MESH_PACKED) return fail(c, EMC_ERR_INVALID, "unknown field_mode");
     A.ex = ex; A.ey = ey; A.ez = ez;
     if (A.n == 0) return EMC_OK;
     cudaError_t e = launch_flight(c, A, replay, field_mode, (cudaStream_t)stream);
@@ -416,6 +418,14 @@ extern "C" int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad
     if (!u_pad || !rho_pad) return fail(c, EMC_ERR_INVALID, "emc_poisson_sor: null");
     return run_poisson_sor(c, u_pad, rho_pad, omega0, tol, max_sweeps, order, sweeps_out, err_out, err_hist,
                            (cudaStream_t)stream);
+}
+
+extern "C" int emc_field_packed(EmcCtx *ctx, const double *u_pad, double *e4, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!u_pad || !e4 || ((uintptr_t)e4 & 31) != 0) return fail(c, EMC_ERR_INVALID, "emc_field_packed: null or unaligned");
+    cudaError_t e = launch_field_packed(c, u_pad, e4, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "field_packed launch");
 }
 
 extern "C" int emc_poisson_last(EmcCtx *ctx, int32_t *sweeps_out, double *err_out, void *stream)

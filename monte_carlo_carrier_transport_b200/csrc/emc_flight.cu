@@ -191,9 +191,15 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
         const int cj = axis_cell(p.y, P.seg[1], P.dl[1], P.inv_dl[1]) + 1;
         const int ck = axis_cell(p.z, P.seg[2], P.dl[2], P.inv_dl[2]) + 1;
         const int64_t c = ((int64_t)ci * (P.seg[1] + 2) + cj) * (P.seg[2] + 2) + ck;
-        efx = __ldg(A.ex + c) * 1e-2;
-        efy = __ldg(A.ey + c) * 1e-2;
-        efz = __ldg(A.ez + c) * 1e-2;
+        if (FIELD == EMC_FIELD_MESH_PACKED) {     // one 32-B record per cell, already V/cm
+            const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
+            const double2 a = __ldg(rec), b = __ldg(rec + 1);
+            efx = a.x; efy = a.y; efz = b.x;
+        } else {
+            efx = __ldg(A.ex + c) * 1e-2;
+            efy = __ldg(A.ey + c) * 1e-2;
+            efz = __ldg(A.ez + c) * 1e-2;
+        }
     }
 }
 
@@ -482,6 +488,7 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     case EMC_FIELD_CONSTANT: return launch_flight_t<STREAM, EMC_FIELD_CONSTANT>(ctx, A, grid, smem, st); \
     case EMC_FIELD_GROUPS:   return launch_flight_t<STREAM, EMC_FIELD_GROUPS>(ctx, A, grid, smem, st);   \
     case EMC_FIELD_MESH:     return launch_flight_t<STREAM, EMC_FIELD_MESH>(ctx, A, grid, smem, st);     \
+    case EMC_FIELD_MESH_PACKED: return launch_flight_t<STREAM, EMC_FIELD_MESH_PACKED>(ctx, A, grid, smem, st); \
     default: return cudaErrorInvalidValue;                                                       \
     }
     if (replay) { EMC_DISPATCH(ReplayStream) } else { EMC_DISPATCH(PhiloxStream) }

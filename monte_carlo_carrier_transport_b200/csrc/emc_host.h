@@ -93,6 +93,7 @@ cudaError_t launch_field(Ctx *ctx, const double *u_pad, double *ex, double *ey, 
 int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega0, double tol, int max_sweeps,
                     int order, int32_t *sweeps_out, double *err_out, double *err_hist, cudaStream_t st);
 
+cudaError_t launch_field_packed(Ctx *ctx, const double *u_pad, double *e4, cudaStream_t st);
 int poisson_last(Ctx *ctx, int32_t *sweeps_out, double *err_out, cudaStream_t st);
 
 }  // namespace emc

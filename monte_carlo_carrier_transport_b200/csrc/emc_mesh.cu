@@ -178,6 +178,34 @@ __global__ void field_kernel(const __grid_constant__ DevConst P, const double *_
     ez[c] = -0.5 * (u[c + 1] - u[c - 1]) / P.dl[2];        // :96
 }
 
+// the same differences, packed (ex, ey, ez, 0) per cell and pre-scaled V/m -> V/cm
+__global__ void field_packed_kernel(const __grid_constant__ DevConst P, const double *__restrict__ u, double4 *e4)
+{
+    const int nx = P.seg[0], ny = P.seg[1], nz = P.seg[2];
+    const int64_t sy = nz + 2, sx = (int64_t)(ny + 2) * (nz + 2);
+    const int64_t total = (int64_t)(nx + 2) * sx;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= total) return;
+    const int k = (int)(c % (nz + 2));
+    const int j = (int)((c / (nz + 2)) % (ny + 2));
+    const int i = (int)(c / sx);
+    double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (!(i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz)) {
+        v.x = (-0.5 * (u[c + sx] - u[c - sx]) / P.dl[0]) * 1e-2;
+        v.y = (-0.5 * (u[c + sy] - u[c - sy]) / P.dl[1]) * 1e-2;
+        v.z = (-0.5 * (u[c + 1] - u[c - 1]) / P.dl[2]) * 1e-2;
+    }
+    e4[c] = v;
+}
+
+cudaError_t launch_field_packed(Ctx *ctx, const double *u_pad, double *e4, cudaStream_t st)
+{
+    const int64_t total = (int64_t)(ctx->dc.seg[0] + 2) * (ctx->dc.seg[1] + 2) * (ctx->dc.seg[2] + 2);
+    ctx->launches++;
+    field_packed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->dc, u_pad, reinterpret_cast<double4 *>(e4));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_field(Ctx *ctx, const double *u_pad, double *ex, double *ey, double *ez, cudaStream_t st)
 {
     const int64_t total = (int64_t)(ctx->dc.seg[0] + 2) * (ctx->dc.seg[1] + 2) * (ctx->dc.seg[2] + 2);

@@ -230,6 +230,8 @@ class Ensemble:
         ex = ey = ez = None
         if field_mode == abi.FIELD_MESH:
             ex, ey, ez = mesh.ex.data_ptr(), mesh.ey.data_ptr(), mesh.ez.data_ptr()
+        elif field_mode == abi.FIELD_MESH_PACKED:
+            ex = mesh.e4.data_ptr()
         c.check(c.lib.emc_flight_scatter(
             c.h, *self._ptrs(), self.n, field_mode, ex, ey, ez, seed, self.pid_offset, step,
             self.obs.data_ptr() if observe else None,
@@ -243,6 +245,8 @@ class Ensemble:
         ex = ey = ez = None
         if field_mode == abi.FIELD_MESH:
             ex, ey, ez = mesh.ex.data_ptr(), mesh.ey.data_ptr(), mesh.ez.data_ptr()
+        elif field_mode == abi.FIELD_MESH_PACKED:
+            ex = mesh.e4.data_ptr()
         c.check(c.lib.emc_flight_scatter_replay(
             c.h, *self._ptrs(), self.n, field_mode, ex, ey, ez, self.pid_offset,
             uniforms.data_ptr(), uniforms.shape[1], cursor.data_ptr(),
@@ -288,6 +292,7 @@ class Mesh:
         self.ex = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.ey = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.ez = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
+        self.e4 = torch.zeros(pad + (4,), dtype=torch.float64, device=ctx.device)   # (ex, ey, ez, 0) in V/cm
         self.set_initial_guess(None)
 
     def set_initial_guess(self, u0):
@@ -349,6 +354,11 @@ class Mesh:
         c.check(c.lib.emc_field(c.h, self.u_pad.data_ptr(), self.ex.data_ptr(), self.ey.data_ptr(),
                                 self.ez.data_ptr(), c.stream))
 
+    def field_packed(self):
+        """The same field as one 32-byte record per cell (the flight kernel's FIELD_MESH_PACKED)."""
+        c = self.ctx
+        c.check(c.lib.emc_field_packed(c.h, self.u_pad.data_ptr(), self.e4.data_ptr(), c.stream))
+
 
 class CoupledStepper:
     """Self-consistent timestep (BASELINE configs 3/4): flight in the mesh field with the
@@ -358,12 +368,16 @@ class CoupledStepper:
 
     def __init__(self, ctx: Context, ens: Ensemble, mesh: Mesh | None = None, seed: int = 12345,
                  tol: float = 1e-6, max_sweeps: int = 10000, order: int = abi.SOR_RED_BLACK,
-                 group=None, fuse_deposit: bool = False):
+                 group=None, fuse_deposit: bool = False, packed_field: bool = True):
         # fuse_deposit: the flight kernel can deposit its end-of-step positions itself (saves
         # re-reading 24 B/particle) but the assignment then runs on half-filled warps inside the
         # register-heavy kernel: measured 0.45 ms fused vs 0.19 ms for the separate deposit kernel
         # at 1.25e7 particles on a 1024x1024 mesh (profiles/coupled_probe.py), so the default is off.
         self.fuse_deposit = fuse_deposit
+        # packed_field: gather one (ex, ey, ez, 0) record per flight segment instead of three
+        # separate arrays; identical values (Mesh.field() still gives the reference's ef_x/y/z)
+        self.packed_field = packed_field
+        self.field_mode = abi.FIELD_MESH_PACKED if packed_field else abi.FIELD_MESH
         self.ctx, self.ens, self.seed = ctx, ens, seed
         self.mesh = mesh or Mesh(ctx)
         self.tol, self.max_sweeps, self.order, self.group = tol, max_sweeps, order, group
@@ -382,12 +396,15 @@ class CoupledStepper:
         m.allreduce(self.group)
         m.to_rho()
         m.solve_async(tol=self.tol, max_sweeps=self.max_sweeps, order=self.order)
-        m.field()
+        if self.packed_field:
+            m.field_packed()
+        else:
+            m.field()
 
     def step(self, observe: bool = True):
         m = self.mesh
         m.zero_counts()
-        self.ens.step(self.n_steps, self.seed, field_mode=abi.FIELD_MESH, mesh=m, observe=observe,
+        self.ens.step(self.n_steps, self.seed, field_mode=self.field_mode, mesh=m, observe=observe,
                       deposit=self.fuse_deposit)
         if not self.fuse_deposit:
             m.deposit(self.ens)

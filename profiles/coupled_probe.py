@@ -55,6 +55,9 @@ def flight(field_mode, deposit):
 print("mesh %s, %d particles" % (mesh_shape, n))
 print("flight const field          %.3f ms" % timeit(flight(abi.FIELD_CONSTANT, False)))
 print("flight mesh field           %.3f ms" % timeit(flight(abi.FIELD_MESH, False)))
+mesh.field()
+mesh.field_packed()
+print("flight packed mesh field    %.3f ms" % timeit(flight(abi.FIELD_MESH_PACKED, False)))
 print("flight const field + deposit %.3f ms" % timeit(flight(abi.FIELD_CONSTANT, True)))
 print("flight mesh field + deposit  %.3f ms" % timeit(flight(abi.FIELD_MESH, True)))
 print("deposit kernel alone        %.3f ms" % timeit(lambda: (mesh.zero_counts(), mesh.deposit(ens))))

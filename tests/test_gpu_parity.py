@@ -596,8 +596,21 @@ def test_coupled_stepper_vs_oracle(torch_mod):
             cnt, u, nsw, fld = oracle_solve(u)
             assert np.array_equal(cs.mesh.counts.cpu().numpy(), cnt), s
             assert np.array_equal(cs.mesh.u_pad.cpu().numpy(), u), s
+            # the stepper gathers from the packed (ex, ey, ez, 0) record, pre-scaled to V/cm
+            e4 = cs.mesh.e4.cpu().numpy()
+            for a in range(3):
+                assert np.array_equal(e4[..., a], fld[a] * 1e-2), (s, a)
+            assert not e4[..., 3].any()
+            cs.mesh.field()
             assert np.array_equal(cs.mesh.ez.cpu().numpy(), fld[2]), s
         compare_states(st, *ens.coords(), np.array(g["tot_dim"]))
+        # three separate field arrays (EMC_FIELD_MESH) give the identical run
+        ens3 = engine.Ensemble(c, n).load(coords, v, dtau)
+        cs3 = engine.CoupledStepper(c, ens3, seed=11, order=abi.SOR_LEXICOGRAPHIC, packed_field=False).prime()
+        for s in range(3):
+            cs3.step()
+        a, b = ens.coords(), ens3.coords()
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
         # the fast path (red-black) stays within the solver tolerance of it
         ens2 = engine.Ensemble(c, n).load(coords, v, dtau)
         cs2 = engine.CoupledStepper(c, ens2, seed=11, order=abi.SOR_RED_BLACK).prime()
