@@ -1,0 +1,161 @@
+"""The five benchmark configurations of BASELINE.json as runnable entry points.
+
+    python -m monte_carlo_carrier_transport_b200.configs c2 [--scale 0.01] [--steps N]
+
+``scale`` multiplies the particle counts (1.0 = the sizes BASELINE.json names).  Every function
+returns plain Python data (per-step rows or a per-field table) computed by the CUDA kernels
+through the C-ABI; nothing here falls back to the CPU.
+
+  c1  reference default run: 10^4 electrons, E = (0,0,-5) kV/cm, 50 steps of 2 fs
+  c2  bulk velocity-field sweep, 24 points 0.1-50 kV/cm, 10^6 electrons per point, one ensemble
+  c3  quasi-1-D slab (nx = ny = 1, nz = 1024), 10^7 super-particles, Poisson every timestep
+      (uniform doping: the reference wires no doping profile)
+  c4  self-consistent run on a 1024 x 1 x 1024 mesh, 10^8 particles over the ranks,
+      NCCL all-reduce of the integer charge mesh every timestep
+  c5  high-field multivalley transient, 10^9 particles weak-scaled (1.25e8 per GPU), 50 kV/cm
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import abi, engine, init_, parallel
+
+SEED = 12345
+
+
+def _rows(ens, steps, seed, step_fn):
+    rows = []
+    for c in range(steps):
+        step_fn(c)
+        o = engine.summarize(ens.last_obs())
+        o.update(step=c, t_ps=c * init_.Parameters.dt * 1e12)
+        rows.append(o)
+    return rows
+
+
+def _global_rows(ens, steps, seed, step_fn, device):
+    """Per-step rows of the WHOLE ensemble (observable sums all-reduced over the ranks)."""
+    rows = []
+    for c in range(steps):
+        step_fn(c)
+        o = engine.summarize(parallel.allreduce_obs(ens.last_obs(), device=device))
+        o.update(step=c, t_ps=c * init_.Parameters.dt * 1e12)
+        rows.append(o)
+    return rows
+
+
+def c1(scale=1.0, steps=None, seed=SEED, device=0):
+    from . import main_
+    ctx = engine.Context(device=device)
+    rows, ens = main_.run(num_carr=max(1, int(10_000 * scale)), pts=steps or init_.Parameters.pts, seed=seed, ctx=ctx)
+    ctx.close()
+    return rows
+
+
+def field_points(n_fields=24, lo=100.0, hi=50_000.0):
+    mags = np.logspace(np.log10(lo), np.log10(hi), n_fields)
+    return np.stack([np.zeros(n_fields), np.zeros(n_fields), -mags], axis=1)
+
+
+def c2(scale=1.0, steps=2500, discard=1000, sample_every=10, seed=SEED, device=0, n_fields=24):
+    """Velocity-field curve: per field point the time average (after ``discard`` steps) of
+    <v_z>, <E> and the valley fractions."""
+    per = max(32, int(1_000_000 * scale))
+    ctx = engine.Context(device=device)
+    fields = field_points(n_fields)
+    ctx.set_field_groups(fields, per)
+    ens = engine.Ensemble(ctx, per * n_fields).init(seed)
+    acc = np.zeros((n_fields, 6))
+    n_samples = 0
+    ptr = ens._ptrs()
+    for c in range(steps):
+        ens.step(c, seed, field_mode=abi.FIELD_GROUPS, observe=False)
+        if c >= discard and (c - discard) % sample_every == 0:
+            for g in range(n_fields):                # observables of one field group = one slice
+                o = abi.EmcObs()
+                off = g * per * 8
+                ctx.check(ctx.lib.emc_observables(ctx.h, ptr[0] + off, ptr[1] + off, ptr[2] + off, ptr[5] + off,
+                                                  ptr[7] + g * per * 4, per, C.byref(o), ctx.stream))
+                s = engine.summarize(o.as_dict())
+                n = max(s["n"], 1)
+                acc[g] += [s["vz"], s["e"], s["n_valley"][0] / n, s["n_valley"][1] / n, s["n_valley"][2] / n,
+                           s["n_fault"]]
+            n_samples += 1
+    ctx.close()
+    acc /= max(n_samples, 1)
+    return [dict(field_kv_cm=float(-fields[g, 2] / 1e3), vz=float(acc[g, 0]), e=float(acc[g, 1]),
+                 frac_gamma=float(acc[g, 2]), frac_l=float(acc[g, 3]), frac_x=float(acc[g, 4]),
+                 faults=float(acc[g, 5]), particles=per, samples=n_samples) for g in range(n_fields)]
+
+
+def _coupled(mesh_shape, n_global, steps, seed, device, efield=(0.0, 0.0, 0.0), max_sweeps=2000):
+    rank, world = parallel.world_info()
+    first, count = parallel.rank_slice(n_global, rank, world)
+    p = engine.params_from_reference_modules(efield=efield, num_carr=n_global)
+    for a in range(3):
+        p.seg[a] = mesh_shape[a]
+        p.dl[a] = p.tot_dim[a] / mesh_shape[a]
+    p.rho_background = float(-init_.GaAs.dope * p.dl[0] * p.dl[1] * p.dl[2] * 1e6)     # init_.py:189-191
+    ctx = engine.Context(p, device=device)
+    ens = engine.Ensemble(ctx, count, pid_offset=first).init(seed)
+    cs = engine.CoupledStepper(ctx, ens, seed=seed, max_sweeps=max_sweeps).prime()
+    rows = _global_rows(ens, steps, seed, lambda c: cs.step(), ctx.device)
+    sweeps, err = cs.mesh.last_solve()
+    for r in rows:
+        r["sor_sweeps_last"] = sweeps
+    ctx.close()
+    return rows
+
+
+def c3(scale=1.0, steps=50, seed=SEED, device=0):
+    return _coupled((1, 1, 1024), max(1024, int(10_000_000 * scale)), steps, seed, device)
+
+
+def c4(scale=1.0, steps=50, seed=SEED, device=0):
+    return _coupled((1024, 1, 1024), max(4096, int(100_000_000 * scale)), steps, seed, device)
+
+
+def c5(scale=1.0, steps=150, seed=SEED, device=0, field_kv_cm=50.0):
+    rank, world = parallel.world_info()
+    n = max(32, int(125_000_000 * scale))            # per GPU: weak scaling
+    ctx = engine.Context(engine.params_from_reference_modules(efield=(0, 0, -field_kv_cm * 1e3)), device=device)
+    ens = engine.Ensemble(ctx, n, pid_offset=rank * n).init(seed)
+    rows = _global_rows(ens, steps, seed, lambda c: ens.step(c, seed), ctx.device)
+    ctx.close()
+    return rows
+
+
+CONFIGS = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("config", choices=sorted(CONFIGS))
+    ap.add_argument("--scale", type=float, default=0.01)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--json", default=None, help="write the result here")
+    a = ap.parse_args(argv)
+    import os
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    kw = dict(scale=a.scale, device=local)
+    if a.steps is not None:
+        kw["steps"] = a.steps
+    out = CONFIGS[a.config](**kw)
+    if int(os.environ.get("RANK", "0")) == 0:
+        if a.json:
+            json.dump(out, open(a.json, "w"), indent=1)
+        for r in out[-3:] if a.config != "c2" else out:
+            print(r)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,12 +4,12 @@ distribution of |dk|/|k| between the CUDA path and the oracle over 400 000 parti
 timesteps, both consuming the identical Philox stream.  Run once with the default (algebraic)
 scatter path and once with EMC_EXACT_LIBM=1 (every acos/asin/atan composed like the reference).
 
-    python profiles/parity_error_growth.py > profiles/r1_parity_error_growth.txt
+    python tests/tools/parity_error_growth.py > profiles/r1_parity_error_growth.txt
 """
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np  # noqa: E402
