@@ -94,7 +94,8 @@ typedef struct EmcParams {
     double mean_energy;   /* init_.py:145 (in units of kT) */
     /* mesh (init_.py:135-150) */
     int32_t seg[3];       /* cells per axis */
-    int32_t pad_;
+    int32_t z_cyclic;     /* 0 = the reference's specular z walls (main_.py:140-154); 1 = extension for bulk
+                             runs (BASELINE configs[1]): z wraps like x and y (main_.py:125-138) */
     double dl[3];         /* cell size */
     double rho_background;/* init_.py:189-191: -dope*prod(dl)*1e6 per cell */
     double rho_increment; /* poisson_.py:36: dope*vol*1e6/num_carr per super-particle */

@@ -31,7 +31,7 @@ class EmcParams(C.Structure):
         ("mass", C.c_double * 3), ("nonparab", C.c_double * 3), ("tot_dim", C.c_double * 3),
         ("efield", C.c_double * 3), ("e_phonon", C.c_double), ("ion_eb", C.c_double),
         ("kT", C.c_double), ("mean_energy", C.c_double),
-        ("seg", C.c_int32 * 3), ("pad_", C.c_int32), ("dl", C.c_double * 3),
+        ("seg", C.c_int32 * 3), ("z_cyclic", C.c_int32), ("dl", C.c_double * 3),
         ("rho_background", C.c_double), ("rho_increment", C.c_double), ("eps_s", C.c_double),
         ("surf_val", C.c_double),
     ]

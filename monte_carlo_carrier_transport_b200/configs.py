@@ -61,11 +61,14 @@ def field_points(n_fields=24, lo=100.0, hi=50_000.0):
     return np.stack([np.zeros(n_fields), np.zeros(n_fields), -mags], axis=1)
 
 
-def c2(scale=1.0, steps=2500, discard=1000, sample_every=10, seed=SEED, device=0, n_fields=24):
+def c2(scale=1.0, steps=2500, discard=1000, sample_every=10, seed=SEED, device=0, n_fields=24, bulk=True):
     """Velocity-field curve: per field point the time average (after ``discard`` steps) of
     <v_z>, <E> and the valley fractions."""
     per = max(32, int(1_000_000 * scale))
-    ctx = engine.Context(device=device)
+    # "bulk": z wraps like x and y.  With the reference's specular z walls (main_.py:140-154) the
+    # slab is a closed box and every steady-state drift velocity is zero (measured: |<v_z>| < 400 m/s
+    # at all 24 fields after 2 ps), so the bulk curve needs the cyclic-z extension.
+    ctx = engine.Context(engine.params_from_reference_modules(z_cyclic=bulk), device=device)
     fields = field_points(n_fields)
     ctx.set_field_groups(fields, per)
     ens = engine.Ensemble(ctx, per * n_fields).init(seed)

@@ -61,6 +61,7 @@ static void fill_devconst(Ctx *c)
     }
     d.r_hbar = 1 / p.hbar;
     d.r_hbar2 = 1 / d.hbar2;
+    d.z_cyclic = p.z_cyclic != 0;
     d.e_phonon = p.e_phonon;
     d.ion_eb = p.ion_eb;
 }

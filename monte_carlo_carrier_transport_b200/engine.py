@@ -26,7 +26,7 @@ def _torch():
     return torch
 
 
-def params_from_reference_modules(efield=None, num_carr=None):
+def params_from_reference_modules(efield=None, num_carr=None, z_cyclic=False):
     """Snapshot init_.Parameters / init_.GaAs / init_.Device (init_.py:58-157) into EmcParams."""
     from . import init_, scatter_
     P, G, D = init_.Parameters, init_.GaAs, init_.Device
@@ -49,6 +49,7 @@ def params_from_reference_modules(efield=None, num_carr=None):
     p.rho_increment = float((G.dope * D.vol * (100 ** 3) / n_carr)[0])
     p.eps_s = G.eps_0
     p.surf_val = 0.6
+    p.z_cyclic = int(bool(z_cyclic))          # extension: cyclic z for bulk runs (default: specular, like the reference)
     return p
 
 
@@ -73,6 +74,7 @@ def params_from_dict(phys: dict, device: dict | None = None):
     p.rho_increment = dev.get("charge", dev.get("rho_increment", 0.0))
     p.eps_s = phys.get("eps_0", 1.0)
     p.surf_val = dev.get("surf_val", 0.6)
+    p.z_cyclic = int(bool(phys.get("z_cyclic", 0)))
     return p
 
 

@@ -133,7 +133,9 @@ void orc_carrier_drift(const OrcParams *p, double coord[6], const double ef[3], 
     /* main_.py:151-153  reflect until inside (NaN guard added: the reference would spin) */
     double L = p->tot_dim[2];
     int guard = 0;
-    while (!(r_[2] >= 0 && r_[2] <= L) && !isnan(r_[2]) && guard++ < 1000000) {
+    /* extension for bulk runs: z wraps like x and y */
+    if (p->z_cyclic) r_[2] = r_[2] - L * (double)(r_[2] >= L) + L * (double)(r_[2] <= 0);
+    while (!p->z_cyclic && !(r_[2] >= 0 && r_[2] <= L) && !isnan(r_[2]) && guard++ < 1000000) {
         int out = (r_[2] > L) || (r_[2] < 0);
         int in  = (r_[2] > 0) && (r_[2] < L);
         k_[2] = -1 * out * k_[2] + in * k_[2];

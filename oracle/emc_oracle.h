@@ -57,7 +57,7 @@ typedef struct OrcParams {
     int64_t group_size;
     const double *field_groups;
     int32_t seg[3];
-    int32_t pad_;
+    int32_t z_cyclic;     /* extension: 1 = z wraps like x and y instead of the specular walls */
     double dl[3];
     const double *ex, *ey, *ez;
     double kT, mean_energy;   /* init_.py:64,145 (ensemble initialisation) */

@@ -43,7 +43,7 @@ class OrcParams(C.Structure):
         ("mech_sampler", (C.c_int32 * ORC_MAX_MECH) * 3),
         ("field_mode", C.c_int32), ("n_groups", C.c_int32), ("group_size", C.c_int64),
         ("field_groups", C.POINTER(C.c_double)),
-        ("seg", C.c_int32 * 3), ("pad_", C.c_int32), ("dl", C.c_double * 3),
+        ("seg", C.c_int32 * 3), ("z_cyclic", C.c_int32), ("dl", C.c_double * 3),
         ("ex", C.POINTER(C.c_double)), ("ey", C.POINTER(C.c_double)), ("ez", C.POINTER(C.c_double)),
         ("kT", C.c_double), ("mean_energy", C.c_double),
     ]
@@ -153,6 +153,7 @@ class Oracle:
         p.ek = _dp(self.ek)
         p.kT, p.mean_energy = phys.get("kT", 0.02585), phys.get("mean_energy", 0.1)
         p.field_mode = 0
+        p.z_cyclic = int(bool(phys.get("z_cyclic", 0)))
         self.p = p
         self.L = lib()
         self._keep = {}

@@ -302,6 +302,34 @@ def test_field_groups_mode_vs_oracle(ctx, torch_mod):
     compare_states(st, *ens.coords(), np.array(g["tot_dim"]))
 
 
+def test_cyclic_z_extension_vs_oracle(torch_mod):
+    """z_cyclic = 1 (bulk runs): z wraps like x and y instead of reflecting; same flag in the oracle."""
+    from monte_carlo_carrier_transport_b200 import engine
+    g = helpers.golden_params()
+    phys = dict(g["phys"], z_cyclic=1, efield=[0, 0, -50000])
+    c = engine.Context(engine.params_from_dict(phys, g["device"]), device=0, tables=helpers.host_tables())
+    try:
+        import oracle as orc_mod
+        ek, tabs, mech = helpers.host_tables()
+        mech_l = [list(zip(m[1].tolist(), m[2].tolist(), m[3].tolist())) for m in mech]
+        o = orc_mod.Oracle(phys, ek, tabs, mech_l)
+        n = 20000
+        coords, v, dtau = hot_ensemble(n, 37, phys)
+        coords[:, 5] = np.where(np.arange(n) % 2 == 0, 1e-10, phys["tot_dim"][2] - 1e-10)   # hug both z faces
+        st = helpers.state_from_coords(coords, v, dtau)
+        ens = engine.Ensemble(c, n).load(coords, v, dtau)
+        for s in range(5):
+            ens.step(s, 3)
+            o.timestep(st, orc.philox_stream(3, s, 0), threads=4)
+        co, val, dt_ = ens.coords()
+        compare_states(st, co, val, dt_, np.array(phys["tot_dim"]))
+        wrapped = np.abs(co[:, 5] - coords[:, 5]) > 0.5 * phys["tot_dim"][2]
+        assert wrapped.sum() > 100                                   # particles did cross the z faces
+        assert np.array_equal(co[:, 2] < 0, st["kz"] < 0)
+    finally:
+        c.close()
+
+
 def test_observables_kernel(ctx, torch_mod, oracle):
     from monte_carlo_carrier_transport_b200 import engine
     g = helpers.golden_params()["phys"]
