@@ -241,6 +241,40 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
             "segments_last_step": obs["n_segments"]}
 
 
+def other_configs_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=10, warmup=3):
+    """The uncoupled configurations other than configs[1], at their BASELINE sizes, as
+    particle-timesteps/s and fraction of the HBM roofline (120 B per particle-timestep):
+    configs[0] (10^4 electrons: launch-latency bound) and configs[4] (1.25e8 per GPU at 50 kV/cm)."""
+    peak, _ = measured_peak_gbs()
+    out = {}
+    for name, n, ef in (("configs[0] reference default, 1e4 electrons, 5 kV/cm", 10_000, (0, 0, -5000.0)),
+                        ("configs[4] high-field transient, 1.25e8 electrons per GPU, 50 kV/cm", 125_000_000,
+                         (0, 0, -50000.0))):
+        ctx = engine.Context(engine.params_from_reference_modules(efield=ef), device=local)
+        ens = engine.Ensemble(ctx, n, pid_offset=rank * n).init(SEED + 2)
+        for s in range(warmup):
+            ens.step(s, SEED + 2)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for s in range(steps):
+            ens.step(warmup + s, SEED + 2)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=ctx.device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.cpu()[0])
+        o = ens.last_obs()
+        ctx.close()
+        del ens
+        torch.cuda.empty_cache()
+        out[name] = {"ms_per_timestep": ms, "particle_timesteps_per_s": world * n / (ms * 1e-3),
+                     "steps_per_s": world * o["n_segments"] / (ms * 1e-3),
+                     "hbm_frac": ALGO_BYTES_PER_PARTICLE_STEP * n / (ms * 1e-3) / 1e9 / peak}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -324,7 +358,8 @@ def run_ours(args):
 
     h2d_bytes, d2h_bytes = hs.h2d_bytes, hs.d2h_bytes
     del hs
-    coupled =coupled_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
+    coupled = coupled_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
+    by_config = other_configs_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
 
     # ---- max over ranks, totals over ranks ---------------------------------------------------
     t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=ctx.device)
@@ -359,7 +394,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes,
                     "api": "engine.HostStepper.step: pinned host (N,6) coords + valley + dtau in, same out"},
-            "gpu_launches": int(launches), "clocks": clk, "coupled": coupled,
+            "gpu_launches": int(launches), "clocks": clk, "coupled": coupled, "by_config": by_config,
         }
         print(json.dumps(line))
     ctx.close()

@@ -444,13 +444,21 @@ template <class Stream, int FIELD, bool EXACT, bool DEPOSIT>
 static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
     auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     // persistent grid: exactly the blocks that are resident at once (one wave), unless the
-    // ensemble is too small to give every block a full tile
-    int per_sm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FLIGHT_THREADS, smem)) != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
+    // ensemble is too small to give every block a full tile.  The attribute / occupancy queries
+    // are cached per kernel variant and device (they cost tens of microseconds per launch).
+    static size_t cached_smem[16];
+    static int cached_per_sm[16];
+    const int dev = ctx->device & 15;
+    cudaError_t e;
+    if (cached_per_sm[dev] == 0 || cached_smem[dev] != smem) {
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        int q = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k, FLIGHT_THREADS, smem)) != cudaSuccess) return e;
+        cached_per_sm[dev] = q < 1 ? 1 : q;
+        cached_smem[dev] = smem;
+    }
+    const int per_sm = cached_per_sm[dev];
     const int resident = ctx->sm_count * per_sm * ctx->waves;
     if (grid > resident) grid = resident;
     k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
