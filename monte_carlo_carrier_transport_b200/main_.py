@@ -227,6 +227,25 @@ def run(num_carr=None, pts=None, seed=12345, elec_field=None, coords=None, valle
     return (rows, ens, hist) if history else (rows, ens)
 
 
+def script(scat_cond=False, save_cond=False, drift_cond=False, filename="EMC_results.csv", seed=12345):
+    """The reference's module body as a function (main_.py:41-88, 325-461): the three condition
+    flags default to False exactly like the shipped script (main_.py:61-63), in which case only
+    the initialisation runs.  Returns the per-step rows (empty if ``drift_cond`` is False)."""
+    import datetime
+    start = datetime.datetime.now()
+    rows = []
+    if scat_cond or drift_cond:
+        default_context()                      # builds and uploads the scattering tables (main_.py:65-66)
+    if drift_cond:
+        rows, _ens = run(seed=seed)
+        if save_cond:
+            save_rows(rows, filename)
+    total = datetime.datetime.now() - start
+    print("---%s minutes, %s seconds ---" % (int(total.total_seconds() / 60),
+                                            np.round(total.total_seconds() % 60, 3)))   # main_.py:456-461
+    return rows
+
+
 # the reference's spreadsheet columns A..G (main_.py:341, 398-403, 448-454)
 SHEET_COLUMNS = ("Time (ps)", "Average z pos. (nm)", "Average velocity (m/s)", "Average energy (eV)",
                  "Gamma-Valley Population", "L-Valley Population", "X-Valley Population")
@@ -262,3 +281,8 @@ def save_rows(rows, path, num_carr=None, elec_field=None):
         for k, v in inputs.items():
             w.writerow([k, v])
     return path
+
+
+if __name__ == "__main__":      # `python -m monte_carlo_carrier_transport_b200.main_ [--scat] [--drift] [--save]`
+    import sys
+    script(scat_cond="--scat" in sys.argv, drift_cond="--drift" in sys.argv, save_cond="--save" in sys.argv)

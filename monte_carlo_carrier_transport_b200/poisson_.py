@@ -91,3 +91,11 @@ def run_script(coords=None, order=abi.SOR_LEXICOGRAPHIC):
     out = solve(coords[:, 3:6], u0=u0, order=order)
     out["coords"] = coords
     return out
+
+
+if __name__ == "__main__":      # `python -m monte_carlo_carrier_transport_b200.poisson_`: the reference script
+    from timeit import default_timer as timer
+    t0 = timer()
+    res = run_script()
+    print("total time: ", timer() - t0)                              # poisson_.py:44
+    print("sweeps %d, last RMS update %.3g, sum(rho) %.6g" % (res["sweeps"], res["err"], res["rho"].sum()))

@@ -167,3 +167,18 @@ def test_main_run_and_host_arrays(mods, tmp_path):
     rows2, ens2 = main_.run(num_carr=20000, pts=3, seed=9, coords=co, valley=val, dtau=dtau)
     ens.step(0, 9); ens.step(1, 9); ens.step(2, 9)
     assert ens2.last_obs() == ens.last_obs()
+
+
+def test_script_entry_point_like_the_reference(mods, tmp_path, capsys):
+    """main_.py as shipped (all three flags False) only initialises; with the flags flipped it
+    runs the 50-step loop of the default device and writes the per-step table."""
+    init_, scatter_, main_, poisson_ = mods
+    assert main_.script() == []
+    out = str(tmp_path / "EMC.csv")
+    rows = main_.script(scat_cond=True, drift_cond=True, save_cond=True, filename=out)
+    assert len(rows) == init_.Parameters.pts and rows[-1]["n"] == init_.Device.num_carr
+    assert "minutes" in capsys.readouterr().out
+    import csv
+    tab = list(csv.reader(open(out)))
+    assert tuple(tab[0]) == main_.SHEET_COLUMNS and len(tab) == 1 + 50 + 1 + 6
+    assert abs(float(tab[50][3]) - 0.023) < 0.003                       # <E> at step 49, cf. free_running_c1.json
