@@ -237,8 +237,10 @@ static int scatter_stream(const OrcParams *p, double coord[6], int32_t *val, Cur
     double e_np; int32_t idx;
     int f = orc_calc_energy(p, coord, *val, &e_np, &idx);
     if (f >= 0) return f;
-    /* Philox layout: every event starts on draw index 4e of the (particle, timestep) stream, so
-       that block 2e = (r2, azimuth) and block 2e+1 = (polar, flight) or (flight, unused) */
+    /* Philox layout: every event starts on draw index 4e of the (particle, timestep) stream:
+       block 2e = (r2, azimuth), block 2e+1 = (polar, flight).  A self-scattering event draws no
+       polar angle and its azimuth has no effect (sin(polar) = 0), so the flight that follows
+       re-reads the azimuth draw 4e+1 and block 2e+1 is never evaluated. */
     if (c->s->mode == 1) c->draw = (c->draw + 3u) & ~3u;
     double r2 = next_uniform(c);
     int mech = choose_mech(p, *val, idx, r2);
@@ -246,6 +248,7 @@ static int scatter_stream(const OrcParams *p, double coord[6], int32_t *val, Cur
     double r_az = next_uniform(c);
     double r_pol = 0.0;
     if (p->mech_sampler[*val][mech] != ORC_SAMPLER_SELF) r_pol = next_uniform(c);
+    else if (c->s->mode == 1) c->draw -= 1u;      /* the caller's free-flight draw is 4e+1 again */
     return scatter_core(p, coord, val, mech, e_np, r_az, r_pol);
 }
 
