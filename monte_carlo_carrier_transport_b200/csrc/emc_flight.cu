@@ -144,10 +144,16 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 // 16 warps/SM); 192 x 3 (96 registers, 18 warps, spills) 2.22 ms; 256 x 3 (80 registers) 1.72 ms.
 #define EMC_FLIGHT_MIN_BLOCKS 1
 #endif
+#ifndef EMC_STAGE_REFILL
+// 1: cp.async (LDGSTS) the next refill batch into shared memory while the current one is
+// processed, so the refill phase never waits on HBM.  Measured with the L2 prefetch one batch
+// further ahead: 1.387 -> 1.370 ms per 2.4e7-particle timestep.
+#define EMC_STAGE_REFILL 1
+#endif
 #ifndef EMC_PREFETCH_BATCHES
 // refill batches to prefetch ahead into L2 (0 = off).  Measured: 0 -> 1.475 ms, 1 -> 1.409 ms,
 // 2 -> 1.411 ms, 4 -> 1.423 ms per 2.4e7-particle timestep.
-#define EMC_PREFETCH_BATCHES 1
+#define EMC_PREFETCH_BATCHES 2
 #endif
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {
@@ -166,7 +172,36 @@ struct WarpQueues {
     WarpQueue sc;                            // mid-event particles that drew a real mechanism ...
     double sc_enp[QCAP], sc_raz[QCAP];       // ... with E_np (scatter_.py:1069) and the azimuth uniform
     int32_t sc_mech[QCAP];
+#if EMC_STAGE_REFILL
+    double stage[7][32];                     // next refill batch, landed here by cp.async (LDGSTS)
+    int32_t stage_val[32];
+#endif
 };
+
+#if EMC_STAGE_REFILL
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc));
+}
+// each lane stages ITS OWN particle of the batch: slot [lane] is written and later read by the
+// same thread only, so the per-thread cp.async group semantics are all the ordering needed
+__device__ __forceinline__ void stage_batch(WarpQueues &WQ, const FlightArgs &A, int64_t j, int64_t wend, int lane)
+{
+    if (j < wend) {
+        cp_async8(&WQ.stage[0][lane], A.kx + j); cp_async8(&WQ.stage[1][lane], A.ky + j);
+        cp_async8(&WQ.stage[2][lane], A.kz + j); cp_async8(&WQ.stage[3][lane], A.x + j);
+        cp_async8(&WQ.stage[4][lane], A.y + j); cp_async8(&WQ.stage[5][lane], A.z + j);
+        cp_async8(&WQ.stage[6][lane], A.dtau + j); cp_async4(&WQ.stage_val[lane], A.valley + j);
+    }
+    asm volatile("cp.async.commit_group;");
+}
+#endif
 
 struct Particle {
     double kx, ky, kz, x, y, z, dte;
@@ -265,6 +300,9 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     if (wstart > A.n) wstart = A.n;
     const int64_t wend = (wstart + slice < A.n) ? wstart + slice : A.n;
     int64_t next = wstart;
+#if EMC_STAGE_REFILL
+    stage_batch(WQ, A, next + lane, wend, lane);
+#endif
     int qn = 0, qsc = 0;                          // lengths of the event / scatter queues (warp-uniform)
     const double dt = P.dt;
 
@@ -305,11 +343,21 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
             i = next + lane;
             act = i < wend;
+#if EMC_STAGE_REFILL
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
             if (act) {
+#if EMC_STAGE_REFILL
+                p.kx = WQ.stage[0][lane]; p.ky = WQ.stage[1][lane]; p.kz = WQ.stage[2][lane];
+                p.x = WQ.stage[3][lane]; p.y = WQ.stage[4][lane]; p.z = WQ.stage[5][lane];
+                p.dte = WQ.stage[6][lane];
+                p.val = WQ.stage_val[lane];
+#else
                 p.kx = A.kx[i]; p.ky = A.ky[i]; p.kz = A.kz[i];
                 p.x = A.x[i]; p.y = A.y[i]; p.z = A.z[i];
                 p.dte = A.dtau[i];
                 p.val = A.valley[i];
+#endif
                 p.off = (uint32_t)(i - wstart);
                 p.grp = 0;
                 if (REPLAY) s0 = (uint32_t)A.cursor[i];
@@ -326,6 +374,9 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 }
             }
             next += 32;
+#if EMC_STAGE_REFILL
+            stage_batch(WQ, A, next + lane, wend, lane);
+#endif
 #if EMC_PREFETCH_BATCHES > 0
             {   // pull the state rows of a later refill batch into L2 while this one is processed
                 const int64_t j = next + (int64_t)(EMC_PREFETCH_BATCHES - 1) * 32 + lane;
