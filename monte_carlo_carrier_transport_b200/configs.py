@@ -105,7 +105,7 @@ def _coupled(mesh_shape, n_global, steps, seed, device, efield=(0.0, 0.0, 0.0), 
     p.rho_background = float(-init_.GaAs.dope * p.dl[0] * p.dl[1] * p.dl[2] * 1e6)     # init_.py:189-191
     ctx = engine.Context(p, device=device)
     ens = engine.Ensemble(ctx, count, pid_offset=first).init(seed)
-    cs = engine.CoupledStepper(ctx, ens, seed=seed, max_sweeps=max_sweeps).prime()
+    cs = engine.CoupledStepper(ctx, ens, seed=seed, max_sweeps=max_sweeps).prime(max_sweeps=50_000)
     rows = _global_rows(ens, steps, seed, lambda c: cs.step(), ctx.device)
     sweeps, err = cs.mesh.last_solve()
     for r in rows:

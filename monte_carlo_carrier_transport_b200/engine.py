@@ -385,19 +385,21 @@ class CoupledStepper:
         self.tol, self.max_sweeps, self.order, self.group = tol, max_sweeps, order, group
         self.n_steps = 0
 
-    def prime(self):
-        """Field of the initial ensemble (the reference would call poisson() before the loop)."""
+    def prime(self, max_sweeps: int | None = None):
+        """Field of the initial ensemble (the reference would call poisson() before the loop).
+        The cold solve may need far more sweeps than the warm-started ones of the time loop
+        (thousands on a 1024 x 1024 mesh): ``max_sweeps`` overrides the per-step cap here."""
         m = self.mesh
         m.zero_counts()
         m.deposit(self.ens)
-        self._solve()
+        self._solve(max_sweeps)
         return self
 
-    def _solve(self):
+    def _solve(self, max_sweeps: int | None = None):
         m = self.mesh
         m.allreduce(self.group)
         m.to_rho()
-        m.solve_async(tol=self.tol, max_sweeps=self.max_sweeps, order=self.order)
+        m.solve_async(tol=self.tol, max_sweeps=max_sweeps or self.max_sweeps, order=self.order)
         if self.packed_field:
             m.field_packed()
         else:

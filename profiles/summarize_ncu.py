@@ -48,15 +48,21 @@ def launches(path, out):
             v = float(r[vi].replace(",", ""))
         except ValueError:
             continue
-        a = agg.setdefault(r[ki].split("(")[0][-70:], [0, 0.0])
+        a = agg.setdefault(r[ki].split("(")[0][-70:], [0, 0.0, []])
         a[0] += 1
         a[1] += v
+        a[2].append(v)
     tot = sum(a[1] for a in agg.values())
     with open(out, "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
-        f.write("# %-70s %6s %12s %8s\n" % ("kernel", "count", "total_ms", "share"))
+        f.write("# bench.py: <PhiloxStream, 1, ..> = the timed configs[1] step (one launch per timestep, 100 % of it);\n"
+                "# <PhiloxStream, 3, ..> + deposit + mesh_to_rho + sor_rb + field_packed = the coupled sub-benchmark, whose\n"
+                "# ONE cold-start solve (thousands of sweeps, outside the timed loop) dominates sor_rb's total: see median/max\n")
+        f.write("# %-70s %6s %12s %8s %10s %10s\n" % ("kernel", "count", "total_ms", "share", "median_ms", "max_ms"))
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write("%-72s %6d %12.3f %7.1f%%\n" % (k, a[0], a[1] / 1e6, 100 * a[1] / tot))
+            med = sorted(a[2])[len(a[2]) // 2]
+            f.write("%-72s %6d %12.3f %7.1f%% %10.4f %10.4f\n" % (k, a[0], a[1] / 1e6, 100 * a[1] / tot, med / 1e6,
+                                                                   max(a[2]) / 1e6))
     print(open(out).read())
 
 
