@@ -37,19 +37,32 @@ deposit_ngp_kernel(const __grid_constant__ DevConst P, const double *__restrict_
         for (int t = threadIdx.x; t < cells; t += blockDim.x) scount[t] = 0u;
         __syncthreads();
     }
+    // four particles per thread and pass: all twelve position loads are issued before the first
+    // is consumed (the kernel is latency bound: ~100 instructions and one atomic per 24 bytes)
+    constexpr int U = 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int hx[3], hy[3], hz[3];
-        const int nx = axis_hits(x[i], P.seg[0], P.dl[0], P.inv_dl[0], hx);
-        const int ny = axis_hits(y[i], P.seg[1], P.dl[1], P.inv_dl[1], hy);
-        const int nz = axis_hits(z[i], P.seg[2], P.dl[2], P.inv_dl[2], hz);
-        for (int a = 0; a < nx; ++a)
-            for (int b = 0; b < ny; ++b)
-                for (int c = 0; c < nz; ++c) {
-                    const int64_t cell = ((int64_t)hx[a] * P.seg[1] + hy[b]) * P.seg[2] + hz[c];
-                    if (SMEM) atomicAdd(&scount[cell], 1u);
-                    else atomicAdd(mesh + cell, 1ull);
-                }
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+        double px[U], py[U], pz[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) { px[u] = x[i]; py[u] = y[i]; pz[u] = z[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * stride >= n) break;
+            int hx[3], hy[3], hz[3];
+            const int nx = axis_hits(px[u], P.seg[0], P.dl[0], P.inv_dl[0], hx);
+            const int ny = axis_hits(py[u], P.seg[1], P.dl[1], P.inv_dl[1], hy);
+            const int nz = axis_hits(pz[u], P.seg[2], P.dl[2], P.inv_dl[2], hz);
+            for (int a = 0; a < nx; ++a)
+                for (int b = 0; b < ny; ++b)
+                    for (int c = 0; c < nz; ++c) {
+                        const int64_t cell = ((int64_t)hx[a] * P.seg[1] + hy[b]) * P.seg[2] + hz[c];
+                        if (SMEM) atomicAdd(&scount[cell], 1u);
+                        else atomicAdd(mesh + cell, 1ull);
+                    }
+        }
     }
     if (SMEM) {
         __syncthreads();
