@@ -210,8 +210,32 @@ struct Particle {
     int32_t grp;
 };
 
+// padded-mesh index of the cell that holds the particle (nearest-cell gather, EMC_FIELD_MESH*)
+__device__ __forceinline__ int64_t mesh_cell(const DevConst &P, const Particle &p)
+{
+    const int ci = axis_cell(p.x, P.seg[0], P.dl[0], P.inv_dl[0]) + 1;
+    const int cj = axis_cell(p.y, P.seg[1], P.dl[1], P.inv_dl[1]) + 1;
+    const int ck = axis_cell(p.z, P.seg[2], P.dl[2], P.inv_dl[2]) + 1;
+    return ((int64_t)ci * (P.seg[1] + 2) + cj) * (P.seg[2] + 2) + ck;
+}
+
+// The field a flight segment sees depends only on where the segment STARTS, and a scatter event
+// does not move the particle: so the event passes know the cell as soon as a particle is popped
+// and pull its field record towards L1 ~500 instructions before the segment needs it.
 template <int FIELD>
-__device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A, const Particle &p,
+__device__ __forceinline__ void field_prefetch(const FlightArgs &A, int64_t c)
+{
+    if (FIELD == EMC_FIELD_MESH_PACKED) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ex + 4 * c));
+    } else if (FIELD == EMC_FIELD_MESH) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ex + c));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ey + c));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ez + c));
+    }
+}
+
+template <int FIELD>
+__device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A, const Particle &p, int64_t c,
                                          double &efx, double &efy, double &efz)
 {
     if (FIELD == EMC_FIELD_CONSTANT) {
@@ -222,10 +246,6 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
         efz = __ldg(P.field_groups + 3 * p.grp + 2);
     } else {
         // nearest-cell gather from the padded (nx+2,ny+2,nz+2) field of emc_field, V/m -> V/cm
-        const int ci = axis_cell(p.x, P.seg[0], P.dl[0], P.inv_dl[0]) + 1;
-        const int cj = axis_cell(p.y, P.seg[1], P.dl[1], P.inv_dl[1]) + 1;
-        const int ck = axis_cell(p.z, P.seg[2], P.dl[2], P.inv_dl[2]) + 1;
-        const int64_t c = ((int64_t)ci * (P.seg[1] + 2) + cj) * (P.seg[2] + 2) + ck;
         if (FIELD == EMC_FIELD_MESH_PACKED) {     // one 32-B record per cell, already V/cm
             const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
             const double2 a = __ldg(rec), b = __ldg(rec + 1);
@@ -338,6 +358,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         int mech = 0;
         double e_np = 0.0, r_az = 0.0;
         bool act, pend = false, fly = false, park = false, tail = false;
+        constexpr bool MESHF = (FIELD == EMC_FIELD_MESH || FIELD == EMC_FIELD_MESH_PACKED);
+        int64_t cell = 0;                                         // mesh cell of the coming flight segment
         double dt_seg = 0.0;
         if (phase == PH_REFILL) {
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
@@ -366,6 +388,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     while (r >= P.group_size) { r -= P.group_size; ++g; }
                     p.grp = (int32_t)(g >= P.n_groups ? P.n_groups - 1 : g);
                 }
+                if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
                 if (p.val >= 0) {                                 // else frozen after a fault
                     const double dte = p.dte;                     // :361
                     fly = true;
@@ -411,6 +434,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             __syncwarp();
             if (act) {
                 i = wstart + p.off;
+                if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
                 if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
                 else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
                 int v = p.val, f;
@@ -460,7 +484,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         }
         if (fly) {                                                // :367 / :373 / :388
             double efx, efy, efz;
-            field_at<FIELD>(P, A, p, efx, efy, efz);
+            field_at<FIELD>(P, A, p, cell, efx, efy, efz);
             const double dtm = div_const(dt_seg, P.mass[p.val], P.r_mass[p.val]);
             carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             acc.c[4]++;
