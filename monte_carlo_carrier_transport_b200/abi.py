@@ -102,6 +102,14 @@ def load(path: str | None = None):
     if _lib is not None and path is None:
         return _lib
     p = path or LIB_PATH
+    if not os.path.exists(p) and path is None and not os.environ.get("EMC_LIB"):
+        # a fresh checkout: compile the extension once (nvcc, ~1 min); failure is reported below
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as exc:      # noqa: BLE001
+            raise RuntimeError("CUDA extension %s is missing and could not be built (%s); "
+                               "there is no CPU fallback" % (p, exc)) from exc
     if not os.path.exists(p):
         raise RuntimeError(
             "CUDA extension %s is missing: build it with `python -m monte_carlo_carrier_transport_b200.build` "
