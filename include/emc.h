@@ -210,6 +210,17 @@ int emc_soa_to_aos(EmcCtx *ctx, const double *kx, const double *ky, const double
  * independent of the order particles are visited in (and of the number of ranks). */
 int emc_deposit(EmcCtx *ctx, const double *x, const double *y, const double *z, int64_t n,
                 int64_t *mesh, int32_t scheme, void *stream);
+/* Multi-GPU: sum the charge meshes of `world` ranks over NVLink peer memory in ONE kernel
+ * (reduce-scatter + all-gather): this rank sums its 1/world slice over all ranks' input meshes
+ * with peer loads and stores the totals into every rank's output mesh.  in_ptrs / out_ptrs:
+ * HOST arrays of `world` peer-mapped device pointers (e.g. torch symmetric memory), each an
+ * int64 mesh of n_cells rounded up to an even count, 16-byte aligned; index = rank.  The caller
+ * orders the launch between two cross-rank barriers (inputs complete before, outputs read
+ * after); the kernel itself never waits on another GPU.  Integer sums: bit-exact. */
+#define EMC_MAX_PEERS 16
+int emc_mesh_allreduce_p2p(EmcCtx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs,
+                           int32_t world, int32_t rank, int64_t n_cells, void *stream);
+
 /* rho_pad (device, (nx+2,ny+2,nz+2), zero halo as np.pad at poisson_.py:53).  NGP: background
  * then `count` sequential += increment (poisson_.py:27,36: bit-identical to the reference's
  * accumulation).  CIC: background + increment * mesh/2^32. */

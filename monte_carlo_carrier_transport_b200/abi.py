@@ -82,6 +82,7 @@ SIGNATURES = {
     "emc_mesh_to_rho": (C.c_int, [_vp, _lp, _i32, _dp, _vp]),
     "emc_poisson_sor": (C.c_int, [_vp, _dp, _dp, _f64, _f64, _i32, _i32, C.POINTER(_i32),
                                   C.POINTER(_f64), _dp, _vp]),
+    "emc_mesh_allreduce_p2p": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp]),
     "emc_field_packed": (C.c_int, [_vp, _dp, _dp, _vp]),
     "emc_poisson_last": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_f64), _vp]),
     "emc_field": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _vp]),

@@ -421,6 +421,19 @@ extern "C" int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad
                            (cudaStream_t)stream);
 }
 
+extern "C" int emc_mesh_allreduce_p2p(EmcCtx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs,
+                                      int32_t world, int32_t rank, int64_t n_cells, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!in_ptrs || !out_ptrs || world < 1 || world > EMC_MAX_PEERS || rank < 0 || rank >= world || n_cells < 1)
+        return fail(c, EMC_ERR_INVALID, "emc_mesh_allreduce_p2p: bad argument");
+    for (int p = 0; p < world; ++p)
+        if (!in_ptrs[p] || !out_ptrs[p] || ((uintptr_t)in_ptrs[p] & 15) || ((uintptr_t)out_ptrs[p] & 15))
+            return fail(c, EMC_ERR_INVALID, "emc_mesh_allreduce_p2p: null or unaligned peer pointer");
+    cudaError_t e = launch_mesh_allreduce_p2p(c, in_ptrs, out_ptrs, world, rank, n_cells, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "mesh_allreduce_p2p launch");
+}
+
 extern "C" int emc_field_packed(EmcCtx *ctx, const double *u_pad, double *e4, void *stream)
 {
     CTX_OR_FAIL(ctx);

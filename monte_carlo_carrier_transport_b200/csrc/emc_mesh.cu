@@ -138,6 +138,56 @@ cudaError_t launch_deposit(Ctx *ctx, const double *x, const double *y, const dou
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// charge-mesh all-reduce over NVLink peer memory (one kernel: reduce-scatter + all-gather)
+//
+// Every rank owns one slice of the mesh: it SUMS that slice over all ranks' input meshes with
+// peer loads and writes the total into every rank's output mesh with peer stores.  Inputs are
+// complete before the launch and outputs are read after it (the caller brackets the launch with
+// a symmetric-memory barrier), so the kernel itself never waits on another GPU.  int64 sums:
+// bit-exact and independent of rank count and order.
+// ------------------------------------------------------------------------------------------
+struct PeerMeshes {
+    const longlong2 *in[EMC_MAX_PEERS];
+    longlong2 *out[EMC_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(256)
+mesh_allreduce_p2p_kernel(const __grid_constant__ PeerMeshes M, int world, int64_t first2, int64_t count2)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count2; t += stride) {
+        const int64_t c = first2 + t;
+        longlong2 s = make_longlong2(0, 0);
+        for (int p = 0; p < world; ++p) {
+            const longlong2 v = M.in[p][c];
+            s.x += v.x;
+            s.y += v.y;
+        }
+        for (int p = 0; p < world; ++p) M.out[p][c] = s;
+    }
+}
+
+cudaError_t launch_mesh_allreduce_p2p(Ctx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs, int world,
+                                      int rank, int64_t n_cells, cudaStream_t st)
+{
+    PeerMeshes M;
+    for (int p = 0; p < world; ++p) {
+        M.in[p] = reinterpret_cast<const longlong2 *>(in_ptrs[p]);
+        M.out[p] = reinterpret_cast<longlong2 *>(out_ptrs[p]);
+    }
+    const int64_t pairs = (n_cells + 1) / 2;                 // meshes are padded to an even cell count
+    const int64_t per = (pairs + world - 1) / world;
+    const int64_t first = (int64_t)rank * per;
+    const int64_t count = first >= pairs ? 0 : (first + per > pairs ? pairs - first : per);
+    if (count == 0) return cudaSuccess;
+    int grid = (int)((count + 255) / 256);
+    if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+    ctx->launches++;
+    mesh_allreduce_p2p_kernel<<<grid, 256, 0, st>>>(M, world, first, count);
+    return cudaGetLastError();
+}
+
 // rho_pad: zero halo (np.pad, poisson_.py:53); interior = background + charge
 __global__ void mesh_to_rho_kernel(const __grid_constant__ DevConst P, const long long *__restrict__ mesh, int scheme,
                                    double background, double increment, double *rho_pad)

@@ -283,11 +283,25 @@ def summarize(obs: dict) -> dict:
 class Mesh:
     """Device-resident charge mesh, rho, potential and field of one Context's geometry."""
 
-    def __init__(self, ctx: Context, scheme: int = abi.DEPOSIT_NGP):
+    def __init__(self, ctx: Context, scheme: int = abi.DEPOSIT_NGP, p2p_group=None):
+        """``p2p_group``: a torch.distributed process group (or ``True`` for the default group)
+        whose ranks share one node: the charge mesh is then placed in NVLink symmetric memory and
+        ``allreduce`` runs this package's own one-kernel reduce-scatter + all-gather over peer
+        pointers (``emc_mesh_allreduce_p2p``) instead of an NCCL all-reduce."""
         torch = _torch()
         self.ctx, self.scheme = ctx, scheme
         nx, ny, nz = ctx.seg
-        self.counts = torch.zeros(nx * ny * nz, dtype=torch.int64, device=ctx.device)
+        cells = nx * ny * nz
+        self.p2p = None
+        self.p2p_error = None
+        if p2p_group is not None and p2p_group is not False:
+            try:
+                self._setup_p2p(cells, p2p_group)
+            except Exception as exc:      # noqa: BLE001  (no symmetric memory on this system: NCCL path)
+                self.p2p, self.p2p_error = None, repr(exc)
+        if self.p2p is None:
+            self.counts = torch.zeros(cells, dtype=torch.int64, device=ctx.device)
+            self.total = self.counts                       # after allreduce(): summed in place
         pad = ctx.padded_shape
         self.rho_pad = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.u_pad = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
@@ -315,14 +329,44 @@ class Mesh:
         p = ens._ptrs()
         c.check(c.lib.emc_deposit(c.h, p[3], p[4], p[5], ens.n, self.counts.data_ptr(), self.scheme, c.stream))
 
+    def _setup_p2p(self, cells: int, group):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        torch = _torch()
+        if group is True:
+            group = dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2:
+            raise RuntimeError("single rank: nothing to reduce")
+        if world > 16:
+            raise RuntimeError("more than EMC_MAX_PEERS ranks")
+        even = cells + (cells & 1)
+        buf = symm.empty((2, even), dtype=torch.int64, device=self.ctx.device)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, group)
+        base = [int(p) for p in hdl.buffer_ptrs]
+        self.p2p = dict(hdl=hdl, world=world, rank=rank, cells=cells, buf=buf,
+                        in_ptrs=(C.c_void_p * world)(*base),
+                        out_ptrs=(C.c_void_p * world)(*[b + even * 8 for b in base]))
+        self.counts = buf[0, :cells]          # this rank's deposits
+        self.total = buf[1, :cells]           # sum over the ranks, written by all peers
+
     def allreduce(self, group=None):
-        """Sum the integer charge mesh over ranks (NCCL over NVLink; gloo on CPU tests)."""
+        """Sum the integer charge mesh over the ranks; the result is ``self.total``.  NVLink peer
+        memory kernel when the mesh lives in symmetric memory, else NCCL (gloo in CPU tests)."""
+        if self.p2p is not None:
+            c, p = self.ctx, self.p2p
+            p["hdl"].barrier(channel=0)                      # every rank's deposits are complete
+            c.check(c.lib.emc_mesh_allreduce_p2p(c.h, p["in_ptrs"], p["out_ptrs"], p["world"], p["rank"],
+                                                 p["cells"], c.stream))
+            p["hdl"].barrier(channel=1)                      # every peer has written its slice of my totals
+            return
         from . import parallel
         parallel.allreduce_counts(self.counts, group)
 
     def to_rho(self):
         c = self.ctx
-        c.check(c.lib.emc_mesh_to_rho(c.h, self.counts.data_ptr(), self.scheme, self.rho_pad.data_ptr(), c.stream))
+        c.check(c.lib.emc_mesh_to_rho(c.h, self.total.data_ptr(), self.scheme, self.rho_pad.data_ptr(), c.stream))
 
     def solve(self, omega0: float = 1.5, tol: float = 1e-6, max_sweeps: int = 10000,
               order: int = abi.SOR_RED_BLACK, history: bool = False):
