@@ -236,6 +236,9 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
     t = [float(v) for v in t.cpu()]
     return {"metric": "ms per coupled MC+Poisson timestep", "ms_per_timestep": t[0], "flight_deposit_ms": t[1],
             "charge_allreduce_ms": t[2], "rho_sor_field_ms": t[3], "sor_sweeps_last_step": sweeps[-1],
+            "charge_allreduce": ("none (1 rank)" if world == 1 else
+                                 "emc_mesh_allreduce_p2p over NVLink symmetric memory" if cs.mesh.p2p is not None
+                                 else "NCCL all_reduce (%s)" % (cs.mesh.p2p_error or "EMC_P2P=0")),
             "sor_sweeps_cold_start": prime_sweeps, "ms_per_timestep_mean": float(np.mean(per)),
             "mesh": "x".join(str(v) for v in COUPLED_MESH), "particles_per_gpu": n, "n_gpus": world,
             "steps": steps, "warmup": warmup, "gpu_launches": int(launches),

@@ -425,7 +425,17 @@ class CoupledStepper:
         self.packed_field = packed_field
         self.field_mode = abi.FIELD_MESH_PACKED if packed_field else abi.FIELD_MESH
         self.ctx, self.ens, self.seed = ctx, ens, seed
-        self.mesh = mesh or Mesh(ctx)
+        if mesh is None:
+            # multi-rank runs on large meshes sum the charge with the NVLink peer-memory kernel
+            # (measured 0.050 vs 0.069 ms NCCL for 1024x1024 at 8 GPUs; on small meshes the two
+            # barriers cost more than NCCL's latency).  EMC_P2P=0 forces NCCL.
+            import os
+            from . import parallel
+            _rank, world = parallel.world_info(group)
+            cells = ctx.seg[0] * ctx.seg[1] * ctx.seg[2]
+            want = world > 1 and cells >= 65536 and os.environ.get("EMC_P2P", "1") != "0"
+            mesh = Mesh(ctx, p2p_group=(group if group is not None else True) if want else None)
+        self.mesh = mesh
         self.tol, self.max_sweeps, self.order, self.group = tol, max_sweeps, order, group
         self.n_steps = 0
 
