@@ -60,7 +60,8 @@ enum { EMC_FAULT_NAN = 0,        /* scatter_.py:45  "Nan energy" */
        EMC_FAULT_DOMAIN = 3,     /* NaN final state (arcsin/arccos/sqrt domain), the reference propagates NaN */
        EMC_FAULT_NEG_ENERGY = 4, /* E0 + dE < 0 -> sqrt(negative) at scatter_.py:1071 */
        EMC_FAULT_ZERO_K = 5,     /* scatter_.py:1079 exact-zero component */
-       EMC_FAULT_STREAM = 6 };   /* replay stream exhausted */
+       EMC_FAULT_STREAM = 6,     /* replay stream exhausted */
+       EMC_FAULT_OUTSIDE = 7 };  /* init_.where_am_i raised "Point is outside all layers" (init_.py:46,56) */
 
 /* charge assignment schemes */
 enum { EMC_DEPOSIT_NGP = 0,      /* poisson_.py:30-38 (inclusive box test, face hits count twice) */
@@ -103,6 +104,20 @@ typedef struct EmcParams {
     double surf_val;      /* Dirichlet value of the z-min face, poisson_.py:51-52 */
 } EmcParams;
 
+/* One init_.Layer (init_.py:15-34) with the per-material numbers the particle loop reads through
+ * `mat[mat_i]` / `scat_tables[mat_i]` (main_.py:366-396): a multi-layer device stacks layers
+ * along z and init_.where_am_i (init_.py:36-56) picks the layer of a particle from its z. */
+#define EMC_MAX_LAYERS 4
+typedef struct EmcLayer {
+    double lz;            /* Layer.lz: thickness along z [m] */
+    double mass[3];       /* matl.mass */
+    double nonparab[3];   /* matl.nonparab */
+    double e_phonon;      /* matl.E_phonon */
+    double ion_eb;        /* scatter_.py:868-869 with matl.dope */
+    double init_weight;   /* share of the initial ensemble placed in this layer by emc_init_ensemble
+                             (extension; all weights 0 = the reference's uniform z, init_.py:200) */
+} EmcLayer;
+
 /* Ensemble observables of one timestep (main_.py:394-403), as raw sums so that
  * ranks can be combined with an integer/double all-reduce. */
 typedef struct EmcObs {
@@ -136,6 +151,26 @@ int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy,
                       const double *cum0, const double *cum1, const double *cum2,
                       const int32_t n_mech[3], const double *dE, const int32_t *trans,
                       const int32_t *sampler);
+
+/* Multi-layer devices (dev.layers, init_.py:127-130; main_.py:366,372,377,387,393 look the layer
+ * up with where_am_i before every drift, scatter and observable).  emc_set_layers replaces the
+ * single material of EmcParams by n_layers (1..EMC_MAX_LAYERS) stacked layers; the tables of each
+ * layer (scat_tables[mat_i], main_.py:66) are then uploaded with emc_upload_tables_layer, same
+ * arguments as emc_upload_tables plus the layer index; all layers share one energy grid and the
+ * per-valley column counts.  sum(lz) should equal EmcParams.tot_dim[2]; a particle whose z falls
+ * outside every layer (where_am_i raises) is frozen with EMC_FAULT_OUTSIDE. */
+int emc_set_layers(EmcCtx *ctx, const EmcLayer *layers, int32_t n_layers);
+int emc_upload_tables_layer(EmcCtx *ctx, int32_t layer, const double *ek, int32_t n_energy,
+                            const double *cum0, const double *cum1, const double *cum2,
+                            const int32_t n_mech[3], const double *dE, const int32_t *trans,
+                            const int32_t *sampler);
+/* Material (layer) used by the single-function batches emc_calc_energy / emc_scatter: the `mat` /
+ * `mat_i` argument of scatter_.calc_energy (scatter_.py:19) and scatter_.scatter (:986).  Default 0. */
+int emc_select_layer(EmcCtx *ctx, int32_t layer);
+/* Background charge per z-cell for emc_mesh_to_rho (extension for doping profiles: the reference
+ * has one uniform background, init_.py:189-191).  HOST pointer to nz doubles; NULL restores the
+ * uniform EmcParams.rho_background. */
+int emc_set_background_profile(EmcCtx *ctx, const double *background_z, int32_t nz);
 
 /* constant field (V/cm) used by EMC_FIELD_CONSTANT; replaces EmcParams.efield */
 int emc_set_efield(EmcCtx *ctx, const double efield[3]);

@@ -12,6 +12,7 @@ import ctypes as C
 import os
 
 EMC_MAX_MECH = 16
+EMC_MAX_LAYERS = 4
 ABI_VERSION = 1
 
 # enums of include/emc.h
@@ -19,7 +20,7 @@ FIELD_CONSTANT, FIELD_GROUPS, FIELD_MESH, FIELD_MESH_PACKED = 0, 1, 2, 3
 DEPOSIT_NGP, DEPOSIT_CIC = 0, 1
 SOR_LEXICOGRAPHIC, SOR_RED_BLACK = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_NO_TABLES, ERR_DIVERGED, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
-FAULT_NAMES = ["nan", "zero_energy", "no_mechanism", "domain", "negative_energy", "zero_k", "stream"]
+FAULT_NAMES = ["nan", "zero_energy", "no_mechanism", "domain", "negative_energy", "zero_k", "stream", "outside"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EMC_LIB") or os.path.join(_HERE, "libemc_b200.so")   # EMC_LIB: tuning variants
@@ -34,6 +35,13 @@ class EmcParams(C.Structure):
         ("seg", C.c_int32 * 3), ("z_cyclic", C.c_int32), ("dl", C.c_double * 3),
         ("rho_background", C.c_double), ("rho_increment", C.c_double), ("eps_s", C.c_double),
         ("surf_val", C.c_double),
+    ]
+
+
+class EmcLayer(C.Structure):
+    _fields_ = [
+        ("lz", C.c_double), ("mass", C.c_double * 3), ("nonparab", C.c_double * 3),
+        ("e_phonon", C.c_double), ("ion_eb", C.c_double), ("init_weight", C.c_double),
     ]
 
 
@@ -64,6 +72,10 @@ SIGNATURES = {
     "emc_last_error": (C.c_char_p, [_vp]),
     "emc_launch_count": (_i64, [_vp]),
     "emc_upload_tables": (C.c_int, [_vp, _dp, _i32, _dp, _dp, _dp, _ip, _dp, _ip, _ip]),
+    "emc_set_layers": (C.c_int, [_vp, C.POINTER(EmcLayer), _i32]),
+    "emc_upload_tables_layer": (C.c_int, [_vp, _i32, _dp, _i32, _dp, _dp, _dp, _ip, _dp, _ip, _ip]),
+    "emc_select_layer": (C.c_int, [_vp, _i32]),
+    "emc_set_background_profile": (C.c_int, [_vp, _dp, _i32]),
     "emc_set_efield": (C.c_int, [_vp, _dp]),
     "emc_set_field_groups": (C.c_int, [_vp, _dp, _i32, _i64]),
     "emc_init_ensemble": (C.c_int, [_vp] + [_dp] * 7 + [_ip, _i64, _u64, _u64, _vp]),

@@ -8,8 +8,10 @@ through the C-ABI; nothing here falls back to the CPU.
 
   c1  reference default run: 10^4 electrons, E = (0,0,-5) kV/cm, 50 steps of 2 fs
   c2  bulk velocity-field sweep, 24 points 0.1-50 kV/cm, 10^6 electrons per point, one ensemble
-  c3  quasi-1-D slab (nx = ny = 1, nz = 1024), 10^7 super-particles, Poisson every timestep
-      (uniform doping: the reference wires no doping profile)
+  c3  1-D n+-n-n+ diode (nx = ny = 1, nz = 1024): three layers 300/300/300 nm doped
+      1e17/1e16/1e17 cm^-3, each with its own scattering tables (init_.where_am_i picks the layer
+      of a particle, main_.py:366-396), per-layer background charge, 10^7 super-particles placed
+      in proportion to the doping, Poisson every timestep
   c4  self-consistent run on a 1024 x 1 x 1024 mesh, 10^8 particles over the ranks,
       NCCL all-reduce of the integer charge mesh every timestep
   c5  high-field multivalley transient, 10^9 particles weak-scaled (1.25e8 per GPU), 50 kV/cm
@@ -95,15 +97,37 @@ def c2(scale=1.0, steps=2500, discard=1000, sample_every=10, seed=SEED, device=0
                  faults=float(acc[g, 5]), particles=per, samples=n_samples) for g in range(n_fields)]
 
 
-def _coupled(mesh_shape, n_global, steps, seed, device, efield=(0.0, 0.0, 0.0), max_sweeps=2000):
+def diode_layers(dopes=(1e17, 1e16, 1e17), lz=(300e-9, 300e-9, 300e-9)):
+    """n+-n-n+ stack along z: one ``init_.Layer`` per region, each with its own material class
+    (a GaAs subclass carrying the region's doping, which drives the ionized-impurity and
+    carrier-carrier rates and the impurity angle: scatter_.py:619-623, 646, 868)."""
+    L0 = init_.Device.layer0
+    mats = {}
+    out = []
+    for d, t in zip(dopes, lz):
+        m = init_.GaAs if d == init_.GaAs.dope else mats.setdefault(d, type("GaAs_%g" % d, (init_.GaAs,), dict(dope=d)))
+        out.append(init_.Layer(m, d, L0.lx, L0.ly, t))
+    return out
+
+
+def _coupled(mesh_shape, n_global, steps, seed, device, efield=(0.0, 0.0, 0.0), max_sweeps=2000, layers=None):
     rank, world = parallel.world_info()
     first, count = parallel.rank_slice(n_global, rank, world)
     p = engine.params_from_reference_modules(efield=efield, num_carr=n_global)
     for a in range(3):
         p.seg[a] = mesh_shape[a]
         p.dl[a] = p.tot_dim[a] / mesh_shape[a]
-    p.rho_background = float(-init_.GaAs.dope * p.dl[0] * p.dl[1] * p.dl[2] * 1e6)     # init_.py:189-191
+    cell = p.dl[0] * p.dl[1] * p.dl[2]
+    p.rho_background = float(-init_.GaAs.dope * cell * 1e6)     # init_.py:189-191
+    if layers is not None:
+        # one charge per super-particle: all dopant charge of the stack / num_carr (init_.py:153-157 summed)
+        p.rho_increment = float(sum(l.dope * l.lx * l.ly * l.lz * 1e6 for l in layers) / n_global)
     ctx = engine.Context(p, device=device)
+    if layers is not None:
+        ctx.set_layers(layers, init_weights=[l.dope * l.lz for l in layers])
+        zc = (np.arange(mesh_shape[2]) + 0.5) * p.dl[2]
+        dope_z = np.array([layers[init_.where_am_i(layers, z)["current_layer"]].dope for z in zc])
+        ctx.set_background_profile(-dope_z * cell * 1e6)
     ens = engine.Ensemble(ctx, count, pid_offset=first).init(seed)
     cs = engine.CoupledStepper(ctx, ens, seed=seed, max_sweeps=max_sweeps).prime(max_sweeps=50_000)
     rows = _global_rows(ens, steps, seed, lambda c: cs.step(), ctx.device)
@@ -114,8 +138,9 @@ def _coupled(mesh_shape, n_global, steps, seed, device, efield=(0.0, 0.0, 0.0), 
     return rows
 
 
-def c3(scale=1.0, steps=50, seed=SEED, device=0):
-    return _coupled((1, 1, 1024), max(1024, int(10_000_000 * scale)), steps, seed, device)
+def c3(scale=1.0, steps=50, seed=SEED, device=0, uniform=False):
+    return _coupled((1, 1, 1024), max(1024, int(10_000_000 * scale)), steps, seed, device,
+                    layers=None if uniform else diode_layers())
 
 
 def c4(scale=1.0, steps=50, seed=SEED, device=0):

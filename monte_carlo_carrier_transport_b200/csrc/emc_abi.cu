@@ -45,14 +45,33 @@ static void fill_devconst(Ctx *c)
     d.q = p.q;
     d.half_q = 0.5 * p.q;
     d.hbar2 = p.hbar * p.hbar;
+    for (int l = 0; l < c->dc.n_layers; ++l) {
+        Mat &m = d.mat[l];
+        const EmcLayer &L = c->layers[l];
+        for (int v = 0; v < 3; ++v) {
+            m.mass[v] = L.mass[v];
+            m.den[v] = 2 * L.mass[v] * p.q;     // (2*m)*q
+            m.four_a[v] = 4 * L.nonparab[v];
+            m.two_a[v] = 2 * L.nonparab[v];
+            m.r_den[v] = 1 / m.den[v];
+            m.r_two_a[v] = 1 / m.two_a[v];
+            m.r_mass[v] = 1 / L.mass[v];
+        }
+        m.e_phonon = L.e_phonon;
+        m.ion_eb = L.ion_eb;
+        d.layer_lz[l] = L.lz;
+    }
+    {   // cumulative shares of the initial ensemble (all weights 0: uniform z like init_.py:200)
+        double tot = 0.0, run = 0.0;
+        for (int l = 0; l < c->dc.n_layers; ++l) tot += c->layers[l].init_weight;
+        for (int l = 0; l < EMC_MAX_LAYERS; ++l) d.layer_cw[l] = 0.0;
+        if (tot > 0)
+            for (int l = 0; l < c->dc.n_layers; ++l) {
+                run += c->layers[l].init_weight;
+                d.layer_cw[l] = (l == c->dc.n_layers - 1) ? 1.0 : run / tot;
+            }
+    }
     for (int v = 0; v < 3; ++v) {
-        d.mass[v] = p.mass[v];
-        d.den[v] = 2 * p.mass[v] * p.q;         // (2*m)*q
-        d.four_a[v] = 4 * p.nonparab[v];
-        d.two_a[v] = 2 * p.nonparab[v];
-        d.r_den[v] = 1 / d.den[v];
-        d.r_two_a[v] = 1 / d.two_a[v];
-        d.r_mass[v] = 1 / p.mass[v];
         d.inv_dl[v] = 1 / p.dl[v];
         d.tot_dim[v] = p.tot_dim[v];
         d.efield[v] = p.efield[v];
@@ -62,8 +81,19 @@ static void fill_devconst(Ctx *c)
     d.r_hbar = 1 / p.hbar;
     d.r_hbar2 = 1 / d.hbar2;
     d.z_cyclic = p.z_cyclic != 0;
-    d.e_phonon = p.e_phonon;
-    d.ion_eb = p.ion_eb;
+}
+
+// the single layer EmcParams describes (init_.py:127: layers = [layer0])
+static void default_layer(Ctx *c)
+{
+    const EmcParams &p = c->params;
+    EmcLayer &L = c->layers[0];
+    std::memset(&L, 0, sizeof(L));
+    L.lz = p.tot_dim[2];
+    for (int v = 0; v < 3; ++v) { L.mass[v] = p.mass[v]; L.nonparab[v] = p.nonparab[v]; }
+    L.e_phonon = p.e_phonon;
+    L.ion_eb = p.ion_eb;
+    c->dc.n_layers = 1;
 }
 
 extern "C" int emc_abi_version(void) { return EMC_ABI_VERSION; }
@@ -97,6 +127,8 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
     c->device = device;
     std::memset(&c->dc, 0, sizeof(c->dc));
     std::memset(&c->mech, 0, sizeof(c->mech));
+    std::memset(c->mech_layers, 0, sizeof(c->mech_layers));
+    default_layer(c);
     fill_devconst(c);
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) goto fail_cuda_create;
@@ -131,8 +163,11 @@ extern "C" void emc_destroy(EmcCtx *ctx)
     if (!ctx) return;
     Ctx *c = &ctx->c;
     cudaSetDevice(c->device);
-    for (int v = 0; v < 3; ++v)
-        if (c->d_cum[v]) cudaFree(c->d_cum[v]);
+    for (int l = 0; l < EMC_MAX_LAYERS; ++l)
+        for (int v = 0; v < 3; ++v)
+            if (c->d_cum_layers[l][v]) cudaFree(c->d_cum_layers[l][v]);
+    if (c->d_mech_layers) cudaFree(c->d_mech_layers);
+    if (c->d_background_z) cudaFree(c->d_background_z);
     if (c->d_groups) cudaFree(c->d_groups);
     if (c->partials) cudaFree(c->partials);
     if (c->ticket) cudaFree(c->ticket);
@@ -151,11 +186,11 @@ extern "C" const char *emc_last_error(const EmcCtx *ctx)
 
 extern "C" int64_t emc_launch_count(const EmcCtx *ctx) { return ctx ? ctx->c.launches : 0; }
 
-extern "C" int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy, const double *cum0,
-                                 const double *cum1, const double *cum2, const int32_t n_mech[3],
-                                 const double *dE, const int32_t *trans, const int32_t *sampler)
+static int upload_tables_layer(Ctx *c, int layer, const double *ek, int32_t n_energy, const double *cum0,
+                               const double *cum1, const double *cum2, const int32_t n_mech[3],
+                               const double *dE, const int32_t *trans, const int32_t *sampler)
 {
-    CTX_OR_FAIL(ctx);
+    if (layer < 0 || layer >= c->dc.n_layers) return fail(c, EMC_ERR_INVALID, "upload_tables: layer out of range");
     if (!ek || !cum0 || !cum1 || !cum2 || !n_mech || !dE || !trans || !sampler || n_energy < 3)
         return fail(c, EMC_ERR_INVALID, "emc_upload_tables: null argument or n_energy < 3");
     // the kernel regenerates the grid as i*step (np.linspace with start 0): verify that is what we were given
@@ -173,6 +208,13 @@ extern "C" int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy
                 return fail(c, EMC_ERR_INVALID, "mechanism metadata out of range");
         }
     }
+    // all layers share the energy grid and the column counts (one DevConst.n_mech / ek_step)
+    for (int l = 0; l < c->dc.n_layers; ++l) {
+        if (l == layer || !c->layer_tables[l]) continue;
+        if (c->dc.n_energy != n_energy || c->dc.ek_step != step || c->dc.e_max != ek[n_energy - 1] ||
+            c->dc.n_mech[0] != n_mech[0] || c->dc.n_mech[1] != n_mech[1] || c->dc.n_mech[2] != n_mech[2])
+            return fail(c, EMC_ERR_UNSUPPORTED, "all layers must share the energy grid and the per-valley column counts");
+    }
     // fast mechanism selection needs even-length (16-B aligned) rows of <= 12 columns that are
     // non-decreasing and NaN-free (choose_mech in emc_device.cuh); anything else is scanned literally
     int literal = 0;
@@ -184,29 +226,104 @@ extern "C" int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy
                 if (std::isnan(row[j]) || (j > 0 && row[j] < row[j - 1])) { literal = 1; break; }
         }
     }
-    c->dc.literal_scan = literal;
+    bool others = false;
+    for (int l = 0; l < c->dc.n_layers; ++l) others = others || (l != layer && c->layer_tables[l]);
+    c->dc.literal_scan = (others ? c->dc.literal_scan : 0) | literal;
     for (int v = 0; v < 3; ++v) {
         const size_t bytes = sizeof(double) * (size_t)n_energy * (size_t)n_mech[v];
-        if (c->d_cum[v]) { cudaFree(c->d_cum[v]); c->d_cum[v] = nullptr; }
-        cudaError_t e = cudaMalloc(&c->d_cum[v], bytes + sizeof(double) * EMC_MAX_MECH);   // + one padding row
+        double *&dst = c->d_cum_layers[layer][v];
+        if (dst) { cudaFree(dst); dst = nullptr; }
+        cudaError_t e = cudaMalloc(&dst, bytes + sizeof(double) * EMC_MAX_MECH);   // + one padding row
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(table)");
-        e = cudaMemset(c->d_cum[v], 0, bytes + sizeof(double) * EMC_MAX_MECH);
+        e = cudaMemset(dst, 0, bytes + sizeof(double) * EMC_MAX_MECH);
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemset(table)");
-        e = cudaMemcpy(c->d_cum[v], cum[v], bytes, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(dst, cum[v], bytes, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(table)");
-        c->dc.cum[v] = c->d_cum[v];
+        c->dc.mat[layer].cum[v] = dst;
         c->dc.n_mech[v] = n_mech[v];
         for (int j = 0; j < EMC_MAX_MECH; ++j) {
-            c->mech.dE[v][j] = dE[v * EMC_MAX_MECH + j];
-            c->mech.trans[v][j] = trans[v * EMC_MAX_MECH + j];
-            c->mech.sampler[v][j] = sampler[v * EMC_MAX_MECH + j];
+            c->mech_layers[layer].dE[v][j] = dE[v * EMC_MAX_MECH + j];
+            c->mech_layers[layer].trans[v][j] = trans[v * EMC_MAX_MECH + j];
+            c->mech_layers[layer].sampler[v][j] = sampler[v * EMC_MAX_MECH + j];
         }
+    }
+    if (layer == 0) c->mech = c->mech_layers[0];
+    if (!c->d_mech_layers) {
+        cudaError_t e = cudaMalloc(&c->d_mech_layers, sizeof(c->mech_layers));
+        if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(mech_layers)");
+    }
+    {
+        cudaError_t e = cudaMemcpy(c->d_mech_layers, c->mech_layers, sizeof(c->mech_layers), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(mech_layers)");
     }
     c->dc.n_energy = n_energy;
     c->dc.ek_step = step;
     c->dc.inv_ek_step = 1 / step;
     c->dc.e_max = ek[n_energy - 1];
+    c->layer_tables[layer] = true;
     c->have_tables = true;
+    for (int l = 0; l < c->dc.n_layers; ++l) c->have_tables = c->have_tables && c->layer_tables[l];
+    return EMC_OK;
+}
+
+extern "C" int emc_upload_tables(EmcCtx *ctx, const double *ek, int32_t n_energy, const double *cum0,
+                                 const double *cum1, const double *cum2, const int32_t n_mech[3],
+                                 const double *dE, const int32_t *trans, const int32_t *sampler)
+{
+    CTX_OR_FAIL(ctx);
+    return upload_tables_layer(c, 0, ek, n_energy, cum0, cum1, cum2, n_mech, dE, trans, sampler);
+}
+
+extern "C" int emc_upload_tables_layer(EmcCtx *ctx, int32_t layer, const double *ek, int32_t n_energy,
+                                       const double *cum0, const double *cum1, const double *cum2,
+                                       const int32_t n_mech[3], const double *dE, const int32_t *trans,
+                                       const int32_t *sampler)
+{
+    CTX_OR_FAIL(ctx);
+    return upload_tables_layer(c, layer, ek, n_energy, cum0, cum1, cum2, n_mech, dE, trans, sampler);
+}
+
+extern "C" int emc_set_layers(EmcCtx *ctx, const EmcLayer *layers, int32_t n_layers)
+{
+    CTX_OR_FAIL(ctx);
+    if (!layers || n_layers < 1 || n_layers > EMC_MAX_LAYERS)
+        return fail(c, EMC_ERR_INVALID, "emc_set_layers: 1..EMC_MAX_LAYERS layers");
+    for (int l = 0; l < n_layers; ++l) {
+        if (!(layers[l].lz > 0) || !(layers[l].init_weight >= 0))
+            return fail(c, EMC_ERR_INVALID, "emc_set_layers: lz must be positive, init_weight non-negative");
+        for (int v = 0; v < 3; ++v)
+            if (!(layers[l].mass[v] > 0) || !(layers[l].nonparab[v] > 0))
+                return fail(c, EMC_ERR_INVALID, "emc_set_layers: mass and nonparab must be positive");
+    }
+    for (int l = 0; l < n_layers; ++l) c->layers[l] = layers[l];
+    c->dc.n_layers = n_layers;
+    // tables have to be uploaded again for every layer
+    for (int l = 0; l < EMC_MAX_LAYERS; ++l) c->layer_tables[l] = false;
+    c->have_tables = false;
+    c->batch_layer = 0;
+    fill_devconst(c);
+    return EMC_OK;
+}
+
+extern "C" int emc_select_layer(EmcCtx *ctx, int32_t layer)
+{
+    CTX_OR_FAIL(ctx);
+    if (layer < 0 || layer >= c->dc.n_layers) return fail(c, EMC_ERR_INVALID, "emc_select_layer: layer out of range");
+    c->batch_layer = layer;
+    return EMC_OK;
+}
+
+extern "C" int emc_set_background_profile(EmcCtx *ctx, const double *background_z, int32_t nz)
+{
+    CTX_OR_FAIL(ctx);
+    if (c->d_background_z) { cudaFree(c->d_background_z); c->d_background_z = nullptr; c->background_nz = 0; }
+    if (!background_z) return EMC_OK;
+    if (nz != c->params.seg[2]) return fail(c, EMC_ERR_INVALID, "emc_set_background_profile: nz must equal seg[2]");
+    cudaError_t e = cudaMalloc(&c->d_background_z, sizeof(double) * (size_t)nz);
+    if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(background)");
+    e = cudaMemcpy(c->d_background_z, background_z, sizeof(double) * (size_t)nz, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(background)");
+    c->background_nz = nz;
     return EMC_OK;
 }
 
@@ -265,6 +382,8 @@ static int flight_common(Ctx *c, FlightArgs &A, bool replay, int32_t field_mode,
     if (field_mode == EMC_FIELD_MESH_PACKED && (!ex || ((uintptr_t)ex & 31) != 0))
         return fail(c, EMC_ERR_INVALID, "EMC_FIELD_MESH_PACKED needs a 32-byte aligned packed field in ex");
     if (field_mode < 0 || field_mode > EMC_FIELD_MESH_PACKED) return fail(c, EMC_ERR_INVALID, "unknown field_mode");
+    if (c->dc.n_layers > 1 && (c->exact_libm || A.mesh))
+        return fail(c, EMC_ERR_UNSUPPORTED, "multi-layer devices: no EMC_EXACT_LIBM, no fused deposit (use emc_deposit)");
     A.ex = ex; A.ey = ey; A.ez = ez;
     if (A.n == 0) return EMC_OK;
     cudaError_t e = launch_flight(c, A, replay, field_mode, (cudaStream_t)stream);

@@ -24,14 +24,14 @@ __device__ __forceinline__ void obs_zero(ObsAcc &a)
     for (int k = 0; k < 6; ++k) a.c[k] = 0u;
 }
 
-__device__ __forceinline__ void obs_particle(const DevConst &P, ObsAcc &a, double kx, double ky, double kz,
-                                             double z, int val)
+__device__ __forceinline__ void obs_particle(const DevConst &P, const Mat &MT, ObsAcc &a, double kx, double ky,
+                                             double kz, double z, int val)
 {
     if (val < 0) { a.c[3]++; return; }
-    // main_.py:105,109,394-397
-    const double E = energy_parabolic(P, kx, ky, kz, val);
-    const double enp = energy_nonparabolic(P, E, val);
-    const double vz = div_const(kz * P.hbar, P.mass[val], P.r_mass[val]);
+    // main_.py:105,109,394-397 (MT = mat[mat_i] of the final position, main_.py:393)
+    const double E = energy_parabolic(P, MT, kx, ky, kz, val);
+    const double enp = energy_nonparabolic(MT, E, val);
+    const double vz = div_const(kz * P.hbar, MT.mass[val], MT.r_mass[val]);
     a.d[0] += z;
     a.d[1] += vz;
     a.d[2] += enp;
@@ -259,16 +259,21 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
 }
 
 // retire a particle: write its state back, add it to the observables and the charge mesh
-template <bool REPLAY, bool DEPOSIT>
+template <bool REPLAY, bool DEPOSIT, bool ML>
 __device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, int64_t i, const Particle &p,
                                        uint32_t cursor, ObsAcc &acc, unsigned int *smesh)
 {
     A.kx[i] = p.kx; A.ky[i] = p.ky; A.kz[i] = p.kz;
     A.x[i] = p.x; A.y[i] = p.y; A.z[i] = p.z;
     A.dtau[i] = p.dte;
-    A.valley[i] = p.val;
+    int val = p.val, layer = 0;
+    if (ML && val >= 0) {                         // main_.py:393: the layer of the final position
+        layer = where_am_i(P, p.z);
+        if (layer < 0) { val = -(1 + EMC_FAULT_OUTSIDE); layer = 0; }
+    }
+    A.valley[i] = val;
     if (REPLAY) A.cursor[i] = (int32_t)cursor;
-    if (A.obs) obs_particle(P, acc, p.kx, p.ky, p.kz, p.z, p.val);
+    if (A.obs) obs_particle(P, P.mat[layer], acc, p.kx, p.ky, p.kz, p.z, val);
     if (DEPOSIT) {
         if (A.smem_cells > 0)
             deposit_ngp_particle(P, p.x, p.y, p.z, [&](int64_t c) { atomicAdd(&smesh[c], 1u); });
@@ -287,21 +292,30 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
     Q.s0[slot] = s0;
 }
 
-template <class Stream, int FIELD, bool EXACT, bool DEPOSIT>
+// ML = multi-layer device (emc_set_layers): the layer of a particle is looked up from its z with
+// where_am_i before every drift, scatter and observable (main_.py:366,372,377,387,393) and selects
+// the material constants, the table and the mechanism metadata.  ML = false compiles to the
+// single-material code (layer 0 everywhere).
+template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML>
 __global__ void __launch_bounds__(FLIGHT_THREADS, EMC_FLIGHT_MIN_BLOCKS)
 flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg,
                       const __grid_constant__ FlightArgs A)
 {
     constexpr bool REPLAY = Stream::is_replay;
-    __shared__ MechMeta M;
+    __shared__ MechMeta Ms[ML ? EMC_MAX_LAYERS : 1];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     WarpQueues *queues = reinterpret_cast<WarpQueues *>(dyn_smem);
     unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + sizeof(WarpQueues) * (FLIGHT_THREADS / 32));
     {
         const int nw = sizeof(MechMeta) / 4;
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(&Mg);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&M);
-        for (int t = threadIdx.x; t < nw; t += blockDim.x) dst[t] = src[t];
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&Ms[0]);
+        if (ML) {                                 // per-layer metadata lives in device memory
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(A.mech_layers);
+            for (int t = threadIdx.x; t < nw * P.n_layers; t += blockDim.x) dst[t] = __ldg(src + t);
+        } else {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&Mg);
+            for (int t = threadIdx.x; t < nw; t += blockDim.x) dst[t] = src[t];
+        }
         for (int t = threadIdx.x; t < A.smem_cells; t += blockDim.x) smesh[t] = 0u;
     }
     __syncthreads();
@@ -360,6 +374,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         bool act, pend = false, fly = false, park = false, tail = false;
         constexpr bool MESHF = (FIELD == EMC_FIELD_MESH || FIELD == EMC_FIELD_MESH_PACKED);
         int64_t cell = 0;                                         // mesh cell of the coming flight segment
+        int layer = 0;                                            // ML: where_am_i of the particle's z
         double dt_seg = 0.0;
         if (phase == PH_REFILL) {
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
@@ -389,6 +404,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     p.grp = (int32_t)(g >= P.n_groups ? P.n_groups - 1 : g);
                 }
                 if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
+                if (ML && p.val >= 0) {                           // :366 / :372
+                    layer = where_am_i(P, p.z);
+                    if (layer < 0) { p.val = -(1 + EMC_FAULT_OUTSIDE); layer = 0; }
+                }
                 if (p.val >= 0) {                                 // else frozen after a fault
                     const double dte = p.dte;                     // :361
                     fly = true;
@@ -438,13 +457,19 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
                 else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
                 int v = p.val, f;
-                if (sel) {
+                if (ML) layer = where_am_i(P, p.z);               // :377 (and :387: a scatter does not move)
+                const Mat &MT = P.mat[ML ? (layer < 0 ? 0 : layer) : 0];
+                const MechMeta &M = Ms[ML ? (layer < 0 ? 0 : layer) : 0];
+                if (ML && layer < 0) {
+                    f = EMC_FAULT_OUTSIDE;
+                    layer = 0;
+                } else if (sel) {
                     // select pass: energy, table row, r2 / azimuth uniforms, mechanism (:1092, :1029-1034)
-                    f = event_select(P, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech);
+                    f = event_select(P, MT, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech);
                     if (f < 0) {
                         if (M.sampler[v][mech] == EMC_SAMPLER_SELF) {
                             rng.draw_polar(false);                // no polar draw (:889); fetches the flight uniform
-                            f = scatter_self<EXACT>(P, M, p.kx, p.ky, p.kz, v, mech, e_np);
+                            f = scatter_self<EXACT>(P, MT, M, p.kx, p.ky, p.kz, v, mech, e_np);
                             tail = true;
                         } else {
                             park = true;                          // real mechanism: finish in a scatter pass
@@ -454,7 +479,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 } else {
                     // scatter pass: polar sampler, rotation (:1059-1089)
                     const double r_pol = rng.draw_polar(true);
-                    f = scatter_core<EXACT>(P, M, p.kx, p.ky, p.kz, v, mech, e_np, r_az, r_pol);
+                    f = scatter_core<EXACT>(P, MT, M, p.kx, p.ky, p.kz, v, mech, e_np, r_az, r_pol);
                     tail = true;
                 }
                 if (rng.overflow()) { f = EMC_FAULT_STREAM; park = false; }
@@ -485,11 +510,12 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         if (fly) {                                                // :367 / :373 / :388
             double efx, efy, efz;
             field_at<FIELD>(P, A, p, cell, efx, efy, efz);
-            const double dtm = div_const(dt_seg, P.mass[p.val], P.r_mass[p.val]);
+            const Mat &MT = P.mat[ML ? layer : 0];
+            const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
             carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             acc.c[4]++;
         }
-        if (act && !pend && !park) retire<REPLAY, DEPOSIT>(P, A, i, p, s0, acc, smesh);
+        if (act && !pend && !park) retire<REPLAY, DEPOSIT, ML>(P, A, i, p, s0, acc, smesh);
         const unsigned pm = __ballot_sync(FULL, pend);
         if (pend) queue_push(WQ.ev, qn + __popc(pm & lt_mask), p, s0);
         qn += __popc(pm);
@@ -515,10 +541,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     if (A.obs) obs_block_reduce_and_finish(acc, A.partials, A.ticket, A.obs);
 }
 
-template <class Stream, int FIELD, bool EXACT, bool DEPOSIT>
+template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML>
 static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
-    auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT>;
+    auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT, ML>;
     // persistent grid: exactly the blocks that are resident at once (one wave), unless the
     // ensemble is too small to give every block a full tile.  The attribute / occupancy queries
     // are cached per kernel variant and device (they cost tens of microseconds per launch).
@@ -543,11 +569,13 @@ static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid
 template <class Stream, int FIELD>
 static cudaError_t launch_flight_t(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
+    // multi-layer devices: default libm composition, separate deposit kernel (checked by the caller)
+    if (ctx->dc.n_layers > 1) return launch_flight_k<Stream, FIELD, false, false, true>(ctx, A, grid, smem, st);
     if (ctx->exact_libm)
-        return A.mesh ? launch_flight_k<Stream, FIELD, true, true>(ctx, A, grid, smem, st)
-                      : launch_flight_k<Stream, FIELD, true, false>(ctx, A, grid, smem, st);
-    return A.mesh ? launch_flight_k<Stream, FIELD, false, true>(ctx, A, grid, smem, st)
-                  : launch_flight_k<Stream, FIELD, false, false>(ctx, A, grid, smem, st);
+        return A.mesh ? launch_flight_k<Stream, FIELD, true, true, false>(ctx, A, grid, smem, st)
+                      : launch_flight_k<Stream, FIELD, true, false, false>(ctx, A, grid, smem, st);
+    return A.mesh ? launch_flight_k<Stream, FIELD, false, true, false>(ctx, A, grid, smem, st)
+                  : launch_flight_k<Stream, FIELD, false, false, false>(ctx, A, grid, smem, st);
 }
 
 cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, cudaStream_t st)
@@ -565,6 +593,7 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     }
     A.partials = ctx->partials;
     A.ticket = ctx->ticket;
+    A.mech_layers = ctx->d_mech_layers;
     ctx->launches++;
 #define EMC_DISPATCH(STREAM)                                                                     \
     switch (field_mode) {                                                                        \
@@ -590,8 +619,14 @@ observables_kernel(const __grid_constant__ DevConst P, const double *kx, const d
     for (int k = 0; k < 5; ++k) acc.d[k] = 0.0;
     for (int k = 0; k < 6; ++k) acc.c[k] = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        obs_particle(P, acc, kx[i], ky[i], kz[i], z[i], valley[i]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int val = valley[i], layer = 0;
+        if (P.n_layers > 1 && val >= 0) {         // main_.py:393
+            layer = where_am_i(P, z[i]);
+            if (layer < 0) { val = -(1 + EMC_FAULT_OUTSIDE); layer = 0; }
+        }
+        obs_particle(P, P.mat[layer], acc, kx[i], ky[i], kz[i], z[i], val);
+    }
     obs_block_reduce_and_finish(acc, partials, ticket, out);
 }
 
@@ -638,12 +673,33 @@ init_ensemble_kernel(const __grid_constant__ DevConst P, double kT, double mean_
         rng.init(seed, pid_offset + (uint64_t)i, 0xFFFFFFFFu);
         const double px = P.tot_dim[0] * rng.next();
         const double py = P.tot_dim[1] * rng.next();
-        const double pz = P.tot_dim[2] * rng.next();
+        double pz;
+        int layer = 0;
+        {
+            const double u = rng.next();
+            if (P.n_layers > 1 && P.layer_cw[P.n_layers - 1] > 0) {
+                // extension (doping profiles): piecewise-uniform z, layer l holds the share
+                // cw[l] - cw[l-1] of the ensemble; inverse CDF of the one uniform
+                double c0 = 0.0, z0 = 0.0;
+                while (layer < P.n_layers - 1 && u >= P.layer_cw[layer]) {
+                    c0 = P.layer_cw[layer];
+                    z0 += P.layer_lz[layer];
+                    ++layer;
+                }
+                pz = z0 + P.layer_lz[layer] * ((u - c0) / (P.layer_cw[layer] - c0));
+            } else {
+                pz = P.tot_dim[2] * u;
+            }
+            if (P.n_layers > 1) {                 // init_.py:214: the material of the layer at z
+                layer = where_am_i(P, pz);
+                if (layer < 0) layer = P.n_layers - 1;
+            }
+        }
         double n1, n2, n3, n4;
         { const double a = rng.next(), b = rng.next(); box_muller(a, b, n1, n2); }
         { const double a = rng.next(), b = rng.next(); box_muller(a, b, n3, n4); }
         const double e = mean_energy * kT + 1E-7 * sqrt(n1 * n1 + n2 * n2 + n3 * n3);
-        const double k = sqrt(2 * P.mass[0] * P.q * e / (P.hbar * P.hbar));      // init_.py:215
+        const double k = sqrt(2 * P.mat[layer].mass[0] * P.q * e / (P.hbar * P.hbar));      // init_.py:215
         double na, nb;
         { const double a = rng.next(), b = rng.next(); box_muller(a, b, na, nb); }
         const double alpha = 2 * 3.14159265358979323846 * na, beta = 2 * 3.14159265358979323846 * nb;
@@ -675,7 +731,7 @@ cudaError_t launch_init_ensemble(Ctx *ctx, double *kx, double *ky, double *kz, d
 // ------------------------------------------------------------------------------------------
 // single-function batches
 // ------------------------------------------------------------------------------------------
-__global__ void calc_energy_kernel(const __grid_constant__ DevConst P, const double *kx, const double *ky,
+__global__ void calc_energy_kernel(const __grid_constant__ DevConst P, int layer, const double *kx, const double *ky,
                                    const double *kz, const int32_t *valley, int64_t n, double *e_np,
                                    int32_t *idx, int32_t *fault)
 {
@@ -683,7 +739,7 @@ __global__ void calc_energy_kernel(const __grid_constant__ DevConst P, const dou
     if (i >= n) return;
     double e = 0.0;
     int32_t j = 0;
-    const int f = calc_energy(P, kx[i], ky[i], kz[i], valley[i], e, j);
+    const int f = calc_energy(P, P.mat[layer], kx[i], ky[i], kz[i], valley[i], e, j);
     e_np[i] = e;
     idx[i] = j;
     fault[i] = f;
@@ -709,7 +765,7 @@ __global__ void carrier_drift_kernel(const __grid_constant__ DevConst P, double 
 }
 
 template <bool EXACT>
-__global__ void scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg, double *kx,
+__global__ void scatter_kernel(const __grid_constant__ DevConst P, int layer, const __grid_constant__ MechMeta Mg, double *kx,
                                double *ky, double *kz, int32_t *valley, const double *u3, int64_t n,
                                int32_t *mech_out, int32_t *n_draws, int32_t *fault)
 {
@@ -728,7 +784,7 @@ __global__ void scatter_kernel(const __grid_constant__ DevConst P, const __grid_
     ReplayStream rng;
     rng.init(u3, 3, i, 0);
     int mech = -1;
-    const int f = scatter_event<EXACT>(P, M, a, b, c, val, rng, &mech);
+    const int f = scatter_event<EXACT>(P, P.mat[layer], M, a, b, c, val, rng, &mech);
     kx[i] = a; ky[i] = b; kz[i] = c;
     valley[i] = val;
     mech_out[i] = mech;
@@ -741,7 +797,8 @@ cudaError_t launch_calc_energy(Ctx *ctx, const double *kx, const double *ky, con
                                cudaStream_t st)
 {
     ctx->launches++;
-    calc_energy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->dc, kx, ky, kz, valley, n, e_np, idx, fault);
+    calc_energy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->dc, ctx->batch_layer, kx, ky, kz, valley, n,
+                                                                    e_np, idx, fault);
     return cudaGetLastError();
 }
 
@@ -767,10 +824,13 @@ cudaError_t launch_scatter(Ctx *ctx, double *kx, double *ky, double *kz, int32_t
 {
     ctx->launches++;
     const unsigned grid = (unsigned)((n + 127) / 128);
+    const int L = ctx->batch_layer;       // emc_select_layer: the mat_i argument of scatter_.scatter
     if (ctx->exact_libm)
-        scatter_kernel<true><<<grid, 128, 0, st>>>(ctx->dc, ctx->mech, kx, ky, kz, valley, u3, n, mech, n_draws, fault);
+        scatter_kernel<true><<<grid, 128, 0, st>>>(ctx->dc, L, ctx->mech_layers[L], kx, ky, kz, valley, u3, n, mech,
+                                                   n_draws, fault);
     else
-        scatter_kernel<false><<<grid, 128, 0, st>>>(ctx->dc, ctx->mech, kx, ky, kz, valley, u3, n, mech, n_draws, fault);
+        scatter_kernel<false><<<grid, 128, 0, st>>>(ctx->dc, L, ctx->mech_layers[L], kx, ky, kz, valley, u3, n, mech,
+                                                    n_draws, fault);
     return cudaGetLastError();
 }
 

@@ -36,19 +36,27 @@ struct FlightArgs {
     unsigned int *ticket;
     int64_t *mesh;
     int32_t smem_cells;
+    const MechMeta *mech_layers; // multi-layer: device array of n_layers mechanism-metadata blocks
 };
 
 struct Ctx {
     EmcParams params;
     DevConst dc;
-    MechMeta mech;
+    MechMeta mech;                // layer 0 (== mech_layers[0]); kernel parameter of single-layer launches
+    MechMeta mech_layers[EMC_MAX_LAYERS];
+    MechMeta *d_mech_layers = nullptr;
+    EmcLayer layers[EMC_MAX_LAYERS];
+    bool layer_tables[EMC_MAX_LAYERS] = {false, false, false, false};
+    int batch_layer = 0;          // emc_select_layer: material of the single-function batches
+    double *d_cum_layers[EMC_MAX_LAYERS][3] = {};
+    double *d_background_z = nullptr;   // emc_set_background_profile
+    int background_nz = 0;
     int device = 0;
     int sm_count = 0;
     int max_grid = 0;             // upper bound of any persistent grid (partials capacity)
     int waves = 1;                // flight kernel: grid = resident blocks * waves (EMC_WAVES)
     bool have_tables = false;
     bool exact_libm = false;      // EMC_EXACT_LIBM=1: compose acos/asin/atan exactly like the reference
-    double *d_cum[3] = {nullptr, nullptr, nullptr};
     double *d_groups = nullptr;
     ObsPartial *partials = nullptr;
     unsigned int *ticket = nullptr;

@@ -190,7 +190,8 @@ cudaError_t launch_mesh_allreduce_p2p(Ctx *ctx, const int64_t *const *in_ptrs, i
 
 // rho_pad: zero halo (np.pad, poisson_.py:53); interior = background + charge
 __global__ void mesh_to_rho_kernel(const __grid_constant__ DevConst P, const long long *__restrict__ mesh, int scheme,
-                                   double background, double increment, double *rho_pad)
+                                   double background, const double *__restrict__ background_z, double increment,
+                                   double *rho_pad)
 {
     const int nx = P.seg[0], ny = P.seg[1], nz = P.seg[2];
     const int64_t total = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
@@ -201,6 +202,7 @@ __global__ void mesh_to_rho_kernel(const __grid_constant__ DevConst P, const lon
     const int i = (int)(c / ((int64_t)(nz + 2) * (ny + 2)));
     if (i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz) { rho_pad[c] = 0.0; return; }
     const long long m = mesh[((int64_t)(i - 1) * ny + (j - 1)) * nz + (k - 1)];
+    if (background_z) background = background_z[k - 1];      // doping profile (emc_set_background_profile)
     double r = background;                                   // poisson_.py:27
     if (scheme == EMC_DEPOSIT_NGP) {
         for (long long t = 0; t < m; ++t) r += increment;    // poisson_.py:36, one += per hit, in sequence
@@ -216,7 +218,7 @@ cudaError_t launch_mesh_to_rho(Ctx *ctx, const int64_t *mesh, int scheme, double
     ctx->launches++;
     mesh_to_rho_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
         ctx->dc, reinterpret_cast<const long long *>(mesh), scheme, ctx->params.rho_background,
-        ctx->params.rho_increment, rho_pad);
+        ctx->d_background_z, ctx->params.rho_increment, rho_pad);
     return cudaGetLastError();
 }
 

@@ -154,6 +154,86 @@ class Context:
             sampler.ctypes.data))
         self.n_mech = n_mech
 
+    def _table_args(self, ek, tabs, mech):
+        ek = np.ascontiguousarray(ek, dtype=np.float64)
+        tabs = [np.ascontiguousarray(t, dtype=np.float64) for t in tabs]
+        n_mech = np.array([t.shape[1] for t in tabs], dtype=np.int32)
+        dE = np.zeros((3, abi.EMC_MAX_MECH), dtype=np.float64)
+        trans = np.zeros((3, abi.EMC_MAX_MECH), dtype=np.int32)
+        sampler = np.zeros((3, abi.EMC_MAX_MECH), dtype=np.int32)
+        for v in range(3):
+            _names, d, t, s = mech[v]
+            dE[v, :len(d)], trans[v, :len(t)], sampler[v, :len(s)] = d, t, s
+        keep = (ek, tabs, n_mech, dE, trans, sampler)
+        return keep, (ek.ctypes.data, len(ek), tabs[0].ctypes.data, tabs[1].ctypes.data, tabs[2].ctypes.data,
+                      n_mech.ctypes.data, dE.ctypes.data, trans.ctypes.data, sampler.ctypes.data)
+
+    def set_layers(self, layers=None, init_weights=None, tables=None) -> None:
+        """Multi-layer device (dev.layers, init_.py:127-130): the kernels then look the layer of a
+        particle up from its z (init_.where_am_i) before every drift, scatter and observable and
+        use that layer's material and table, as main_.py:366-396 does.
+
+        ``layers``: list of ``init_.Layer`` (default ``init_.Device.layers``); the material of
+        layer i is ``layers[i].matl`` and its tables are ``scatter_.calc_scatter_table(dfEk, i)``
+        with ``Device.Materials[i] = layers[i].matl`` (init_.py:129), unless ``tables`` gives one
+        ``(ek, [tab_G, tab_L, tab_X], mechanism_arrays)`` per layer.  ``init_weights``: share of the
+        initial ensemble per layer for ``Ensemble.init`` (extension; default uniform z)."""
+        from . import init_, scatter_
+        layers = list(init_.Device.layers if layers is None else layers)
+        n = len(layers)
+        assert 1 <= n <= abi.EMC_MAX_LAYERS
+        w = [0.0] * n if init_weights is None else [float(x) for x in init_weights]
+        if tables is None:
+            saved = init_.Device.Materials
+            init_.Device.Materials = [l.matl for l in layers]            # init_.py:129
+            try:
+                dfEk = init_.init_energy_df(2, 10000)
+                ek = dfEk["Ek"].to_numpy()
+                tables, ebs = [], []
+                for i in range(n):
+                    first = next(j for j in range(i + 1) if layers[j].matl is layers[i].matl)
+                    if first < i:
+                        tables.append(tables[first])
+                    else:
+                        tables.append((ek, [t.to_numpy() for t in scatter_.calc_scatter_table(dfEk, i)],
+                                       scatter_.mechanism_arrays(i)))
+                    ebs.append(float(scatter_.ion_eb(i)))
+            finally:
+                init_.Device.Materials = saved
+        else:
+            saved = init_.Device.Materials
+            init_.Device.Materials = [l.matl for l in layers]
+            try:
+                ebs = [float(scatter_.ion_eb(i)) for i in range(n)]
+            finally:
+                init_.Device.Materials = saved
+        arr = (abi.EmcLayer * n)()
+        for i, l in enumerate(layers):
+            arr[i].lz = float(l.lz)
+            for v in range(3):
+                arr[i].mass[v] = l.matl.mass[v]
+                arr[i].nonparab[v] = l.matl.nonparab[v]
+            arr[i].e_phonon = l.matl.E_phonon
+            arr[i].ion_eb = ebs[i]
+            arr[i].init_weight = w[i]
+        self.check(self.lib.emc_set_layers(self.h, arr, n))
+        for i in range(n):
+            keep, args = self._table_args(*tables[i])
+            self.check(self.lib.emc_upload_tables_layer(self.h, i, *args))
+        self.layers = layers
+
+    def select_layer(self, layer: int) -> None:
+        """Material used by ``emc_calc_energy`` / ``emc_scatter`` (their ``mat`` / ``mat_i`` argument)."""
+        self.check(self.lib.emc_select_layer(self.h, int(layer)))
+
+    def set_background_profile(self, background_z) -> None:
+        """Per-z-cell background charge for ``Mesh.to_rho`` (doping profiles); None = uniform."""
+        if background_z is None:
+            self.check(self.lib.emc_set_background_profile(self.h, None, 0))
+            return
+        b = np.ascontiguousarray(background_z, dtype=np.float64)
+        self.check(self.lib.emc_set_background_profile(self.h, b.ctypes.data, len(b)))
+
     def set_efield(self, efield) -> None:
         ef = np.ascontiguousarray(efield, dtype=np.float64)
         assert ef.shape == (3,)

@@ -98,8 +98,12 @@ def IMP(Ek, mat_i, val, T):
     Ek = _as_energy(Ek)
     Ld = 1 / np.sqrt(Parameters.q * mat.dope * 1E2 ** 3 / (mat.eps_0 * Parameters.kT))
     k = _wavevector(Ek, mat, val)
+    # The reference evaluates this per energy through np.vectorize, so its `k**2` is the SCALAR
+    # power = libm pow(k, 2.0), which differs from the array fast path k*k in the last bit for
+    # ~0.1 % of the arguments; Python's float ** is the same libm call.
+    k2 = np.array([float(x) ** 2 for x in np.ravel(k)], dtype=np.float64).reshape(np.shape(k))
     return (2 * np.pi * mat.dope * Parameters.q ** 2 / (Parameters.hbar_eVs * mat.eps_0 ** 2)) * \
-        density_of_states(Ek, mat.mass[val]) * (1 / Ld ** 2) * (1 / (1 / Ld ** 2 + 4 * k ** 2)) * 1E2
+        density_of_states(Ek, mat.mass[val]) * (1 / Ld ** 2) * (1 / (1 / Ld ** 2 + 4 * k2)) * 1E2
 
 
 def cc(Ek, mat_i, val, T):

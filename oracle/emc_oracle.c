@@ -284,10 +284,29 @@ static void obs_add(OrcObs *a, const OrcObs *b)
     a->n_fault += b->n_fault; a->n_segments += b->n_segments; a->n_events += b->n_events;
 }
 
-/* main_.py:394-397 for one particle */
-static void obs_particle(const OrcParams *p, const double coord[6], int val, OrcObs *o)
+/* where_am_i: init_.py:36-56 */
+int orc_where_am_i(const OrcParams *p, double dist)
+{
+    if (dist < 0) return -1;                      /* :45-46 */
+    for (int l = 0; l < p->n_layers; ++l) {       /* :48 */
+        if (dist <= p->layer_lz[l]) return l;     /* :50 */
+        dist -= p->layer_lz[l];                   /* :54 */
+    }
+    return -1;                                    /* :56 */
+}
+
+/* material of layer l (single-layer runs: the struct itself) */
+static const OrcParams *mat_of(const OrcParams *p, int l)
+{
+    return (p->n_layers > 1 && l >= 0) ? p->layer_mat[l] : p;
+}
+
+/* main_.py:393-397 for one particle */
+static void obs_particle(const OrcParams *pg, const double coord[6], int val, OrcObs *o)
 {
     if (val < 0) { o->n_fault++; return; }
+    const OrcParams *p = pg;
+    if (pg->n_layers > 1) p = mat_of(pg, orc_where_am_i(pg, coord[5]));      /* :393 */
     double E = (0.0 + coord[0] * coord[0]); E = E + coord[1] * coord[1]; E = E + coord[2] * coord[2];
     E = E * (p->hbar * p->hbar) / (2 * p->mass[val] * p->q);           /* main_.py:105 */
     double a = p->nonparab[val];
@@ -307,17 +326,29 @@ static void step_particle(const OrcParams *p, double coord[6], double *dtau, int
     double dt = p->dt;
     double dte = *dtau;                           /* :361 */
     double ef[3];
+    const int ML = p->n_layers > 1;
+    const OrcParams *pm = p;                      /* mat[mat_i] / scat_tables[mat_i] */
+    if (ML) {                                     /* :366 / :372 */
+        int l = orc_where_am_i(p, coord[5]);
+        if (l < 0) { *valley = -(1 + ORC_FAULT_OUTSIDE); return; }
+        pm = mat_of(p, l);
+    }
     field_at(p, c->s, c->i, coord, ef);
     if (dte >= dt) {                              /* :363 */
-        orc_carrier_drift(p, coord, ef, dt, p->mass[*valley]);     /* :367 */
+        orc_carrier_drift(p, coord, ef, dt, pm->mass[*valley]);     /* :367 */
         o->n_segments++;
     } else {
         double dt2 = dte;                         /* :370 */
-        orc_carrier_drift(p, coord, ef, dt2, p->mass[*valley]);    /* :373 */
+        orc_carrier_drift(p, coord, ef, dt2, pm->mass[*valley]);    /* :373 */
         o->n_segments++;
         while (dte < dt) {                        /* :375 */
             double dte2 = dte;                    /* :376 */
-            int f = scatter_stream(p, coord, valley, c);                  /* :378 */
+            if (ML) {                             /* :377 (and :387: a scatter does not move the particle) */
+                int l = orc_where_am_i(p, coord[5]);
+                if (l < 0) { *valley = -(1 + ORC_FAULT_OUTSIDE); *dtau = dte; return; }
+                pm = mat_of(p, l);
+            }
+            int f = scatter_stream(pm, coord, valley, c);                 /* :378 */
             if (c->overflow) f = ORC_FAULT_STREAM;
             if (f >= 0) { *valley = -(1 + f); *dtau = dte; return; }
             o->n_events++;
@@ -326,7 +357,7 @@ static void step_particle(const OrcParams *p, double coord[6], double *dtau, int
             double dtp = dt - dte2;               /* :381 */
             dt2 = (dt3 <= dtp) ? dt3 : dtp;       /* :382-385 */
             if (p->field_mode == 2) field_at(p, c->s, c->i, coord, ef);
-            orc_carrier_drift(p, coord, ef, dt2, p->mass[*valley]);/* :388 */
+            orc_carrier_drift(p, coord, ef, dt2, pm->mass[*valley]);/* :388 */
             o->n_segments++;
             dte = dte2 + dt3;                     /* :389 */
         }
@@ -355,6 +386,8 @@ void orc_timestep(const OrcParams *p, int64_t n, double *kx, double *ky, double 
             step_particle(p, coord, &dtau[i], &valley[i], &c, &local);
             kx[i] = coord[0]; ky[i] = coord[1]; kz[i] = coord[2];
             x[i] = coord[3]; y[i] = coord[4]; z[i] = coord[5];
+            if (p->n_layers > 1 && valley[i] >= 0 && orc_where_am_i(p, coord[5]) < 0)
+                valley[i] = -(1 + ORC_FAULT_OUTSIDE);              /* :393 would raise */
             obs_particle(p, coord, valley[i], &local);
         }
 #ifdef _OPENMP
@@ -399,11 +432,28 @@ void orc_init_ensemble(const OrcParams *p, int64_t n, double *kx, double *ky, do
         x[i] = p->tot_dim[0] * u[0];
         y[i] = p->tot_dim[1] * u[1];
         z[i] = p->tot_dim[2] * u[2];
+        const OrcParams *pm = p;
+        if (p->n_layers > 1) {
+            int layer = 0;
+            if (p->layer_cw[p->n_layers - 1] > 0) {
+                /* extension (doping profiles): piecewise-uniform z by inverse CDF of u[2] */
+                double c0 = 0.0, z0 = 0.0;
+                while (layer < p->n_layers - 1 && u[2] >= p->layer_cw[layer]) {
+                    c0 = p->layer_cw[layer];
+                    z0 += p->layer_lz[layer];
+                    ++layer;
+                }
+                z[i] = z0 + p->layer_lz[layer] * ((u[2] - c0) / (p->layer_cw[layer] - c0));
+            }
+            layer = orc_where_am_i(p, z[i]);      /* init_.py:214 */
+            if (layer < 0) layer = p->n_layers - 1;
+            pm = mat_of(p, layer);
+        }
         double n1, n2, n3, n4, na, nb;
         box_muller(u[3], u[4], &n1, &n2);
         box_muller(u[5], u[6], &n3, &n4);
         double e = p->mean_energy * p->kT + 1E-7 * sqrt(n1 * n1 + n2 * n2 + n3 * n3);
-        double k = sqrt(2 * p->mass[0] * p->q * e / (p->hbar * p->hbar));    /* init_.py:215 */
+        double k = sqrt(2 * pm->mass[0] * p->q * e / (p->hbar * p->hbar));   /* init_.py:215 */
         box_muller(u[7], u[8], &na, &nb);
         double alpha = 2 * M_PI * na, beta = 2 * M_PI * nb;
         kx[i] = k * cos(alpha) * sin(beta);       /* init_.py:218-220 */
@@ -420,7 +470,9 @@ void orc_observables(const OrcParams *p, int64_t n, const double *kx, const doub
     obs_zero(obs);
     for (int64_t i = 0; i < n; ++i) {
         double coord[6] = { kx[i], ky[i], kz[i], 0, 0, z[i] };
-        obs_particle(p, coord, valley[i], obs);
+        int val = valley[i];
+        if (p->n_layers > 1 && val >= 0 && orc_where_am_i(p, z[i]) < 0) val = -(1 + ORC_FAULT_OUTSIDE);
+        obs_particle(p, coord, val, obs);
     }
 }
 

@@ -29,7 +29,9 @@ enum { ORC_SAMPLER_SELF = 0, ORC_SAMPLER_ISO = 1, ORC_SAMPLER_POP_ABS = 2,
 /* fault codes; a faulted particle gets valley = -(1+code) and is frozen */
 enum { ORC_FAULT_NAN = 0, ORC_FAULT_ZERO_E = 1, ORC_FAULT_NO_MECH = 2,
        ORC_FAULT_DOMAIN = 3, ORC_FAULT_NEG_ENERGY = 4, ORC_FAULT_ZERO_K = 5,
-       ORC_FAULT_STREAM = 6 };
+       ORC_FAULT_STREAM = 6, ORC_FAULT_OUTSIDE = 7 /* where_am_i raised, init_.py:46,56 */ };
+
+#define ORC_MAX_LAYERS 4
 
 typedef struct OrcParams {
     double dt;            /* init_.py:60  */
@@ -61,7 +63,18 @@ typedef struct OrcParams {
     double dl[3];
     const double *ex, *ey, *ez;
     double kT, mean_energy;   /* init_.py:64,145 (ensemble initialisation) */
+    /* multi-layer devices (dev.layers, init_.py:127-130): n_layers > 1 makes the loop look the
+       layer up with where_am_i (init_.py:36-56) before every drift / scatter / observable
+       (main_.py:366,372,377,387,393) and read mass, nonparab, e_phonon, ion_eb, tables and
+       mechanism metadata from layer_mat[layer]; everything else comes from this struct */
+    int32_t n_layers;
+    double layer_lz[ORC_MAX_LAYERS];
+    const struct OrcParams *layer_mat[ORC_MAX_LAYERS];
+    double layer_cw[ORC_MAX_LAYERS];   /* cumulative shares of the initial ensemble (extension); all 0 = uniform z */
 } OrcParams;
+
+/* init_.where_am_i (init_.py:36-56): layer index or -1 where the reference raises */
+int    orc_where_am_i(const OrcParams *p, double dist);
 
 typedef struct OrcObs {
     double sum_z, sum_vz, sum_e;        /* main_.py:394-400 */

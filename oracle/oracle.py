@@ -17,7 +17,8 @@ _LIB_PATH = os.path.join(_HERE, "libemc_oracle.so")
 ORC_MAX_MECH = 16
 
 SAMPLER_SELF, SAMPLER_ISO, SAMPLER_POP_ABS, SAMPLER_POP_EMS, SAMPLER_ION = range(5)
-FAULT_NAMES = ["nan", "zero_energy", "no_mechanism", "domain", "negative_energy", "zero_k", "stream"]
+FAULT_NAMES = ["nan", "zero_energy", "no_mechanism", "domain", "negative_energy", "zero_k", "stream", "outside"]
+ORC_MAX_LAYERS = 4
 
 
 def build(force: bool = False) -> str:
@@ -32,21 +33,27 @@ def build(force: bool = False) -> str:
 
 
 class OrcParams(C.Structure):
-    _fields_ = [
-        ("dt", C.c_double), ("gamma", C.c_double), ("hbar", C.c_double), ("q", C.c_double),
-        ("mass", C.c_double * 3), ("nonparab", C.c_double * 3), ("tot_dim", C.c_double * 3),
-        ("efield", C.c_double * 3), ("e_phonon", C.c_double), ("ion_eb", C.c_double),
-        ("n_energy", C.c_int32), ("n_mech", C.c_int32 * 3),
-        ("ek", C.POINTER(C.c_double)), ("cum", C.POINTER(C.c_double) * 3),
-        ("mech_dE", (C.c_double * ORC_MAX_MECH) * 3),
-        ("mech_trans", (C.c_int32 * ORC_MAX_MECH) * 3),
-        ("mech_sampler", (C.c_int32 * ORC_MAX_MECH) * 3),
-        ("field_mode", C.c_int32), ("n_groups", C.c_int32), ("group_size", C.c_int64),
-        ("field_groups", C.POINTER(C.c_double)),
-        ("seg", C.c_int32 * 3), ("z_cyclic", C.c_int32), ("dl", C.c_double * 3),
-        ("ex", C.POINTER(C.c_double)), ("ey", C.POINTER(C.c_double)), ("ez", C.POINTER(C.c_double)),
-        ("kT", C.c_double), ("mean_energy", C.c_double),
-    ]
+    pass
+
+
+OrcParams._fields_ = [
+    ("dt", C.c_double), ("gamma", C.c_double), ("hbar", C.c_double), ("q", C.c_double),
+    ("mass", C.c_double * 3), ("nonparab", C.c_double * 3), ("tot_dim", C.c_double * 3),
+    ("efield", C.c_double * 3), ("e_phonon", C.c_double), ("ion_eb", C.c_double),
+    ("n_energy", C.c_int32), ("n_mech", C.c_int32 * 3),
+    ("ek", C.POINTER(C.c_double)), ("cum", C.POINTER(C.c_double) * 3),
+    ("mech_dE", (C.c_double * ORC_MAX_MECH) * 3),
+    ("mech_trans", (C.c_int32 * ORC_MAX_MECH) * 3),
+    ("mech_sampler", (C.c_int32 * ORC_MAX_MECH) * 3),
+    ("field_mode", C.c_int32), ("n_groups", C.c_int32), ("group_size", C.c_int64),
+    ("field_groups", C.POINTER(C.c_double)),
+    ("seg", C.c_int32 * 3), ("z_cyclic", C.c_int32), ("dl", C.c_double * 3),
+    ("ex", C.POINTER(C.c_double)), ("ey", C.POINTER(C.c_double)), ("ez", C.POINTER(C.c_double)),
+    ("kT", C.c_double), ("mean_energy", C.c_double),
+    ("n_layers", C.c_int32), ("layer_lz", C.c_double * ORC_MAX_LAYERS),
+    ("layer_mat", C.POINTER(OrcParams) * ORC_MAX_LAYERS),
+    ("layer_cw", C.c_double * ORC_MAX_LAYERS),
+]
 
 
 class OrcObs(C.Structure):
@@ -86,6 +93,8 @@ def lib():
         L.orc_philox_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_calc_energy.restype = C.c_int
         L.orc_calc_energy.argtypes = [C.POINTER(OrcParams), dp, C.c_int, dp, ip]
+        L.orc_where_am_i.restype = C.c_int
+        L.orc_where_am_i.argtypes = [C.POINTER(OrcParams), C.c_double]
         L.orc_free_flight.restype = C.c_double
         L.orc_free_flight.argtypes = [C.c_double, C.c_double]
         L.orc_carrier_drift.argtypes = [C.POINTER(OrcParams), dp, dp, C.c_double, C.c_double]
@@ -154,6 +163,7 @@ class Oracle:
         p.kT, p.mean_energy = phys.get("kT", 0.02585), phys.get("mean_energy", 0.1)
         p.field_mode = 0
         p.z_cyclic = int(bool(phys.get("z_cyclic", 0)))
+        p.n_layers = 1
         self.p = p
         self.L = lib()
         self._keep = {}
@@ -175,6 +185,23 @@ class Oracle:
         for a in range(3):
             self.p.seg[a], self.p.dl[a] = int(seg[a]), float(dl[a])
         self.p.ex, self.p.ey, self.p.ez = (_dp(a) for a in arrs)
+
+    def set_layers(self, lz, materials, init_weights=None):
+        """Multi-layer device: ``materials`` are Oracle objects (one per layer, each holding that
+        layer's mass / nonparab / e_phonon / ion_eb / tables / mechanism metadata)."""
+        assert 1 <= len(lz) == len(materials) <= ORC_MAX_LAYERS
+        self._keep["layers"] = list(materials)
+        self.p.n_layers = len(lz)
+        w = np.zeros(len(lz)) if init_weights is None else np.asarray(init_weights, dtype=np.float64)
+        tot, run = float(w.sum()), 0.0
+        for l, (t, m) in enumerate(zip(lz, materials)):
+            self.p.layer_lz[l] = float(t)
+            self.p.layer_mat[l] = C.pointer(m.p)
+            run += float(w[l])
+            self.p.layer_cw[l] = 0.0 if tot <= 0 else (1.0 if l == len(lz) - 1 else run / tot)
+
+    def where_am_i(self, dist):
+        return int(self.L.orc_where_am_i(C.byref(self.p), float(dist)))
 
     def init_ensemble(self, n, seed, pid_offset=0):
         st = {k: np.zeros(n, dtype=np.float64) for k in ("kx", "ky", "kz", "x", "y", "z", "dtau")}

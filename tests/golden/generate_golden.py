@@ -403,6 +403,158 @@ def gen_high_field():
     _free_run(777, 1500, 150, [0, 0, -50000], "free_running_hf")
 
 
+# ----------------------------------------------------------------------------------
+# Two-layer device: dev.layers = [GaAs 400 nm, a second material 500 nm].  The reference
+# wires multi-layer devices through where_am_i -> mat[mat_i] / scat_tables[mat_i]
+# (main_.py:366-396) but ships one layer; the second material is a subclass of the
+# reference's GaAs with the attributes below overridden, appended to the reference's own
+# Materials list (an in-memory list: no source edit).
+LAYER2 = dict(dope=1E17, e_phonon=0.0340, mass_rel=[0.07, 0.18, 0.55], nonparab=[0.55, 0.40, 0.25])
+LAYER_LZ = [400E-9, 500E-9]
+
+
+def second_material(ri):
+    m0 = ri.Parameters.m_0
+    return type("GaAsLayer2", (ri.GaAs,), dict(
+        dope=LAYER2["dope"], E_phonon=LAYER2["e_phonon"],
+        mass={v: LAYER2["mass_rel"][v] * m0 for v in range(3)},
+        nonparab={v: LAYER2["nonparab"][v] for v in range(3)}))
+
+
+def replay_layers(ns, ri, rsc, dfEk, tabs, layers, mat, coords, valley, dtau, U, n_steps, efield, dt,
+                  snap_steps):
+    """main_.py:360-397 including the where_am_i lookups, around the reference's own functions."""
+    N = len(coords)
+    stream = Stream(U)
+    fault_step = np.full(N, -1)
+    snaps = {}
+    n_seg = n_ev = 0
+    crossings = 0
+    where = ri.where_am_i
+    np.random.uniform, keep = stream.uniform, np.random.uniform
+    try:
+        for c in range(n_steps):
+            for carr in range(N):
+                if fault_step[carr] >= 0:
+                    continue
+                stream.i = carr
+                saved = (coords[carr].copy(), valley[carr], dtau[carr])
+                try:
+                    with np.errstate(all="ignore"):
+                        dte = dtau[carr]
+                        l_start = where(layers, coords[carr][5])['current_layer']
+                        if dte >= dt:
+                            dt2 = dt
+                            mat_i = where(layers, coords[carr][5])['current_layer']          # :366
+                            drift = ns["carrier_drift"](coords[carr], efield, dt2,
+                                                        mat[mat_i].mass[int(valley[carr])])
+                            n_seg += 1
+                        else:
+                            dt2 = dte
+                            mat_i = where(layers, coords[carr][5])['current_layer']          # :372
+                            drift = ns["carrier_drift"](coords[carr], efield, dt2,
+                                                        mat[mat_i].mass[int(valley[carr])])
+                            n_seg += 1
+                            while dte < dt:
+                                dte2 = dte
+                                mat_i = where(layers, drift[5])['current_layer']             # :377
+                                drift, valley[carr] = rsc.scatter(
+                                    drift, tabs[mat_i][int(valley[carr])], int(valley[carr]), dfEk, mat_i)
+                                if np.isnan(drift).any():
+                                    raise FloatingPointError("NaN after scatter")
+                                n_ev += 1
+                                dt3 = ns["free_flight"](mat[0].tot_scat)
+                                dtp = dt - dte2
+                                dt2 = dt3 if dt3 <= dtp else dtp
+                                mat_i = where(layers, drift[5])['current_layer']             # :387
+                                drift = ns["carrier_drift"](drift, efield, dt2,
+                                                            mat[mat_i].mass[int(valley[carr])])
+                                n_seg += 1
+                                dte = dte2 + dt3
+                        dte -= dt
+                        dtau[carr] = dte
+                        coords[carr] = drift
+                        mat_i = where(layers, drift[5])['current_layer']                     # :393
+                        ns["calc_energy"](drift[0:3], int(valley[carr]), mat[mat_i])
+                        crossings += int(mat_i != l_start)
+                except Exception as exc:     # noqa: BLE001
+                    fault_step[carr] = c
+                    coords[carr], valley[carr], dtau[carr] = saved
+                    print("layers: particle %d faulted in step %d: %r" % (carr, c, exc))
+            if c in snap_steps:
+                snaps[c] = (coords.copy(), valley.copy(), dtau.copy())
+    finally:
+        np.random.uniform = keep
+    return snaps, fault_step, stream.cur.copy(), n_seg, n_ev, crossings
+
+
+def gen_layers():
+    ri, rsc, dfEk, tabs0, mech0 = reference_setup()
+    ns = rs.exec_main()
+    P, G, D = ri.Parameters, ri.GaAs, ri.Device
+    G2 = second_material(ri)
+    layers = [ri.Layer(G, G.dope, D.layer0.lx, D.layer0.ly, LAYER_LZ[0]),
+              ri.Layer(G2, G2.dope, D.layer0.lx, D.layer0.ly, LAYER_LZ[1])]
+    mat = [G, G2]
+    rsc.Materials.append(G2)                # the list scatter_.py indexes with mat_i (scatter_.py:15)
+    try:
+        assert rsc.Materials[1] is G2 and len(rsc.Materials) == 2
+        tabs = [tabs0, rsc.calc_scatter_table(dfEk, 1)]
+        mech1 = rsc.scatter_mech(1)
+        cs = dict(seed=4203, N=192, steps=30, efield=[1000, -500, -30000], e_lo=2e-2, e_hi=0.9, L=384,
+                  snaps=[0, 9, 29])
+        rng = np.random.RandomState(cs["seed"])
+        N = cs["N"]
+        valleys = rng.randint(0, 3, N)
+        coords, valley = make_ensemble(ri, rng, N, cs["e_lo"], cs["e_hi"], valleys)
+        # a few particles exactly on / next to the interface and the walls
+        zi = LAYER_LZ[0]
+        coords[:6, 5] = [zi, np.nextafter(zi, 1), np.nextafter(zi, 0), 0.0, float(D.tot_dim[2]), zi / 2]
+        coords[6:110, 5] = zi + rng.uniform(-25e-9, 25e-9, 104)      # a crowd around the interface
+        U = np.random.RandomState(cs["seed"] + 1000).random_sample((N, cs["L"]))
+        dtau = np.array([(-1 / G.tot_scat) * np.log(U[i, 0]) for i in range(N)])
+        out = dict(coords0=coords.copy(), valley0=valley.copy(), dtau0=dtau.copy())
+        t = time.time()
+        snaps, fault_step, cur, n_seg, n_ev, crossings = replay_layers(
+            ns, ri, rsc, dfEk, tabs, layers, mat, coords, valley, dtau, U[:, 1:], cs["steps"],
+            np.array(cs["efield"], dtype=float), P.dt, set(cs["snaps"]))
+        print("layers: %.1f s, %d segments, %d events, faults %d, interface crossings %d" % (
+            time.time() - t, n_seg, n_ev, int((fault_step >= 0).sum()), crossings))
+        for s_, (cc, vv, dd) in snaps.items():
+            out["coords_s%d" % s_], out["valley_s%d" % s_], out["dtau_s%d" % s_] = cc, vv, dd
+        out["fault_step"], out["cursor_end"] = fault_step, cur + 1
+        # where_am_i known answers (init_.py:36-56), -1 where the reference raises
+        zs = np.concatenate([[0.0, zi, np.nextafter(zi, 1), np.nextafter(zi, 0), sum(LAYER_LZ),
+                              np.nextafter(sum(LAYER_LZ), 1), -1e-12, 1e-3],
+                             np.random.RandomState(5).uniform(0, sum(LAYER_LZ), 200)])
+        wl = []
+        for z in zs:
+            try:
+                wl.append(ri.where_am_i(layers, z)['current_layer'])
+            except ValueError:
+                wl.append(-1)
+        out["where_z"], out["where_layer"] = zs, np.array(wl)
+        sub_rows = np.unique(np.concatenate([np.arange(0, 10000, 50), np.arange(0, 100), [9998, 9999]]))
+        out["sub_rows"] = sub_rows
+        tab_meta = []
+        for v, tb in enumerate(tabs[1]):
+            a = np.ascontiguousarray(tb.to_numpy())
+            tab_meta.append(dict(valley=v, shape=list(a.shape), sha16=sha16(a)))
+            out["table%d_sub" % v] = a[sub_rows]
+        b = (1 / (2 * G2.dope)) ** (1 / 3)
+        meta = dict(versions=versions(), layer2=LAYER2, layer_lz=LAYER_LZ, case=dict(
+            cs, n_segments=n_seg, n_events=n_ev, crossings=crossings,
+            note="uniforms = RandomState(seed+1000).random_sample((N,L)); uniform 0 = initial free flight"),
+            tables_layer2=tab_meta, ion_eb_layer2=P.q / (2 * G2.eps_0 * b),
+            mech_layer2=[[dict(name=k, dE=float(m["dE"]), trans=int(m["trans"]),
+                               sampler=SAMPLER_ID[m["polar"].__name__]) for k, m in mech1[v].items()]
+                         for v in range(3)])
+        np.savez_compressed(os.path.join(HERE, "layers.npz"), **out)
+        json.dump(meta, open(os.path.join(HERE, "layers.json"), "w"), indent=1)
+    finally:
+        rsc.Materials.remove(G2)
+
+
 if __name__ == "__main__":
     if not rs.reference_available():
         sys.exit("reference not available; fixtures can only be regenerated in the build container")

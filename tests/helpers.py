@@ -65,3 +65,59 @@ def rel_err(a, b):
     scale = np.maximum(np.abs(a), np.abs(b))
     scale[scale == 0] = 1.0
     return np.abs(a - b) / scale
+
+
+# ------------------------------------------------------------------------------------------
+# two-layer device of tests/golden/layers.* (generate_golden.py gen_layers): layer 0 = GaAs
+# 400 nm, layer 1 = a GaAs subclass with the attributes recorded in layers.json, 500 nm
+# ------------------------------------------------------------------------------------------
+def layers_meta() -> dict:
+    return json.load(open(os.path.join(GOLDEN, "layers.json")))
+
+
+def layered_device():
+    """([Layer0, Layer1], per-layer (ek, tabs, mech) from the product's host builder)."""
+    if "layers" not in _cache:
+        from monte_carlo_carrier_transport_b200 import init_, scatter_
+        meta = layers_meta()
+        l2 = meta["layer2"]
+        m0 = init_.Parameters.m_0
+        G2 = type("GaAsLayer2", (init_.GaAs,), dict(
+            dope=l2["dope"], E_phonon=l2["e_phonon"],
+            mass={v: l2["mass_rel"][v] * m0 for v in range(3)},
+            nonparab={v: l2["nonparab"][v] for v in range(3)}))
+        L0 = init_.Device.layer0
+        layers = [init_.Layer(init_.GaAs, init_.GaAs.dope, L0.lx, L0.ly, meta["layer_lz"][0]),
+                  init_.Layer(G2, G2.dope, L0.lx, L0.ly, meta["layer_lz"][1])]
+        saved = init_.Device.Materials
+        init_.Device.Materials = [l.matl for l in layers]
+        try:
+            dfEk = init_.init_energy_df(2, 10000)
+            tabs1 = [np.ascontiguousarray(t.to_numpy()) for t in scatter_.calc_scatter_table(dfEk, 1)]
+            mech1 = scatter_.mechanism_arrays(1)
+            eb1 = float(scatter_.ion_eb(1))
+        finally:
+            init_.Device.Materials = saved
+        ek = dfEk["Ek"].to_numpy().copy()
+        _cache["layers"] = (layers, [host_tables(), (ek, tabs1, mech1)], eb1)
+    return _cache["layers"]
+
+
+def make_layered_oracle(efield=None, init_weights=None):
+    """Oracle of the two-layer device: a base Oracle (layer 0 material + globals) whose
+    layer_mat[] point at one Oracle per layer."""
+    import oracle as orc
+    layers, tables, eb1 = layered_device()
+    base = make_oracle(efield)
+    g = golden_params()
+    phys1 = dict(g["phys"])
+    G2 = layers[1].matl
+    phys1.update(mass=[G2.mass[v] for v in range(3)], nonparab=[G2.nonparab[v] for v in range(3)],
+                 e_phonon=G2.E_phonon, ion_eb=eb1)
+    if efield is not None:
+        phys1["efield"] = list(efield)
+    ek, tabs1, mech1 = tables[1]
+    m1 = orc.Oracle(phys1, ek, tabs1, [list(zip(m[1].tolist(), m[2].tolist(), m[3].tolist())) for m in mech1])
+    m0 = make_oracle(efield)
+    base.set_layers([l.lz for l in layers], [m0, m1], init_weights)
+    return base

@@ -58,6 +58,13 @@ def test_struct_layouts_match_the_header(lib, tmp_path):
     P, O = abi.EmcParams, abi.EmcObs
     assert got == [C.sizeof(P), P.seg.offset, P.dl.offset, P.surf_val.offset, C.sizeof(O),
                    O.n_valley.offset, O.n_events.offset]
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "emc.h"\n'
+                    'int main(void){printf("%zu %zu %zu %zu\\n", sizeof(EmcLayer), offsetof(EmcLayer, nonparab), '
+                    'offsetof(EmcLayer, ion_eb), offsetof(EmcLayer, init_weight));return 0;}\n')
+    subprocess.run(["gcc", "-I", os.path.join(helpers.ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    L = abi.EmcLayer
+    assert got == [C.sizeof(L), L.nonparab.offset, L.ion_eb.offset, L.init_weight.offset]
     assert abi.OBS_NBYTES == 88
 
 

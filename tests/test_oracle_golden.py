@@ -145,6 +145,75 @@ def test_replay_trajectories(case):
         assert (n_seg, n_ev) == (meta["n_segments"], meta["n_events"])
 
 
+def test_layer2_tables_match_reference_hashes():
+    """The host builder's tables for the second material == the reference's (SHA + sampled rows)."""
+    import hashlib
+    meta = helpers.layers_meta()
+    _layers, tables, eb1 = helpers.layered_device()
+    g = helpers.golden_npz("layers")
+    ek, tabs1, mech1 = tables[1]
+    for v in range(3):
+        assert hashlib.sha256(tabs1[v].tobytes()).hexdigest()[:16] == meta["tables_layer2"][v]["sha16"], v
+        assert np.array_equal(tabs1[v][g["sub_rows"]], g["table%d_sub" % v])
+        ref = meta["mech_layer2"][v]
+        assert [m["trans"] for m in ref] == mech1[v][2].tolist()
+        assert [m["sampler"] for m in ref] == mech1[v][3].tolist()
+        assert np.array_equal(np.array([m["dE"] for m in ref]), mech1[v][1])
+    assert eb1 == meta["ion_eb_layer2"]
+
+
+def test_where_am_i_known_answers():
+    """init_.where_am_i (init_.py:36-56) incl. the interface, the walls and the raising cases."""
+    g = helpers.golden_npz("layers")
+    o = helpers.make_layered_oracle()
+    got = np.array([o.where_am_i(z) for z in g["where_z"]])
+    assert np.array_equal(got, g["where_layer"])
+    from monte_carlo_carrier_transport_b200 import init_
+    layers, _t, _e = helpers.layered_device()
+    for z, l in zip(g["where_z"], g["where_layer"]):
+        if l < 0:
+            with pytest.raises(ValueError):
+                init_.where_am_i(layers, z)
+        else:
+            assert init_.where_am_i(layers, z)["current_layer"] == l
+
+
+def test_two_layer_replay_trajectories():
+    """main_.py:360-397 with the where_am_i lookups (two materials, two tables) driven by the
+    reference's own functions vs the oracle on the same per-particle uniform stream."""
+    meta = helpers.layers_meta()["case"]
+    r = helpers.golden_npz("layers")
+    o = helpers.make_layered_oracle(efield=meta["efield"])
+    N, L = meta["N"], meta["L"]
+    U = np.random.RandomState(meta["seed"] + 1000).random_sample((N, L))
+    st = helpers.state_from_coords(r["coords0"], r["valley0"], r["dtau0"])
+    Uloop = np.ascontiguousarray(U[:, 1:])
+    cursor = np.zeros(N, dtype=np.int32)
+    stream = orc.replay_stream(Uloop, cursor)
+    fault_step = r["fault_step"]
+    n_seg = n_ev = 0
+    for s in range(meta["steps"]):
+        obs = o.timestep(st, stream)
+        n_seg += obs["n_segments"]
+        n_ev += obs["n_events"]
+        assert np.array_equal(st["valley"] < 0, (fault_step >= 0) & (fault_step <= s)), s
+        if s in meta["snaps"]:
+            ok = st["valley"] >= 0
+            ref = r["coords_s%d" % s]
+            got = helpers.coords_from_state(st)
+            assert np.array_equal(st["valley"][ok], r["valley_s%d" % s][ok])
+            kn = np.linalg.norm(ref[ok, :3], axis=1, keepdims=True)
+            assert np.max(np.abs(got[ok, :3] - ref[ok, :3]) / kn) < 1e-10, s
+            assert np.max(np.abs(got[ok, 3:] - ref[ok, 3:]) / np.array(o.p.tot_dim[:])) < 1e-10, s
+            assert np.max(helpers.rel_err(st["dtau"][ok], r["dtau_s%d" % s][ok])) < 1e-9
+    ok = st["valley"] >= 0
+    assert np.array_equal(cursor[ok] + 1, r["cursor_end"][ok])
+    # the three particles the reference faulted on still consumed segments/events before: compare
+    # the totals only over a fault-free run
+    if not (fault_step >= 0).any():
+        assert (n_seg, n_ev) == (meta["n_segments"], meta["n_events"])
+
+
 def test_division_by_run_constants_is_correctly_rounded():
     """csrc/emc_device.cuh div_const (reciprocal + two FMA residual corrections) == IEEE '/':
     the five operations restated in C, 2e6 random dividends per divisor the kernels use, over the
