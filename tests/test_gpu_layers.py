@@ -99,7 +99,7 @@ def test_two_layer_philox_timesteps_vs_oracle(lctx, torch_mod, efield):
             assert abs(og[key] - oo[key]) <= 1e-9 * abs(oo[key]), (s, key)
         if s in (0, 5, steps - 1):
             compare_states(st, *ens.coords(), dims)
-    assert crossed > 1000                       # the interface is actually exercised
+    assert crossed > 300                        # the interface is actually exercised
     lctx.set_efield(g["efield"])
 
 
