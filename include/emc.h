@@ -232,6 +232,11 @@ int emc_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, int32_t *valley
                 const double *u3, int64_t n, int32_t *mech, int32_t *n_draws, int32_t *fault,
                 void *stream);
 
+/* Self-test of the guard-free sqrt / division / log the kernels use (csrc/emc_device.cuh): n
+ * Philox-drawn operand sets are compared BIT FOR BIT with CUDA's correctly rounded sqrt(), `/`
+ * and its log().  mismatches (HOST): counts for division, sqrt, log; all must be 0. */
+int emc_selftest_math(EmcCtx *ctx, int64_t n, uint64_t seed, int64_t mismatches[3], void *stream);
+
 /* ---- layout helpers for callers that hold the reference's (N,6) array (main_.py:51-52) ----- */
 int emc_aos_to_soa(EmcCtx *ctx, const double *coords6, int64_t n, double *kx, double *ky,
                    double *kz, double *x, double *y, double *z, void *stream);

@@ -486,6 +486,25 @@ extern "C" int emc_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, int3
     return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "scatter launch");
 }
 
+extern "C" int emc_selftest_math(EmcCtx *ctx, int64_t n, uint64_t seed, int64_t mismatches[3], void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!mismatches || n < 0) return fail(c, EMC_ERR_INVALID, "emc_selftest_math: bad argument");
+    unsigned long long *d = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMalloc(&d, 3 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(selftest)");
+    unsigned long long h[3] = {0, 0, 0};
+    if ((e = cudaMemsetAsync(d, 0, sizeof(h), st)) == cudaSuccess &&
+        (e = launch_selftest_math(c, n, seed, d, st)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st)) == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(c, e, "selftest_math");
+    for (int k = 0; k < 3; ++k) mismatches[k] = (int64_t)h[k];
+    return EMC_OK;
+}
+
 extern "C" int emc_aos_to_soa(EmcCtx *ctx, const double *coords6, int64_t n, double *kx, double *ky, double *kz,
                               double *x, double *y, double *z, void *stream)
 {

@@ -144,6 +144,11 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 // 16 warps/SM); 192 x 3 (96 registers, 18 warps, spills) 2.22 ms; 256 x 3 (80 registers) 1.72 ms.
 #define EMC_FLIGHT_MIN_BLOCKS 1
 #endif
+#ifndef EMC_SPEC_SELECT
+// 1: free-running select passes run select_self_spec (all dependency chains of a self-scattering
+// event issued before the first decision, emc_device.cuh) instead of event_select + scatter_self
+#define EMC_SPEC_SELECT 1
+#endif
 #ifndef EMC_STAGE_REFILL
 // 1: cp.async (LDGSTS) the next refill batch into shared memory while the current one is
 // processed, so the refill phase never waits on HBM.  Measured with the L2 prefetch one batch
@@ -373,6 +378,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         double e_np = 0.0, r_az = 0.0;
         bool act, pend = false, fly = false, park = false, tail = false;
         constexpr bool MESHF = (FIELD == EMC_FIELD_MESH || FIELD == EMC_FIELD_MESH_PACKED);
+        constexpr bool SPEC = EMC_SPEC_SELECT && !REPLAY && !EXACT;
+        double lg = 0.0;                                          // SPEC: log(flight uniform) of a finished event
         int64_t cell = 0;                                         // mesh cell of the coming flight segment
         int layer = 0;                                            // ML: where_am_i of the particle's z
         double dt_seg = 0.0;
@@ -463,6 +470,13 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 if (ML && layer < 0) {
                     f = EMC_FAULT_OUTSIDE;
                     layer = 0;
+                } else if (sel && SPEC) {
+                    bool is_self;
+                    f = select_self_spec(P, MT, M, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
+                    if (f < 0) {
+                        if (is_self) tail = true;
+                        else { park = true; s0 = rng.state(); }
+                    }
                 } else if (sel) {
                     // select pass: energy, table row, r2 / azimuth uniforms, mechanism (:1092, :1029-1034)
                     f = event_select(P, MT, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech);
@@ -479,6 +493,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 } else {
                     // scatter pass: polar sampler, rotation (:1059-1089)
                     const double r_pol = rng.draw_polar(true);
+                    if (SPEC) lg = fast_log(rng.free_flight());   // independent of the rotation below
                     f = scatter_core<EXACT>(P, MT, M, p.kx, p.ky, p.kz, v, mech, e_np, r_az, r_pol);
                     tail = true;
                 }
@@ -490,7 +505,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 // the event happened: draw the next free flight and fly (main_.py:379-389)
                 acc.c[5]++;
                 const double dte2 = p.dte;                        // :376
-                const double dt3 = P.neg_inv_gamma * log(rng.free_flight());         // :379
+                const double dt3 = P.neg_inv_gamma * (SPEC ? lg : fast_log(rng.free_flight()));    // :379
                 if (rng.overflow()) {
                     p.val = -(1 + EMC_FAULT_STREAM);
                 } else {
@@ -831,6 +846,80 @@ cudaError_t launch_scatter(Ctx *ctx, double *kx, double *ky, double *kz, int32_t
     else
         scatter_kernel<false><<<grid, 128, 0, st>>>(ctx->dc, L, ctx->mech_layers[L], kx, ky, kz, valley, u3, n, mech,
                                                     n_draws, fault);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// self-test of the branch-free sqrt / division / log (emc_device.cuh) against CUDA's own
+// correctly rounded sqrt(), `/` and its log(): bit-for-bit, on operands drawn from Philox over
+// the ranges the kernels use and well beyond.  counts[0..2] = mismatches of div, sqrt, log.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double selftest_operand(uint32_t a, uint32_t b, int e_lo, int e_span, bool neg)
+{
+    // mantissa from 52 random bits, exponent uniform in [e_lo, e_lo + e_span), random sign if asked
+    const uint64_t mant = (((uint64_t)a << 32) | b) & 0x000fffffffffffffULL;
+    const int ex = e_lo + (int)((a >> 20) % (uint32_t)e_span);
+    const uint64_t sign = (neg && (b & 1u)) ? 0x8000000000000000ULL : 0ULL;
+    return __longlong_as_double((long long)(sign | ((uint64_t)(ex + 1023) << 52) | mant));
+}
+
+__global__ void selftest_math_kernel(int64_t n, uint64_t seed, unsigned long long *counts)
+{
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    unsigned long long bad_div = 0, bad_sqrt = 0, bad_log = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint4 r0 = philox4x32_10(make_uint4(0u, 0x5e1f7e57u, (uint32_t)i, (uint32_t)(i >> 32)), key);
+        const uint4 r1 = philox4x32_10(make_uint4(1u, 0x5e1f7e57u, (uint32_t)i, (uint32_t)(i >> 32)), key);
+        // division: wide range, and the kernel's own shape kz / |k|, kx / (|k| sin)
+        {
+            const double a = selftest_operand(r0.x, r0.y, -80, 160, true);
+            const double b = selftest_operand(r0.z, r0.w, -80, 160, true);
+            bad_div += __double_as_longlong(fast_div(a, b)) != __double_as_longlong(a / b);
+            const double k0 = selftest_operand(r1.x, r1.y, 20, 16, false);
+            const double kz = k0 * (2 * u53(r1.z, r1.w) - 1);
+            bad_div += __double_as_longlong(fast_div(kz, k0)) != __double_as_longlong(kz / k0);
+            bad_div += __double_as_longlong(fast_div(0.0, k0)) != __double_as_longlong(0.0 / k0);
+        }
+        // sqrt: wide range, |k|^2, 1 + 4 alpha E, (1 - c)(1 + c) down to the last ulp below 1
+        {
+            const double a = selftest_operand(r0.x, r0.z, -200, 400, false);
+            bad_sqrt += __double_as_longlong(fast_sqrt(a)) != __double_as_longlong(sqrt(a));
+            const double c = 2 * u53(r1.x, r1.w) - 1;
+            const double w = (1 - c) * (1 + c);
+            bad_sqrt += __double_as_longlong(fast_sqrt(w)) != __double_as_longlong(sqrt(w));
+            const double cc = 1 - ldexp(u53(r1.y, r1.z), -(int)(r0.w % 50u));          // c -> 1
+            const double ww = (1 - cc) * (1 + cc);
+            bad_sqrt += __double_as_longlong(fast_sqrt(ww)) != __double_as_longlong(sqrt(ww));
+            const double e = 1 + 4 * 0.61 * (2 * u53(r0.y, r1.y));
+            bad_sqrt += __double_as_longlong(fast_sqrt(e)) != __double_as_longlong(sqrt(e));
+        }
+        // log: the uniforms of free_flight and general positive normal numbers
+        {
+            const double u = u53(r0.x, r1.x);
+            if (u > 0) bad_log += __double_as_longlong(fast_log(u)) != __double_as_longlong(log(u));
+            const double v = ldexp(u53(r0.z, r1.z), -(int)(r0.y % 53u));                 // small uniforms
+            if (v > 0) bad_log += __double_as_longlong(fast_log(v)) != __double_as_longlong(log(v));
+            const double a = selftest_operand(r0.w, r1.w, -300, 600, false);
+            bad_log += __double_as_longlong(fast_log(a)) != __double_as_longlong(log(a));
+        }
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        // specials: zero and negative arguments
+        bad_sqrt += __double_as_longlong(fast_sqrt(0.0)) != __double_as_longlong(0.0);
+        bad_sqrt += !isnan(fast_sqrt(-1.0));
+        bad_log += !(fast_log(0.0) < -1e308);
+        bad_div += !isnan(fast_div(1.0, 0.0));
+    }
+    if (bad_div) atomicAdd(&counts[0], bad_div);
+    if (bad_sqrt) atomicAdd(&counts[1], bad_sqrt);
+    if (bad_log) atomicAdd(&counts[2], bad_log);
+}
+
+cudaError_t launch_selftest_math(Ctx *ctx, int64_t n, uint64_t seed, unsigned long long *counts_dev, cudaStream_t st)
+{
+    ctx->launches++;
+    selftest_math_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(n, seed, counts_dev);
     return cudaGetLastError();
 }
 

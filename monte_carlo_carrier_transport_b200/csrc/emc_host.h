@@ -92,6 +92,8 @@ cudaError_t launch_aos_to_soa(Ctx *ctx, const double *c6, int64_t n, double *kx,
 cudaError_t launch_soa_to_aos(Ctx *ctx, const double *kx, const double *ky, const double *kz, const double *x,
                               const double *y, const double *z, int64_t n, double *c6, cudaStream_t st);
 
+cudaError_t launch_selftest_math(Ctx *ctx, int64_t n, uint64_t seed, unsigned long long *counts_dev, cudaStream_t st);
+
 // emc_mesh.cu
 cudaError_t launch_deposit(Ctx *ctx, const double *x, const double *y, const double *z, int64_t n, int64_t *mesh,
                            int scheme, cudaStream_t st);
