@@ -53,7 +53,8 @@ def workload_config(n_gpus):
             "particles_per_gpu": N_FIELDS * PER_FIELD, "field_points": N_FIELDS,
             "global_particles": N_FIELDS * PER_FIELD * n_gpus,
             "parallelism": "particle slices per rank, no data-path collective",
-            "l2_policy": "inputs larger than L2 (1.44 GB of particle state per GPU vs 126 MB L2)"}
+            "l2_policy": "inputs larger than L2 (1.44 GB of particle state per GPU vs 126 MB L2)",
+            "observables": "main_.py:394-403 reduced for every timestep inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -204,12 +205,15 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
     stage = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     sweeps = []
     launches0 = ctx.launch_count()
+    obs_hist = torch.zeros((steps, 11), dtype=torch.int64, device=ctx.device)
+    ctx.set_obs_phase(True)       # per-step observables reduced while the next step loads the state
     barrier()
     ev[0].record()
     for s in range(steps):
         m = cs.mesh
         m.zero_counts()
-        ens.step(cs.n_steps, cs.seed, field_mode=cs.field_mode, mesh=m, observe=True, deposit=False)
+        ens.step(cs.n_steps, cs.seed, field_mode=cs.field_mode, mesh=m, observe=True, deposit=False,
+                 obs_out=obs_hist[s])
         m.deposit(ens)
         stage[s][0].record()
         m.allreduce()
@@ -220,7 +224,9 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
         stage[s][2].record()
         cs.n_steps += 1
         ev[s + 1].record()
+    ens.observables()             # the last step's observables (stand-alone reduction)
     barrier()
+    ctx.set_obs_phase(False)
     launches = ctx.launch_count() - launches0
     sweeps.append(cs.mesh.last_solve()[0])
     per = np.array([ev[s].elapsed_time(ev[s + 1]) for s in range(steps)])
@@ -231,7 +237,7 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
                      dtype=torch.float64, device=ctx.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    obs = ens.last_obs()
+    obs = engine._obs_from_raw(obs_hist[-1].cpu().numpy())
     ctx.close()
     t = [float(v) for v in t.cpu()]
     return {"metric": "ms per coupled MC+Poisson timestep", "ms_per_timestep": t[0], "flight_deposit_ms": t[1],
@@ -261,11 +267,14 @@ def other_configs_bench(torch, dist, engine, abi, local, rank, world, barrier, s
             ens.step(s, SEED + 2)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.set_obs_phase(True)
         a.record()
         for s in range(steps):
             ens.step(warmup + s, SEED + 2)
+        ens.observables()
         b.record()
         barrier()
+        ctx.set_obs_phase(False)
         t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=ctx.device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -320,21 +329,29 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     barrier()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Observables of main_.py:394-403 for EVERY timestep.  Default phase "before": launch c reduces
+    # the state step c-1 left behind while it loads it (all lanes busy), and ONE stand-alone
+    # emc_observables after the loop (inside the timed region) reads the final state -- K+1
+    # reductions for K steps, the rows shifted back by engine.Ensemble.run_steps.  "after": the
+    # reduction at particle retirement (half-filled warps), as in earlier rounds.
+    before = args.obs_phase == "before"
+    ctx.set_obs_phase(before)
     t_start.record()
     for s in range(steps):
         ev[s][0].record()
-        ens.step(warmup + s, SEED, field_mode=abi.FIELD_GROUPS)
+        ens.step(warmup + s, SEED, field_mode=abi.FIELD_GROUPS, obs_out=obs_keep[s])
         ev[s][1].record()
-        obs_keep[s].copy_(ens.obs, non_blocking=True)
+    final_obs = ens.observables() if before else None
     t_stop.record()
     barrier()
+    ctx.set_obs_phase(False)
     launches = ctx.launch_count() - launches0
     elapsed_ms = t_start.elapsed_time(t_stop)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     raw = obs_keep.cpu().numpy()
     segments = int(raw[:, 9].sum())
     events = int(raw[:, 10].sum())
-    faults = int(raw[-1, 8])
+    faults = int(final_obs["n_fault"]) if final_obs is not None else int(raw[-1, 8])
     clk = clocks.stop() if rank == 0 else None
 
     # ---- end-to-end arm: the caller holds HOST arrays (the reference's coords/valley/dtau) ----
@@ -414,6 +431,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-coupled", action="store_true", help="skip the coupled MC+Poisson sub-benchmark")
+    ap.add_argument("--obs-phase", default="before", choices=["before", "after"],
+                    help="per-step observables reduced while loading the next step's state (default) or at retirement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

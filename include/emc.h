@@ -164,6 +164,14 @@ int emc_upload_tables_layer(EmcCtx *ctx, int32_t layer, const double *ek, int32_
                             const double *cum0, const double *cum1, const double *cum2,
                             const int32_t n_mech[3], const double *dE, const int32_t *trans,
                             const int32_t *sampler);
+/* When are the observables of emc_flight_scatter / emc_flight_scatter_replay taken?
+ *   0 (default): after the timestep, as main_.py:394-403 does;
+ *   1: BEFORE it -- the sums and valley counts describe the ensemble as the call found it (i.e. the
+ *      result of the previous timestep), n_segments / n_events still count the call's own work.
+ * In mode 1 the reduction runs in the kernel's load phase with all 32 lanes of a warp busy instead
+ * of at particle retirement (17 of 32 on average): a time loop gets the same rows one launch later
+ * and reads the last one with emc_observables. */
+int emc_set_obs_phase(EmcCtx *ctx, int32_t before_step);
 /* Material (layer) used by the single-function batches emc_calc_energy / emc_scatter: the `mat` /
  * `mat_i` argument of scatter_.calc_energy (scatter_.py:19) and scatter_.scatter (:986).  Default 0. */
 int emc_select_layer(EmcCtx *ctx, int32_t layer);

@@ -29,22 +29,11 @@ from . import abi, engine, init_, parallel
 SEED = 12345
 
 
-def _rows(ens, steps, seed, step_fn):
-    rows = []
-    for c in range(steps):
-        step_fn(c)
-        o = engine.summarize(ens.last_obs())
-        o.update(step=c, t_ps=c * init_.Parameters.dt * 1e12)
-        rows.append(o)
-    return rows
-
-
-def _global_rows(ens, steps, seed, step_fn, device):
+def _global_rows(raw_rows, device):
     """Per-step rows of the WHOLE ensemble (observable sums all-reduced over the ranks)."""
     rows = []
-    for c in range(steps):
-        step_fn(c)
-        o = engine.summarize(parallel.allreduce_obs(ens.last_obs(), device=device))
+    for c, obs in enumerate(raw_rows):
+        o = engine.summarize(parallel.allreduce_obs(obs, device=device))
         o.update(step=c, t_ps=c * init_.Parameters.dt * 1e12)
         rows.append(o)
     return rows
@@ -130,7 +119,7 @@ def _coupled(mesh_shape, n_global, steps, seed, device, efield=(0.0, 0.0, 0.0), 
         ctx.set_background_profile(-dope_z * cell * 1e6)
     ens = engine.Ensemble(ctx, count, pid_offset=first).init(seed)
     cs = engine.CoupledStepper(ctx, ens, seed=seed, max_sweeps=max_sweeps).prime(max_sweeps=50_000)
-    rows = _global_rows(ens, steps, seed, lambda c: cs.step(), ctx.device)
+    rows = _global_rows(cs.run_steps(steps), ctx.device)
     sweeps, err = cs.mesh.last_solve()
     for r in rows:
         r["sor_sweeps_last"] = sweeps
@@ -152,7 +141,7 @@ def c5(scale=1.0, steps=150, seed=SEED, device=0, field_kv_cm=50.0):
     n = max(32, int(125_000_000 * scale))            # per GPU: weak scaling
     ctx = engine.Context(engine.params_from_reference_modules(efield=(0, 0, -field_kv_cm * 1e3)), device=device)
     ens = engine.Ensemble(ctx, n, pid_offset=rank * n).init(seed)
-    rows = _global_rows(ens, steps, seed, lambda c: ens.step(c, seed), ctx.device)
+    rows = _global_rows(ens.run_steps(0, steps, seed), ctx.device)
     ctx.close()
     return rows
 

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 #include "emc_host.h"
 
 using namespace emc;
@@ -22,6 +23,16 @@ static std::string g_create_error;
         cudaError_t e__ = cudaSetDevice(c->device);            \
         if (e__ != cudaSuccess) return fail_cuda(c, e__, "cudaSetDevice"); \
     }
+
+// +0 exactly (not -0, not tiny): what carrier_drift<ZONLY> may drop
+static bool is_plus_zero(double v) { return v == 0.0 && !std::signbit(v); }
+
+static void update_zonly_constant(Ctx *c)
+{
+    const char *env = std::getenv("EMC_ZONLY");
+    const bool allow = !(env && std::atoi(env) == 0);
+    c->zonly_constant = allow && is_plus_zero(c->dc.efield[0]) && is_plus_zero(c->dc.efield[1]);
+}
 
 static int fail(Ctx *c, int code, const char *msg)
 {
@@ -130,6 +141,7 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
     std::memset(c->mech_layers, 0, sizeof(c->mech_layers));
     default_layer(c);
     fill_devconst(c);
+    update_zonly_constant(c);
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) goto fail_cuda_create;
     c->sm_count = prop.multiProcessorCount;
@@ -215,11 +227,11 @@ static int upload_tables_layer(Ctx *c, int layer, const double *ek, int32_t n_en
             c->dc.n_mech[0] != n_mech[0] || c->dc.n_mech[1] != n_mech[1] || c->dc.n_mech[2] != n_mech[2])
             return fail(c, EMC_ERR_UNSUPPORTED, "all layers must share the energy grid and the per-valley column counts");
     }
-    // fast mechanism selection needs even-length (16-B aligned) rows of <= 12 columns that are
-    // non-decreasing and NaN-free (choose_mech in emc_device.cuh); anything else is scanned literally
+    // fast mechanism selection needs rows of <= 12 columns that are non-decreasing and NaN-free
+    // (choose_mech in emc_device.cuh); anything else is scanned literally
     int literal = 0;
     for (int v = 0; v < 3 && !literal; ++v) {
-        if ((n_mech[v] & 1) || n_mech[v] > 12) literal = 1;
+        if (n_mech[v] > 12) literal = 1;
         for (int64_t i = 0; i < n_energy && !literal; ++i) {
             const double *row = cum[v] + i * n_mech[v];
             for (int j = 0; j < n_mech[v]; ++j)
@@ -228,16 +240,30 @@ static int upload_tables_layer(Ctx *c, int layer, const double *ek, int32_t n_en
     }
     bool others = false;
     for (int l = 0; l < c->dc.n_layers; ++l) others = others || (l != layer && c->layer_tables[l]);
-    c->dc.literal_scan = (others ? c->dc.literal_scan : 0) | literal;
+    if (others && c->dc.literal_scan != literal)
+        return fail(c, EMC_ERR_UNSUPPORTED, "all layers must use the same table layout (padded or literal rows)");
+    c->dc.literal_scan = literal;
     for (int v = 0; v < 3; ++v) {
-        const size_t bytes = sizeof(double) * (size_t)n_energy * (size_t)n_mech[v];
+        // device rows: padded to 12 doubles with +inf (32-B aligned, no column-count guards in
+        // choose_mech), or the caller's layout when the rows have to be scanned literally
+        const int stride = literal ? n_mech[v] : 12;
+        c->dc.row_stride[v] = stride;
+        std::vector<double> staged;
+        const double *src = cum[v];
+        if (!literal) {
+            staged.assign((size_t)n_energy * 12, HUGE_VAL);
+            for (int64_t i = 0; i < n_energy; ++i)
+                std::memcpy(&staged[(size_t)i * 12], cum[v] + i * n_mech[v], sizeof(double) * (size_t)n_mech[v]);
+            src = staged.data();
+        }
+        const size_t bytes = sizeof(double) * (size_t)n_energy * (size_t)stride;
         double *&dst = c->d_cum_layers[layer][v];
         if (dst) { cudaFree(dst); dst = nullptr; }
         cudaError_t e = cudaMalloc(&dst, bytes + sizeof(double) * EMC_MAX_MECH);   // + one padding row
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(table)");
         e = cudaMemset(dst, 0, bytes + sizeof(double) * EMC_MAX_MECH);
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemset(table)");
-        e = cudaMemcpy(dst, cum[v], bytes, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(table)");
         c->dc.mat[layer].cum[v] = dst;
         c->dc.n_mech[v] = n_mech[v];
@@ -257,6 +283,7 @@ static int upload_tables_layer(Ctx *c, int layer, const double *ek, int32_t n_en
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(mech_layers)");
     }
     c->dc.n_energy = n_energy;
+    c->dc.n_energy_m2 = (double)(n_energy - 2);
     c->dc.ek_step = step;
     c->dc.inv_ek_step = 1 / step;
     c->dc.e_max = ek[n_energy - 1];
@@ -305,6 +332,13 @@ extern "C" int emc_set_layers(EmcCtx *ctx, const EmcLayer *layers, int32_t n_lay
     return EMC_OK;
 }
 
+extern "C" int emc_set_obs_phase(EmcCtx *ctx, int32_t before_step)
+{
+    CTX_OR_FAIL(ctx);
+    c->obs_before = before_step != 0;
+    return EMC_OK;
+}
+
 extern "C" int emc_select_layer(EmcCtx *ctx, int32_t layer)
 {
     CTX_OR_FAIL(ctx);
@@ -332,6 +366,7 @@ extern "C" int emc_set_efield(EmcCtx *ctx, const double efield[3])
     CTX_OR_FAIL(ctx);
     if (!efield) return fail(c, EMC_ERR_INVALID, "emc_set_efield: null");
     for (int a = 0; a < 3; ++a) c->params.efield[a] = c->dc.efield[a] = efield[a];
+    update_zonly_constant(c);
     return EMC_OK;
 }
 
@@ -347,6 +382,12 @@ extern "C" int emc_set_field_groups(EmcCtx *ctx, const double *efields, int32_t 
     c->dc.field_groups = c->d_groups;
     c->dc.n_groups = n_groups;
     c->dc.group_size = group_size;
+    {
+        const char *env = std::getenv("EMC_ZONLY");
+        bool z = !(env && std::atoi(env) == 0);
+        for (int g = 0; g < n_groups && z; ++g) z = is_plus_zero(efields[3 * g]) && is_plus_zero(efields[3 * g + 1]);
+        c->zonly_groups = z;
+    }
     return EMC_OK;
 }
 
@@ -385,6 +426,9 @@ static int flight_common(Ctx *c, FlightArgs &A, bool replay, int32_t field_mode,
     if (c->dc.n_layers > 1 && (c->exact_libm || A.mesh))
         return fail(c, EMC_ERR_UNSUPPORTED, "multi-layer devices: no EMC_EXACT_LIBM, no fused deposit (use emc_deposit)");
     A.ex = ex; A.ey = ey; A.ez = ez;
+    A.obs_before = c->obs_before;
+    c->dc.zonly = (field_mode == EMC_FIELD_CONSTANT && c->zonly_constant) ||
+                  (field_mode == EMC_FIELD_GROUPS && c->zonly_groups);
     if (A.n == 0) return EMC_OK;
     cudaError_t e = launch_flight(c, A, replay, field_mode, (cudaStream_t)stream);
     return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "flight_scatter launch");

@@ -246,9 +246,9 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
     if (FIELD == EMC_FIELD_CONSTANT) {
         efx = P.efield[0]; efy = P.efield[1]; efz = P.efield[2];
     } else if (FIELD == EMC_FIELD_GROUPS) {
-        efx = __ldg(P.field_groups + 3 * p.grp);
-        efy = __ldg(P.field_groups + 3 * p.grp + 1);
         efz = __ldg(P.field_groups + 3 * p.grp + 2);
+        if (P.zonly) { efx = 0.0; efy = 0.0; }
+        else { efx = __ldg(P.field_groups + 3 * p.grp); efy = __ldg(P.field_groups + 3 * p.grp + 1); }
     } else {
         // nearest-cell gather from the padded (nx+2,ny+2,nz+2) field of emc_field, V/m -> V/cm
         if (FIELD == EMC_FIELD_MESH_PACKED) {     // one 32-B record per cell, already V/cm
@@ -278,7 +278,7 @@ __device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, i
     }
     A.valley[i] = val;
     if (REPLAY) A.cursor[i] = (int32_t)cursor;
-    if (A.obs) obs_particle(P, P.mat[layer], acc, p.kx, p.ky, p.kz, p.z, val);
+    if (A.obs && !A.obs_before) obs_particle(P, P.mat[layer], acc, p.kx, p.ky, p.kz, p.z, val);
     if (DEPOSIT) {
         if (A.smem_cells > 0)
             deposit_ngp_particle(P, p.x, p.y, p.z, [&](int64_t c) { atomicAdd(&smesh[c], 1u); });
@@ -415,6 +415,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     layer = where_am_i(P, p.z);
                     if (layer < 0) { p.val = -(1 + EMC_FAULT_OUTSIDE); layer = 0; }
                 }
+                // obs_before: the observables of the ensemble AS LOADED (= the result of the previous
+                // timestep) are reduced here, where all 32 lanes are busy, instead of at retirement
+                // (17 of 32 lanes on average); a time loop reads the same rows one launch later
+                if (A.obs && A.obs_before) obs_particle(P, P.mat[ML ? layer : 0], acc, p.kx, p.ky, p.kz, p.z, p.val);
                 if (p.val >= 0) {                                 // else frozen after a fault
                     const double dte = p.dte;                     // :361
                     fly = true;
@@ -527,7 +531,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             field_at<FIELD>(P, A, p, cell, efx, efy, efz);
             const Mat &MT = P.mat[ML ? layer : 0];
             const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
-            carrier_drift(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
+            if ((FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) && P.zonly)
+                carrier_drift<true>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
+            else
+                carrier_drift<false>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             acc.c[4]++;
         }
         if (act && !pend && !park) retire<REPLAY, DEPOSIT, ML>(P, A, i, p, s0, acc, smesh);

@@ -36,6 +36,7 @@ struct FlightArgs {
     unsigned int *ticket;
     int64_t *mesh;
     int32_t smem_cells;
+    int32_t obs_before;          // emc_set_obs_phase: reduce the observables of the state as loaded
     const MechMeta *mech_layers; // multi-layer: device array of n_layers mechanism-metadata blocks
 };
 
@@ -47,6 +48,9 @@ struct Ctx {
     MechMeta *d_mech_layers = nullptr;
     EmcLayer layers[EMC_MAX_LAYERS];
     bool layer_tables[EMC_MAX_LAYERS] = {false, false, false, false};
+    int obs_before = 0;           // emc_set_obs_phase
+    bool zonly_constant = false;  // dc.efield has Ex = Ey = +0
+    bool zonly_groups = false;    // every field group has Ex = Ey = +0
     int batch_layer = 0;          // emc_select_layer: material of the single-function batches
     double *d_cum_layers[EMC_MAX_LAYERS][3] = {};
     double *d_background_z = nullptr;   // emc_set_background_profile

@@ -98,6 +98,7 @@ class Context:
             raise abi.EmcError(st, msg.decode() if msg else "?")
         self.h = h
         self._keep = []
+        self.obs_before = False
         if tables is None:
             from . import init_, scatter_
             dfEk = init_.init_energy_df(2, 10000)
@@ -222,6 +223,13 @@ class Context:
             self.check(self.lib.emc_upload_tables_layer(self.h, i, *args))
         self.layers = layers
 
+    def set_obs_phase(self, before_step: bool) -> None:
+        """``True``: ``Ensemble.step(observe=True)`` reduces the observables of the ensemble as the
+        step FOUND it (= after the previous step) in the kernel's fully occupied load phase;
+        ``engine.run_steps`` shifts the rows back.  Default ``False``: after the step."""
+        self.check(self.lib.emc_set_obs_phase(self.h, int(bool(before_step))))
+        self.obs_before = bool(before_step)
+
     def select_layer(self, layer: int) -> None:
         """Material used by ``emc_calc_energy`` / ``emc_scatter`` (their ``mat`` / ``mat_i`` argument)."""
         self.check(self.lib.emc_select_layer(self.h, int(layer)))
@@ -246,7 +254,11 @@ class Context:
 
 
 def _obs_from_tensor(t) -> dict:
-    raw = t.cpu().numpy()
+    return _obs_from_raw(t.cpu().numpy())
+
+
+def _obs_from_raw(raw) -> dict:
+    raw = np.ascontiguousarray(raw)
     d = raw[:5].view(np.float64)
     c = raw[5:]
     return dict(sum_z=float(d[0]), sum_vz=float(d[1]), sum_e=float(d[2]), sum_vz2=float(d[3]),
@@ -266,6 +278,7 @@ class Ensemble:
         self.state = torch.zeros((7, self.n), dtype=torch.float64, device=ctx.device)
         self.valley = torch.zeros(self.n, dtype=torch.int32, device=ctx.device)
         self.obs = torch.zeros(11, dtype=torch.int64, device=ctx.device)    # one EmcObs (88 B)
+        self._obs_cache = None
 
     def _ptrs(self):
         base, stride = self.state.data_ptr(), self.n * 8
@@ -306,9 +319,13 @@ class Ensemble:
 
     # -- the timestep -----------------------------------------------------------------
     def step(self, step: int, seed: int, field_mode: int = abi.FIELD_CONSTANT, mesh: "Mesh | None" = None,
-             observe: bool = True, deposit: bool = False):
-        """One timestep of main_.py:360-397 for the whole ensemble (asynchronous)."""
+             observe: bool = True, deposit: bool = False, obs_out=None):
+        """One timestep of main_.py:360-397 for the whole ensemble (asynchronous).  ``obs_out``: an
+        11-element int64 device tensor that receives the EmcObs instead of ``self.obs``."""
         c = self.ctx
+        obs_t = self.obs if obs_out is None else obs_out
+        if obs_out is None:
+            self._obs_cache = None
         ex = ey = ez = None
         if field_mode == abi.FIELD_MESH:
             ex, ey, ez = mesh.ex.data_ptr(), mesh.ey.data_ptr(), mesh.ez.data_ptr()
@@ -316,13 +333,47 @@ class Ensemble:
             ex = mesh.e4.data_ptr()
         c.check(c.lib.emc_flight_scatter(
             c.h, *self._ptrs(), self.n, field_mode, ex, ey, ez, seed, self.pid_offset, step,
-            self.obs.data_ptr() if observe else None,
+            obs_t.data_ptr() if observe else None,
             mesh.counts.data_ptr() if deposit else None, c.stream))
+
+    def run_steps(self, first_step: int, n_steps: int, seed: int, step_fn=None, **step_kw):
+        """``n_steps`` timesteps with the per-step observables of main_.py:394-403, no host round
+        trip inside the loop.  Uses the before-step observable phase (``emc_set_obs_phase``): launch
+        c reduces the state that step c-1 left behind while it loads it (all lanes busy), one
+        stand-alone ``emc_observables`` reads the final state, and the rows are shifted back so
+        that ``rows[c]`` describes the ensemble AFTER step ``first_step + c`` exactly as with
+        ``step(); last_obs()``.  ``step_fn(c, obs_out)`` replaces the plain ``step`` (coupled loops)."""
+        torch = _torch()
+        c = self.ctx
+        hist = torch.zeros((n_steps + 1, 11), dtype=torch.int64, device=c.device)
+        was = c.obs_before
+        c.set_obs_phase(True)
+        try:
+            for k in range(n_steps):
+                if step_fn is not None:
+                    step_fn(first_step + k, hist[k])
+                else:
+                    self.step(first_step + k, seed, obs_out=hist[k], **step_kw)
+        finally:
+            c.set_obs_phase(was)
+        p = self._ptrs()
+        final = abi.EmcObs()
+        c.check(c.lib.emc_observables(c.h, p[0], p[1], p[2], p[5], p[7], self.n, C.byref(final), c.stream))
+        raw = hist.cpu().numpy()
+        rows = []
+        for k in range(n_steps):
+            work = _obs_from_raw(raw[k])                      # n_segments / n_events of step k
+            state = _obs_from_raw(raw[k + 1]) if k + 1 < n_steps else final.as_dict()
+            state["n_segments"], state["n_events"] = work["n_segments"], work["n_events"]
+            rows.append(state)
+        self._obs_cache = dict(rows[-1]) if rows else None      # what last_obs() reports after the loop
+        return rows
 
     def step_replay(self, uniforms, cursor, field_mode: int = abi.FIELD_CONSTANT, mesh: "Mesh | None" = None,
                     observe: bool = True, deposit: bool = False):
         """Replay mode: uniforms (n, L) float64 device tensor, cursor (n,) int32 device tensor."""
         c = self.ctx
+        self._obs_cache = None
         assert uniforms.is_contiguous() and uniforms.shape[0] == self.n
         ex = ey = ez = None
         if field_mode == abi.FIELD_MESH:
@@ -336,7 +387,10 @@ class Ensemble:
             mesh.counts.data_ptr() if deposit else None, c.stream))
 
     def last_obs(self) -> dict:
-        """Observables written by the last ``step(observe=True)`` (synchronises)."""
+        """Observables written by the last ``step(observe=True)`` (synchronises), or the last row
+        of the last ``run_steps``."""
+        if getattr(self, "_obs_cache", None) is not None:
+            return dict(self._obs_cache)
         return _obs_from_tensor(self.obs)
 
     def observables(self) -> dict:
@@ -539,15 +593,21 @@ class CoupledStepper:
         else:
             m.field()
 
-    def step(self, observe: bool = True):
+    def step(self, observe: bool = True, obs_out=None):
         m = self.mesh
         m.zero_counts()
         self.ens.step(self.n_steps, self.seed, field_mode=self.field_mode, mesh=m, observe=observe,
-                      deposit=self.fuse_deposit)
+                      deposit=self.fuse_deposit, obs_out=obs_out)
         if not self.fuse_deposit:
             m.deposit(self.ens)
         self._solve()
         self.n_steps += 1
+
+    def run_steps(self, n_steps: int):
+        """``n_steps`` coupled timesteps; rows[c] = observables after step c (``Ensemble.run_steps``:
+        reduced in the load phase of the next launch, no host round trip inside the loop)."""
+        return self.ens.run_steps(self.n_steps, n_steps, self.seed,
+                                  step_fn=lambda _c, out: self.step(observe=True, obs_out=out))
 
 
 class HostStepper:

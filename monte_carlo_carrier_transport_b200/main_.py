@@ -217,14 +217,20 @@ def run(num_carr=None, pts=None, seed=12345, elec_field=None, coords=None, valle
         ens.init(seed)
     rows = []
     hist = [] if history else None
-    for c in range(pts):
-        ens.step(c, seed)
-        o = engine.summarize(ens.last_obs())
+    if history:
+        for c in range(pts):
+            ens.step(c, seed)
+            o = engine.summarize(ens.last_obs())
+            o.update(step=c, t_ps=c * param.dt * 1e12)
+            rows.append(o)
+            hist.append(ens.coords())
+        return rows, ens, hist
+    # no per-step host round trip: observables reduced in the load phase of the next launch
+    for c, obs in enumerate(ens.run_steps(0, pts, seed)):
+        o = engine.summarize(obs)
         o.update(step=c, t_ps=c * param.dt * 1e12)
         rows.append(o)
-        if history:
-            hist.append(ens.coords())
-    return (rows, ens, hist) if history else (rows, ens)
+    return rows, ens
 
 
 def script(scat_cond=False, save_cond=False, drift_cond=False, filename="EMC_results.csv", seed=12345):

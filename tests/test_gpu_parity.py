@@ -681,3 +681,29 @@ def test_ragged_ensemble_sizes_vs_oracle(ctx, torch_mod, n):
         assert k_err(co[ok, :3], ref[ok, :3]) < 1e-6
     frozen = ~ok & (v < 0)
     assert np.array_equal(co[frozen], coords[frozen])                    # frozen on entry: untouched
+
+
+def test_observables_before_step_phase(ctx, torch_mod):
+    """emc_set_obs_phase(1): launch c reduces the ensemble as it FOUND it; Ensemble.run_steps shifts
+    the rows back, so they must equal step(); last_obs() of the default phase row for row, with the
+    floating-point sums bit-identical (same fixed-order reduction over the same values) whenever
+    the launch shape is the same."""
+    from monte_carlo_carrier_transport_b200 import engine
+    g = helpers.golden_params()["phys"]
+    n, steps, seed = 30011, 6, 515
+    coords, v, dtau = hot_ensemble(n, 61, g)
+    a = engine.Ensemble(ctx, n).load(coords, v, dtau)
+    b = engine.Ensemble(ctx, n).load(coords, v, dtau)
+    ref = []
+    for s in range(steps):
+        a.step(s, seed)
+        ref.append(a.last_obs())
+    rows = b.run_steps(0, steps, seed)
+    assert ctx.obs_before is False                       # restored
+    for s in range(steps):
+        for key in ("n_valley", "n_fault", "n_segments", "n_events"):
+            assert rows[s][key] == ref[s][key], (s, key)
+        for key in ("sum_z", "sum_vz", "sum_e", "sum_vz2", "sum_e2"):
+            assert abs(rows[s][key] - ref[s][key]) <= 1e-12 * abs(ref[s][key]), (s, key)
+    ca, cb = a.coords(), b.coords()
+    assert all(np.array_equal(x, y) for x, y in zip(ca, cb))      # the trajectories do not depend on the phase
