@@ -152,8 +152,10 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 #ifndef EMC_STAGE_REFILL
 // 1: cp.async (LDGSTS) the next refill batch into shared memory while the current one is
 // processed, so the refill phase never waits on HBM.  Measured with the L2 prefetch one batch
-// further ahead: 1.387 -> 1.370 ms per 2.4e7-particle timestep.
-#define EMC_STAGE_REFILL 1
+// further ahead: 1.387 -> 1.370 ms per 2.4e7-particle timestep in round r1h; since the event
+// body lost 15 % of its instructions (r1n) the staging's own 5 % of issue slots cost more than
+// the wait it hides: 1.177 ms staged vs 1.160 ms with plain loads behind the L2 prefetch.
+#define EMC_STAGE_REFILL 0
 #endif
 #ifndef EMC_PREFETCH_BATCHES
 // refill batches to prefetch ahead into L2 (0 = off).  Measured: 0 -> 1.475 ms, 1 -> 1.409 ms,
