@@ -303,8 +303,13 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
 // where_am_i before every drift, scatter and observable (main_.py:366,372,377,387,393) and selects
 // the material constants, the table and the mechanism metadata.  ML = false compiles to the
 // single-material code (layer 0 everywhere).
+#ifdef EMC_FLIGHT_MAXNREG
+#define EMC_FLIGHT_BOUNDS __maxnreg__(EMC_FLIGHT_MAXNREG)     // tuning: explicit register cap instead of launch bounds
+#else
+#define EMC_FLIGHT_BOUNDS __launch_bounds__(FLIGHT_THREADS, EMC_FLIGHT_MIN_BLOCKS)
+#endif
 template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML>
-__global__ void __launch_bounds__(FLIGHT_THREADS, EMC_FLIGHT_MIN_BLOCKS)
+__global__ void EMC_FLIGHT_BOUNDS
 flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg,
                       const __grid_constant__ FlightArgs A)
 {
@@ -433,12 +438,16 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             stage_batch(WQ, A, next + lane, wend, lane);
 #endif
 #if EMC_PREFETCH_BATCHES > 0
-            {   // pull the state rows of a later refill batch into L2 while this one is processed
-                const int64_t j = next + (int64_t)(EMC_PREFETCH_BATCHES - 1) * 32 + lane;
-                if (j < wend) {
-                    prefetch_l2(A.kx + j); prefetch_l2(A.ky + j); prefetch_l2(A.kz + j);
-                    prefetch_l2(A.x + j); prefetch_l2(A.y + j); prefetch_l2(A.z + j);
-                    prefetch_l2(A.dtau + j); prefetch_l2(A.valley + j);
+            {   // pull the state rows of a later refill batch into L2 while this one is processed:
+                // a batch is 256 B of each of the seven fp64 rows (two 128-B lines) and 128 B of the
+                // valley row, so ONE prefetch instruction covers it -- lane l < 14 takes line l&1 of
+                // row l>>1, lane 14 the valley line (the row pointers are consecutive kernel
+                // parameters, indexed from the constant bank)
+                const int64_t j0 = next + (int64_t)(EMC_PREFETCH_BATCHES - 1) * 32;
+                if (j0 < wend && lane < 15 && (!(lane & 1) || lane == 14 || j0 + 16 < wend)) {
+                    const char *base = reinterpret_cast<const char *>((&A.kx)[lane >> 1]);
+                    const int64_t off = lane < 14 ? j0 * 8 + (lane & 1) * 128 : j0 * 4;
+                    prefetch_l2(base + off);
                 }
             }
 #endif
