@@ -289,6 +289,55 @@ def other_configs_bench(torch, dist, engine, abi, local, rank, world, barrier, s
     return out
 
 
+def diode_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=20, warmup=5):
+    """BASELINE configs[2]: 1-D n+-n-n+ diode (three layers 1e17/1e16/1e17 cm^-3, per-layer tables
+    and background charge, where_am_i in the kernel), 10^7 super-particles, 1 x 1 x 1024 mesh,
+    Poisson every timestep.  Median ms per coupled timestep over `steps`, CUDA events."""
+    from monte_carlo_carrier_transport_b200 import configs, init_
+    n_global = 10_000_000
+    n = n_global // world
+    layers = configs.diode_layers()
+    p = engine.params_from_reference_modules(efield=(0.0, 0.0, 0.0), num_carr=n_global)
+    mesh_shape = (1, 1, 1024)
+    for a in range(3):
+        p.seg[a] = mesh_shape[a]
+        p.dl[a] = p.tot_dim[a] / mesh_shape[a]
+    cell = p.dl[0] * p.dl[1] * p.dl[2]
+    p.rho_background = float(-init_.GaAs.dope * cell * 1e6)
+    p.rho_increment = float(sum(l.dope * l.lx * l.ly * l.lz * 1e6 for l in layers) / n_global)
+    ctx = engine.Context(p, device=local)
+    ctx.set_layers(layers, init_weights=[l.dope * l.lz for l in layers])
+    zc = (np.arange(mesh_shape[2]) + 0.5) * p.dl[2]
+    dope_z = np.array([layers[init_.where_am_i(layers, z)["current_layer"]].dope for z in zc])
+    ctx.set_background_profile(-dope_z * cell * 1e6)
+    ens = engine.Ensemble(ctx, n, pid_offset=rank * n).init(SEED + 3)
+    cs = engine.CoupledStepper(ctx, ens, seed=SEED + 3, max_sweeps=2000).prime(max_sweeps=50_000)
+    for _ in range(warmup):
+        cs.step()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    hist = torch.zeros((steps, 11), dtype=torch.int64, device=ctx.device)
+    ctx.set_obs_phase(True)
+    barrier()
+    ev[0].record()
+    for s in range(steps):
+        cs.step(observe=True, obs_out=hist[s])
+        ev[s + 1].record()
+    final = ens.observables()
+    barrier()
+    ctx.set_obs_phase(False)
+    per = np.array([ev[s].elapsed_time(ev[s + 1]) for s in range(steps)])
+    t = torch.tensor([np.median(per)], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sweeps = cs.mesh.last_solve()[0]
+    seg = int(hist[-1, 9].cpu())
+    ctx.close()
+    return {"ms_per_timestep": float(t.cpu()[0]), "particles_per_gpu": n, "mesh": "1x1x1024", "layers": 3,
+            "sor_sweeps_last_step": sweeps, "segments_last_step": seg, "faulted_particles": int(final["n_fault"]),
+            "valley_counts": final["n_valley"]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -382,6 +431,9 @@ def run_ours(args):
     del hs
     coupled = coupled_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
     by_config = other_configs_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
+    if by_config is not None:
+        by_config["configs[2] n+-n-n+ diode, 3 layers, 1e7 super-particles, Poisson every timestep"] = \
+            diode_bench(torch, dist, engine, abi, local, rank, world, barrier)
 
     # ---- max over ranks, totals over ranks ---------------------------------------------------
     t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=ctx.device)

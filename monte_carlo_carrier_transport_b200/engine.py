@@ -657,6 +657,9 @@ class HostStepper:
         """One timestep on the pinned host arrays, in place; returns the observables."""
         torch = _torch()
         c, lib = self.ctx, self.ctx.lib
+        if c.obs_before:
+            raise RuntimeError("HostStepper returns the observables AFTER the step: call "
+                               "Context.set_obs_phase(False) first")
         cur = torch.cuda.current_stream(c.device)
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(cur)
