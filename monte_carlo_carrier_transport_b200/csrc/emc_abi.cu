@@ -46,6 +46,34 @@ static int fail_cuda(Ctx *c, cudaError_t e, const char *where)
     return EMC_ERR_CUDA;
 }
 
+// init_.where_am_i (init_.py:36-56) on the host, the reference's own arithmetic
+static int where_am_i_host(const EmcLayer *layers, int n, double dist)
+{
+    if (dist < 0) return -1;
+    for (int l = 0; l < n; ++l) {
+        if (dist <= layers[l].lz) return l;
+        dist -= layers[l].lz;
+    }
+    return -1;
+}
+
+// largest double d >= 0 with where_am_i(d) in [0, l]: the loop is monotone in d, so bisection over
+// the (ordered) bit patterns of the non-negative doubles finds it exactly
+static double layer_threshold(const EmcLayer *layers, int n, int l)
+{
+    auto inside = [&](double d) { const int w = where_am_i_host(layers, n, d); return w >= 0 && w <= l; };
+    uint64_t lo = 0, hi = 0x7ff0000000000000ULL;        // +0 is inside (layer 0), +inf is not
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        double d;
+        std::memcpy(&d, &mid, sizeof(d));
+        if (inside(d)) lo = mid; else hi = mid;
+    }
+    double d;
+    std::memcpy(&d, &lo, sizeof(d));
+    return d;
+}
+
 static void fill_devconst(Ctx *c)
 {
     const EmcParams &p = c->params;
@@ -71,6 +99,7 @@ static void fill_devconst(Ctx *c)
         m.e_phonon = L.e_phonon;
         m.ion_eb = L.ion_eb;
         d.layer_lz[l] = L.lz;
+        d.layer_thr[l] = layer_threshold(c->layers, c->dc.n_layers, l);
     }
     {   // cumulative shares of the initial ensemble (all weights 0: uniform z like init_.py:200)
         double tot = 0.0, run = 0.0;
