@@ -245,6 +245,13 @@ int emc_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, int32_t *valley
  * and its log().  mismatches (HOST): counts for division, sqrt, log; all must be 0. */
 int emc_selftest_math(EmcCtx *ctx, int64_t n, uint64_t seed, int64_t mismatches[3], void *stream);
 
+/* Self-test of emc_mesh_to_rho's closed-form replay of the reference's sequential accumulation
+ * (`rho[idx] += charge` once per particle, poisson_.py:36): n Philox-drawn (background, increment,
+ * count <= max_count) triples, result compared BIT FOR BIT with the literal loop. *mismatches (HOST)
+ * must be 0. */
+int emc_selftest_accumulate(EmcCtx *ctx, int64_t n, uint64_t seed, int32_t max_count,
+                            int64_t *mismatches, void *stream);
+
 /* ---- layout helpers for callers that hold the reference's (N,6) array (main_.py:51-52) ----- */
 int emc_aos_to_soa(EmcCtx *ctx, const double *coords6, int64_t n, double *kx, double *ky,
                    double *kz, double *x, double *y, double *z, void *stream);

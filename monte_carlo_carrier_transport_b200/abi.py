@@ -90,6 +90,7 @@ SIGNATURES = {
     "emc_carrier_drift": (C.c_int, [_vp] + [_dp] * 6 + [_dp, _dp, _dp, _i64, _vp]),
     "emc_scatter": (C.c_int, [_vp, _dp, _dp, _dp, _ip, _dp, _i64, _ip, _ip, _ip, _vp]),
     "emc_selftest_math": (C.c_int, [_vp, _i64, _u64, C.POINTER(_i64), _vp]),
+    "emc_selftest_accumulate": (C.c_int, [_vp, _i64, _u64, _i32, C.POINTER(_i64), _vp]),
     "emc_aos_to_soa": (C.c_int, [_vp, _dp, _i64] + [_dp] * 6 + [_vp]),
     "emc_soa_to_aos": (C.c_int, [_vp] + [_dp] * 6 + [_i64, _dp, _vp]),
     "emc_deposit": (C.c_int, [_vp, _dp, _dp, _dp, _i64, _lp, _i32, _vp]),

@@ -578,6 +578,25 @@ extern "C" int emc_selftest_math(EmcCtx *ctx, int64_t n, uint64_t seed, int64_t 
     return EMC_OK;
 }
 
+extern "C" int emc_selftest_accumulate(EmcCtx *ctx, int64_t n, uint64_t seed, int32_t max_count, int64_t *mismatches,
+                                       void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!mismatches || n < 0 || max_count < 1) return fail(c, EMC_ERR_INVALID, "emc_selftest_accumulate: bad argument");
+    unsigned long long *d = nullptr, h = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMalloc(&d, sizeof(unsigned long long));
+    if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(selftest)");
+    if ((e = cudaMemsetAsync(d, 0, sizeof(h), st)) == cudaSuccess &&
+        (e = launch_selftest_accumulate(c, n, seed, max_count, d, st)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, st)) == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(c, e, "selftest_accumulate");
+    *mismatches = (int64_t)h;
+    return EMC_OK;
+}
+
 extern "C" int emc_aos_to_soa(EmcCtx *ctx, const double *coords6, int64_t n, double *kx, double *ky, double *kz,
                               double *x, double *y, double *z, void *stream)
 {

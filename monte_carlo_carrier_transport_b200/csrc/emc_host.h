@@ -101,6 +101,8 @@ cudaError_t launch_selftest_math(Ctx *ctx, int64_t n, uint64_t seed, unsigned lo
 // emc_mesh.cu
 cudaError_t launch_deposit(Ctx *ctx, const double *x, const double *y, const double *z, int64_t n, int64_t *mesh,
                            int scheme, cudaStream_t st);
+cudaError_t launch_selftest_accumulate(Ctx *ctx, int64_t n, uint64_t seed, int max_count, unsigned long long *bad_dev,
+                                       cudaStream_t st);
 cudaError_t launch_mesh_to_rho(Ctx *ctx, const int64_t *mesh, int scheme, double *rho_pad, cudaStream_t st);
 cudaError_t launch_field(Ctx *ctx, const double *u_pad, double *ex, double *ey, double *ez, cudaStream_t st);
 // returns 0 / EMC_ERR_*; fills sweeps/err; synchronises

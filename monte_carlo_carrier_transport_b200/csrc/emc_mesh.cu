@@ -188,6 +188,97 @@ cudaError_t launch_mesh_allreduce_p2p(Ctx *ctx, const int64_t *const *in_ptrs, i
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// r after m sequential `r = r + inc` in round-to-nearest-even double arithmetic -- the
+// reference's accumulation `rho[idx] += charge` once per particle (poisson_.py:36) -- WITHOUT m
+// dependent additions.  (A cell of the 1-D diode mesh holds 10^4 super-particles: the literal loop
+// was 40-80 us of one serial DADD chain per thread, a quarter of that configuration's timestep.)
+//
+// While r stays strictly inside one binade [2^e, 2^(e+1)) (in magnitude) every value is a
+// multiple of u = 2^(e-52), so RN(r + inc) = r + d with d = inc rounded to the nearest multiple
+// of u -- the same d for every step of the binade, as long as inc/u is not exactly half-way
+// between two integers (then the tie rule looks at the parity of r: taken literally).  So the
+// steps of a binade collapse into one exact multiply-add (k*d and r + k*d are multiples of u below
+// 2^(e+1): representable), with literal single steps only within two steps of a binade boundary,
+// at zero / subnormals, and for ties.  d == 0 means r has stopped moving.  Exactly the literal
+// result for every input; emc_selftest_accumulate checks it against the literal loop.
+// ------------------------------------------------------------------------------------------
+__device__ double add_repeated(double r, double inc, long long m)
+{
+    if (inc < 0) return -add_repeated(-r, -inc, m);          // RN is symmetric (one level: -inc > 0)
+    if (!(inc > 0)) {                                        // zero or NaN increment
+        for (long long t = 0; t < m && t < 2; ++t) r = r + inc;
+        return r;
+    }
+    while (m > 0) {
+        const double a = fabs(r);
+        bool literal = !(a >= 4.450147717014403e-308) || !(a < 4.49e307);     // zero, subnormal fringe, huge, NaN
+        long long k = 0;
+        double d = 0.0;
+        if (!literal) {
+            const int e = (int)((__double2hiint(a) >> 20) & 0x7ff) - 1023;    // a in [2^e, 2^(e+1))
+            const double u = __hiloint2double((e - 52 + 1023) << 20, 0);       // 2^(e-52), normal: e >= -1021
+            const double lo = __hiloint2double((e + 1023) << 20, 0);           // 2^e
+            const double qf = inc * __hiloint2double((52 - e + 1023) << 20, 0);   // inc / u, exact unless it overflows
+            if (!(qf < 4503599627370496.0)) literal = true;                    // inc >= 2^52 u: one step leaves the binade
+            else {
+                const double q = rint(qf);
+                if (fabs(qf - q) == 0.5) literal = true;                       // tie: depends on the parity of r
+                else {
+                    d = q * u;
+                    if (d == 0.0) return r;                                    // inc < u/2: r never changes again
+                    // room to the boundary the walk approaches, keeping two steps of margin
+                    const double room = r > 0 ? (2 * lo - r) - 2 * d : (a - lo) - 2 * d;
+                    if (!(room > d)) literal = true;
+                    else {
+                        const double kf = floor(room / d) - 1;
+                        k = kf > 9.0e18 ? m : (long long)kf;
+                        if (k > m) k = m;
+                        if (k < 1) literal = true;
+                    }
+                }
+            }
+        }
+        if (literal) { r = r + inc; --m; }
+        else { r = r + (double)k * d; m -= k; }
+    }
+    return r;
+}
+
+__global__ void selftest_accumulate_kernel(int64_t n, uint64_t seed, int max_count, unsigned long long *bad)
+{
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    unsigned long long mism = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint4 r0 = philox4x32_10(make_uint4(0u, 0xacc0acc0u, (uint32_t)i, (uint32_t)(i >> 32)), key);
+        const uint4 r1 = philox4x32_10(make_uint4(1u, 0xacc0acc0u, (uint32_t)i, (uint32_t)(i >> 32)), key);
+        // background of either sign over 24 binades, increment over 40 binades, sometimes with few
+        // mantissa bits (ties, exact sums) and sometimes exactly cancelling the background
+        double bg = ldexp(1.0 + u53(r0.x, r0.y), (int)(r0.z % 24u) - 12);
+        if (r0.w & 1u) bg = -bg;
+        if ((r0.w & 0xf0u) == 0) bg = 0.0;
+        double inc = ldexp(1.0 + u53(r1.x, r1.y), (int)(r1.z % 40u) - 30);
+        if (r1.w & 2u) inc = ldexp((double)(1u + (r1.x & 7u)), (int)(r1.z % 40u) - 32);     // short mantissa
+        if ((r1.w & 0x300u) == 0 && bg < 0) inc = -bg / (double)(1 + (r1.y % 50u));         // passes through zero
+        if (r1.w & 4u) inc = -inc;
+        const long long m = (long long)(u53(r0.y, r1.y) * u53(r0.x, r1.w) * max_count);
+        double lit = bg;
+        for (long long t = 0; t < m; ++t) lit = lit + inc;
+        const double fast = add_repeated(bg, inc, m);
+        mism += __double_as_longlong(lit) != __double_as_longlong(fast);
+    }
+    if (mism) atomicAdd(bad, mism);
+}
+
+cudaError_t launch_selftest_accumulate(Ctx *ctx, int64_t n, uint64_t seed, int max_count, unsigned long long *bad_dev,
+                                       cudaStream_t st)
+{
+    ctx->launches++;
+    selftest_accumulate_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(n, seed, max_count, bad_dev);
+    return cudaGetLastError();
+}
+
 // rho_pad: zero halo (np.pad, poisson_.py:53); interior = background + charge
 __global__ void mesh_to_rho_kernel(const __grid_constant__ DevConst P, const long long *__restrict__ mesh, int scheme,
                                    double background, const double *__restrict__ background_z, double increment,
@@ -205,7 +296,7 @@ __global__ void mesh_to_rho_kernel(const __grid_constant__ DevConst P, const lon
     if (background_z) background = background_z[k - 1];      // doping profile (emc_set_background_profile)
     double r = background;                                   // poisson_.py:27
     if (scheme == EMC_DEPOSIT_NGP) {
-        for (long long t = 0; t < m; ++t) r += increment;    // poisson_.py:36, one += per hit, in sequence
+        r = add_repeated(r, increment, m);                   // poisson_.py:36, one += per hit, in sequence
     } else {
         r = background + increment * ((double)m / 4294967296.0);
     }

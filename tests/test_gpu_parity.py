@@ -73,6 +73,17 @@ def test_guard_free_math_is_bit_identical_to_cuda_libm(ctx):
     assert list(bad) == [0, 0, 0], dict(div=bad[0], sqrt=bad[1], log=bad[2])
 
 
+def test_sequential_accumulation_closed_form(ctx):
+    """emc_mesh_to_rho replays `rho[idx] += charge` (poisson_.py:36, once per particle) binade by
+    binade instead of count-many dependent additions: identical bits to the literal loop for random
+    (background, increment, count) incl. sign changes, ties, exact cancellation and stagnation."""
+    bad = C.c_int64(-1)
+    ctx.check(ctx.lib.emc_selftest_accumulate(ctx.h, 3_000_000, 777, 3000, C.byref(bad), ctx.stream))
+    assert bad.value == 0
+    ctx.check(ctx.lib.emc_selftest_accumulate(ctx.h, 200_000, 778, 60000, C.byref(bad), ctx.stream))
+    assert bad.value == 0
+
+
 def test_free_flight_kat(ctx, torch_mod):
     torch = torch_mod
     k = helpers.golden_npz("kat")
