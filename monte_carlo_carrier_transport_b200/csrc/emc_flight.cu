@@ -157,6 +157,14 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 // the wait it hides: 1.177 ms staged vs 1.160 ms with plain loads behind the L2 prefetch.
 #define EMC_STAGE_REFILL 0
 #endif
+#ifndef EMC_STAGE_FIELD
+// 1: EMC_FIELD_MESH_PACKED gathers the 32-byte field record of a particle's cell with cp.async
+// into a per-lane shared-memory slot as soon as the particle is popped / loaded; the flight
+// segment, ~500 instructions later in an event pass, reads it from there.  The gather (L2, often
+// DRAM: the streaming particle state evicts the 34 MB field) no longer stalls the segment:
+// profiles/r1s: long-scoreboard stall 2.1 cycles per issue with the prefetch.L1 hint.
+#define EMC_STAGE_FIELD 1
+#endif
 #ifndef EMC_PREFETCH_BATCHES
 // refill batches to prefetch ahead into L2 (0 = off).  Measured: 0 -> 1.475 ms, 1 -> 1.409 ms,
 // 2 -> 1.411 ms, 4 -> 1.423 ms per 2.4e7-particle timestep.
@@ -182,6 +190,10 @@ struct WarpQueues {
 #if EMC_STAGE_REFILL
     double stage[7][32];                     // next refill batch, landed here by cp.async (LDGSTS)
     int32_t stage_val[32];
+#endif
+#if EMC_STAGE_FIELD
+    double2 fs_a[32], fs_b[32];              // EMC_FIELD_MESH_PACKED: (ex, ey), (ez, 0) of each lane's cell
+    double2 rs_a[32], rs_b[32];              // the same for the NEXT refill batch, staged one refill ahead
 #endif
 };
 
@@ -229,11 +241,27 @@ __device__ __forceinline__ int64_t mesh_cell(const DevConst &P, const Particle &
 // The field a flight segment sees depends only on where the segment STARTS, and a scatter event
 // does not move the particle: so the event passes know the cell as soon as a particle is popped
 // and pull its field record towards L1 ~500 instructions before the segment needs it.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc));
+}
+
 template <int FIELD>
-__device__ __forceinline__ void field_prefetch(const FlightArgs &A, int64_t c)
+__device__ __forceinline__ void field_prefetch(const FlightArgs &A, int64_t c, WarpQueues &WQ, int lane,
+                                               bool refill_slot = false)
 {
     if (FIELD == EMC_FIELD_MESH_PACKED) {
+#if EMC_STAGE_FIELD
+        // each lane stages ITS OWN record and reads it back itself: the per-thread cp.async group
+        // semantics are all the ordering needed
+        const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
+        cp_async16(refill_slot ? &WQ.rs_a[lane] : &WQ.fs_a[lane], rec);
+        cp_async16(refill_slot ? &WQ.rs_b[lane] : &WQ.fs_b[lane], rec + 1);
+        asm volatile("cp.async.commit_group;");
+#else
         asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ex + 4 * c));
+#endif
     } else if (FIELD == EMC_FIELD_MESH) {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ex + c));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ey + c));
@@ -243,7 +271,8 @@ __device__ __forceinline__ void field_prefetch(const FlightArgs &A, int64_t c)
 
 template <int FIELD>
 __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A, const Particle &p, int64_t c,
-                                         double &efx, double &efy, double &efz)
+                                         double &efx, double &efy, double &efz, WarpQueues &WQ, int lane,
+                                         bool refill_slot = false)
 {
     if (FIELD == EMC_FIELD_CONSTANT) {
         efx = P.efield[0]; efy = P.efield[1]; efz = P.efield[2];
@@ -254,8 +283,13 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
     } else {
         // nearest-cell gather from the padded (nx+2,ny+2,nz+2) field of emc_field, V/m -> V/cm
         if (FIELD == EMC_FIELD_MESH_PACKED) {     // one 32-B record per cell, already V/cm
+#if EMC_STAGE_FIELD
+            // landed: the caller waited for the group
+            const double2 a = refill_slot ? WQ.rs_a[lane] : WQ.fs_a[lane], b = refill_slot ? WQ.rs_b[lane] : WQ.fs_b[lane];
+#else
             const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
             const double2 a = __ldg(rec), b = __ldg(rec + 1);
+#endif
             efx = a.x; efy = a.y; efz = b.x;
         } else {
             efx = __ldg(A.ex + c) * 1e-2;
@@ -350,6 +384,11 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     stage_batch(WQ, A, next + lane, wend, lane);
 #endif
     int qn = 0, qsc = 0;                          // lengths of the event / scatter queues (warp-uniform)
+    // EMC_FIELD_MESH_PACKED: a refill pass gathers the field record of the FOLLOWING batch (whose
+    // positions it loads early and turns into a cell after its own flight), so that a refill never
+    // waits for two dependent memory round trips (state, then field)
+    constexpr bool AHEAD = EMC_STAGE_FIELD && FIELD == EMC_FIELD_MESH_PACKED;
+    bool field_staged = false;                    // the batch at `next` has its field record in the rs slots
     const double dt = P.dt;
 
     // EMC_FIELD_GROUPS: group index / remainder of the slice's next particle, advanced without
@@ -390,10 +429,16 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         int64_t cell = 0;                                         // mesh cell of the coming flight segment
         int layer = 0;                                            // ML: where_am_i of the particle's z
         double dt_seg = 0.0;
+        double nx_ = 0.0, ny_ = 0.0, nz_ = 0.0;                   // AHEAD: position of the lane's particle in the next batch
+        bool ahead = false;
         if (phase == PH_REFILL) {
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
             i = next + lane;
             act = i < wend;
+            if (AHEAD && i + 32 < wend) {
+                ahead = true;
+                nx_ = A.x[i + 32]; ny_ = A.y[i + 32]; nz_ = A.z[i + 32];
+            }
 #if EMC_STAGE_REFILL
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
@@ -417,7 +462,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     while (r >= P.group_size) { r -= P.group_size; ++g; }
                     p.grp = (int32_t)(g >= P.n_groups ? P.n_groups - 1 : g);
                 }
-                if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
+                if (MESHF && !(AHEAD && field_staged)) {
+                    cell = mesh_cell(P, p);
+                    field_prefetch<FIELD>(A, cell, WQ, lane, AHEAD);
+                }
                 if (ML && p.val >= 0) {                           // :366 / :372
                     layer = where_am_i(P, p.z);
                     if (layer < 0) { p.val = -(1 + EMC_FAULT_OUTSIDE); layer = 0; }
@@ -475,7 +523,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             __syncwarp();
             if (act) {
                 i = wstart + p.off;
-                if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
+                if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell, WQ, lane); }
                 if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
                 else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
                 int v = p.val, f;
@@ -537,9 +585,14 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 s0 = rng.state();                                 // faulted: cursor as far as it was read
             }
         }
+#if EMC_STAGE_FIELD
+        // every lane that staged a field record waits for it here, flying or not (a parked lane
+        // re-stages into the same slot in its scatter pass: no copy may still be in flight then)
+        if (FIELD == EMC_FIELD_MESH_PACKED) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
         if (fly) {                                                // :367 / :373 / :388
             double efx, efy, efz;
-            field_at<FIELD>(P, A, p, cell, efx, efy, efz);
+            field_at<FIELD>(P, A, p, cell, efx, efy, efz, WQ, lane, AHEAD && phase == PH_REFILL);
             const Mat &MT = P.mat[ML ? layer : 0];
             const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
             if ((FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) && P.zonly)
@@ -547,6 +600,15 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             else
                 carrier_drift<false>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             acc.c[4]++;
+        }
+        if (AHEAD && phase == PH_REFILL) {
+            // the rs slots of this batch have been read (own lane, program order): gather the next one
+            if (ahead) {
+                Particle q;
+                q.x = nx_; q.y = ny_; q.z = nz_;
+                field_prefetch<FIELD>(A, mesh_cell(P, q), WQ, lane, true);
+            }
+            field_staged = next < wend;           // `next` already points at that batch
         }
         if (act && !pend && !park) retire<REPLAY, DEPOSIT, ML>(P, A, i, p, s0, acc, smesh);
         const unsigned pm = __ballot_sync(FULL, pend);
