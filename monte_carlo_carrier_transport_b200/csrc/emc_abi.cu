@@ -181,6 +181,8 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
         const char *env = std::getenv("EMC_BLOCKS_PER_SM");
         if (env && std::atoi(env) > 0) per_sm = std::atoi(env);
         c->max_grid = c->sm_count * per_sm;
+        const char *fa = std::getenv("EMC_FIELD_AHEAD");
+        c->no_field_ahead = fa && std::atoi(fa) == 0;
         const char *ex = std::getenv("EMC_EXACT_LIBM");
         c->exact_libm = ex && std::atoi(ex) != 0;
     }

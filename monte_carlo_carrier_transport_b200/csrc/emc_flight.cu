@@ -157,13 +157,16 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 // the wait it hides: 1.177 ms staged vs 1.160 ms with plain loads behind the L2 prefetch.
 #define EMC_STAGE_REFILL 0
 #endif
-#ifndef EMC_STAGE_FIELD
-// 1: EMC_FIELD_MESH_PACKED gathers the 32-byte field record of a particle's cell with cp.async
-// into a per-lane shared-memory slot as soon as the particle is popped / loaded; the flight
-// segment, ~500 instructions later in an event pass, reads it from there.  The gather (L2, often
-// DRAM: the streaming particle state evicts the 34 MB field) no longer stalls the segment:
-// profiles/r1s: long-scoreboard stall 2.1 cycles per issue with the prefetch.L1 hint.
-#define EMC_STAGE_FIELD 1
+#ifndef EMC_FIELD_AHEAD
+// 1: EMC_FIELD_MESH_PACKED on meshes too large for L1: a refill pass loads the POSITIONS of the
+// following batch early and, after its own flight, gathers that batch's 32-byte field records with
+// cp.async into per-lane shared-memory slots, so that the next refill does not wait for two
+// dependent memory round trips (state, then field).  Measured, 1024 x 1 x 1024 mesh, 1.25e7
+// particles (profiles/r1s, r1t): flight+deposit 0.883 -> 0.843 ms.  Variants that lost: the same
+// with prefetch hints instead of staging (0.914 ms), staging the event passes' gathers too (no
+// gain: they are ~500 instructions ahead of their use anyway), and any of it on a mesh whose
+// field fits L1 (diode, 1024 cells: pure overhead) -- hence the run-time switch FlightArgs.field_ahead.
+#define EMC_FIELD_AHEAD 1
 #endif
 #ifndef EMC_PREFETCH_BATCHES
 // refill batches to prefetch ahead into L2 (0 = off).  Measured: 0 -> 1.475 ms, 1 -> 1.409 ms,
@@ -177,8 +180,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 constexpr int QCAP = 64;                    // a phase runs only if its pushes fit: <= 32 + 32
 struct WarpQueue {
     double kx[QCAP], ky[QCAP], kz[QCAP], x[QCAP], y[QCAP], z[QCAP], dte[QCAP];
-    int32_t val[QCAP];
-    uint32_t off[QCAP];                      // particle index relative to the warp's slice
+    uint32_t off[QCAP];                      // particle index relative to the warp's slice (< 2^29) | valley << 29
     uint32_t s0[QCAP];                       // random-stream state: Philox event counter / replay cursor
     int32_t grp[QCAP];                       // EMC_FIELD_GROUPS: field group of the particle
 };
@@ -191,10 +193,12 @@ struct WarpQueues {
     double stage[7][32];                     // next refill batch, landed here by cp.async (LDGSTS)
     int32_t stage_val[32];
 #endif
-#if EMC_STAGE_FIELD
-    double2 fs_a[32], fs_b[32];              // EMC_FIELD_MESH_PACKED: (ex, ey), (ez, 0) of each lane's cell
-    double2 rs_a[32], rs_b[32];              // the same for the NEXT refill batch, staged one refill ahead
-#endif
+};
+// EMC_FIELD_MESH_PACKED with field_ahead only (kept out of WarpQueues: shared memory the other modes
+// do not need would shrink their L1 -- the table-row gathers live on its hit rate: 2 KB per warp
+// more cost the configs[1] kernel 3.4 % in r1t)
+struct FieldStage {
+    double2 rs_a[32], rs_b[32];              // (ex, ey), (ez, 0) of each lane's cell in the NEXT refill batch
 };
 
 #if EMC_STAGE_REFILL
@@ -248,20 +252,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 }
 
 template <int FIELD>
-__device__ __forceinline__ void field_prefetch(const FlightArgs &A, int64_t c, WarpQueues &WQ, int lane,
-                                               bool refill_slot = false)
+__device__ __forceinline__ void field_prefetch(const FlightArgs &A, int64_t c)
 {
     if (FIELD == EMC_FIELD_MESH_PACKED) {
-#if EMC_STAGE_FIELD
-        // each lane stages ITS OWN record and reads it back itself: the per-thread cp.async group
-        // semantics are all the ordering needed
-        const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
-        cp_async16(refill_slot ? &WQ.rs_a[lane] : &WQ.fs_a[lane], rec);
-        cp_async16(refill_slot ? &WQ.rs_b[lane] : &WQ.fs_b[lane], rec + 1);
-        asm volatile("cp.async.commit_group;");
-#else
         asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ex + 4 * c));
-#endif
     } else if (FIELD == EMC_FIELD_MESH) {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ex + c));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ey + c));
@@ -269,10 +263,20 @@ __device__ __forceinline__ void field_prefetch(const FlightArgs &A, int64_t c, W
     }
 }
 
+// each lane stages ITS OWN record and reads it back itself: the per-thread cp.async group
+// semantics are all the ordering needed
+__device__ __forceinline__ void field_stage(const FlightArgs &A, int64_t c, FieldStage &FS, int lane)
+{
+    const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
+    cp_async16(&FS.rs_a[lane], rec);
+    cp_async16(&FS.rs_b[lane], rec + 1);
+    asm volatile("cp.async.commit_group;");
+}
+
 template <int FIELD>
 __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A, const Particle &p, int64_t c,
-                                         double &efx, double &efy, double &efz, WarpQueues &WQ, int lane,
-                                         bool refill_slot = false)
+                                         double &efx, double &efy, double &efz, FieldStage &FS, int lane,
+                                         bool staged = false)
 {
     if (FIELD == EMC_FIELD_CONSTANT) {
         efx = P.efield[0]; efy = P.efield[1]; efz = P.efield[2];
@@ -283,13 +287,13 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
     } else {
         // nearest-cell gather from the padded (nx+2,ny+2,nz+2) field of emc_field, V/m -> V/cm
         if (FIELD == EMC_FIELD_MESH_PACKED) {     // one 32-B record per cell, already V/cm
-#if EMC_STAGE_FIELD
-            // landed: the caller waited for the group
-            const double2 a = refill_slot ? WQ.rs_a[lane] : WQ.fs_a[lane], b = refill_slot ? WQ.rs_b[lane] : WQ.fs_b[lane];
-#else
-            const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
-            const double2 a = __ldg(rec), b = __ldg(rec + 1);
-#endif
+            double2 a, b;
+            if (staged) {                         // landed: the caller waited for the cp.async group
+                a = FS.rs_a[lane]; b = FS.rs_b[lane];
+            } else {
+                const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
+                a = __ldg(rec); b = __ldg(rec + 1);
+            }
             efx = a.x; efy = a.y; efz = b.x;
         } else {
             efx = __ldg(A.ex + c) * 1e-2;
@@ -329,7 +333,7 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
     Q.kx[slot] = p.kx; Q.ky[slot] = p.ky; Q.kz[slot] = p.kz;
     Q.x[slot] = p.x; Q.y[slot] = p.y; Q.z[slot] = p.z;
     Q.dte[slot] = p.dte;
-    Q.val[slot] = p.val; Q.off[slot] = p.off; Q.grp[slot] = p.grp;
+    Q.off[slot] = p.off | ((uint32_t)p.val << 29); Q.grp[slot] = p.grp;      // only live particles (valley 0..2) are queued
     Q.s0[slot] = s0;
 }
 
@@ -351,7 +355,11 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     __shared__ MechMeta Ms[ML ? EMC_MAX_LAYERS : 1];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     WarpQueues *queues = reinterpret_cast<WarpQueues *>(dyn_smem);
-    unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + sizeof(WarpQueues) * (FLIGHT_THREADS / 32));
+    constexpr bool AHEAD_OK = EMC_FIELD_AHEAD && FIELD == EMC_FIELD_MESH_PACKED;
+    const bool AHEAD = AHEAD_OK && A.field_ahead;                 // warp-uniform (kernel argument)
+    const size_t fs_bytes = AHEAD ? sizeof(FieldStage) : 0;
+    FieldStage *fstages = reinterpret_cast<FieldStage *>(dyn_smem + sizeof(WarpQueues) * (FLIGHT_THREADS / 32));
+    unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes) * (FLIGHT_THREADS / 32));
     {
         const int nw = sizeof(MechMeta) / 4;
         uint32_t *dst = reinterpret_cast<uint32_t *>(&Ms[0]);
@@ -373,6 +381,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     WarpQueues &WQ = queues[warp];
+    FieldStage &FS = fstages[AHEAD ? warp : 0];                   // only dereferenced when AHEAD
     const int64_t total_warps = (int64_t)gridDim.x * (FLIGHT_THREADS / 32);
     const int64_t gw = (int64_t)blockIdx.x * (FLIGHT_THREADS / 32) + warp;
     const int64_t slice = (((A.n + total_warps - 1) / total_warps) + 31) & ~(int64_t)31;
@@ -387,7 +396,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     // EMC_FIELD_MESH_PACKED: a refill pass gathers the field record of the FOLLOWING batch (whose
     // positions it loads early and turns into a cell after its own flight), so that a refill never
     // waits for two dependent memory round trips (state, then field)
-    constexpr bool AHEAD = EMC_STAGE_FIELD && FIELD == EMC_FIELD_MESH_PACKED;
+
     bool field_staged = false;                    // the batch at `next` has its field record in the rs slots
     const double dt = P.dt;
 
@@ -462,9 +471,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     while (r >= P.group_size) { r -= P.group_size; ++g; }
                     p.grp = (int32_t)(g >= P.n_groups ? P.n_groups - 1 : g);
                 }
-                if (MESHF && !(AHEAD && field_staged)) {
+                if (MESHF && !(AHEAD && field_staged)) {     // else: staged by the previous refill
                     cell = mesh_cell(P, p);
-                    field_prefetch<FIELD>(A, cell, WQ, lane, AHEAD);
+                    if (AHEAD) field_stage(A, cell, FS, lane);
+                    else field_prefetch<FIELD>(A, cell);
                 }
                 if (ML && p.val >= 0) {                           // :366 / :372
                     layer = where_am_i(P, p.z);
@@ -516,14 +526,15 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 p.kx = Qp.kx[slot]; p.ky = Qp.ky[slot]; p.kz = Qp.kz[slot];
                 p.x = Qp.x[slot]; p.y = Qp.y[slot]; p.z = Qp.z[slot];
                 p.dte = Qp.dte[slot];
-                p.val = Qp.val[slot]; p.off = Qp.off[slot]; p.grp = Qp.grp[slot];
+                { const uint32_t w = Qp.off[slot]; p.off = w & 0x1fffffffu; p.val = (int32_t)(w >> 29); }
+                p.grp = Qp.grp[slot];
                 s0 = Qp.s0[slot];
                 if (!sel) { mech = WQ.sc_mech[slot]; e_np = WQ.sc_enp[slot]; r_az = WQ.sc_raz[slot]; }
             }
             __syncwarp();
             if (act) {
                 i = wstart + p.off;
-                if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell, WQ, lane); }
+                if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
                 if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
                 else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
                 int v = p.val, f;
@@ -585,14 +596,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 s0 = rng.state();                                 // faulted: cursor as far as it was read
             }
         }
-#if EMC_STAGE_FIELD
-        // every lane that staged a field record waits for it here, flying or not (a parked lane
-        // re-stages into the same slot in its scatter pass: no copy may still be in flight then)
-        if (FIELD == EMC_FIELD_MESH_PACKED) asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
+        if (AHEAD_OK && AHEAD && phase == PH_REFILL) asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (fly) {                                                // :367 / :373 / :388
             double efx, efy, efz;
-            field_at<FIELD>(P, A, p, cell, efx, efy, efz, WQ, lane, AHEAD && phase == PH_REFILL);
+            field_at<FIELD>(P, A, p, cell, efx, efy, efz, FS, lane, AHEAD_OK && AHEAD && phase == PH_REFILL);
             const Mat &MT = P.mat[ML ? layer : 0];
             const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
             if ((FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) && P.zonly)
@@ -606,7 +613,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             if (ahead) {
                 Particle q;
                 q.x = nx_; q.y = ny_; q.z = nz_;
-                field_prefetch<FIELD>(A, mesh_cell(P, q), WQ, lane, true);
+                field_stage(A, mesh_cell(P, q), FS, lane);
             }
             field_staged = next < wend;           // `next` already points at that batch
         }
@@ -680,6 +687,10 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     int grid = (int)(blocks_needed < (int64_t)ctx->max_grid ? blocks_needed : ctx->max_grid);
     if (grid < 1) grid = 1;
     size_t smem = sizeof(WarpQueues) * (FLIGHT_THREADS / 32);
+    // refill-ahead field staging only where the field does not live in L1 anyway (EMC_FIELD_AHEAD)
+    const int64_t field_cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];
+    A.field_ahead = EMC_FIELD_AHEAD && field_mode == EMC_FIELD_MESH_PACKED && field_cells >= 8192 && !ctx->no_field_ahead;
+    if (A.field_ahead) smem += sizeof(FieldStage) * (FLIGHT_THREADS / 32);
     A.smem_cells = 0;
     if (A.mesh) {
         const int64_t cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];

@@ -36,6 +36,7 @@ struct FlightArgs {
     unsigned int *ticket;
     int64_t *mesh;
     int32_t smem_cells;
+    int32_t field_ahead;         // EMC_FIELD_MESH_PACKED: stage the next refill batch's field records (launch_flight decides)
     int32_t obs_before;          // emc_set_obs_phase: reduce the observables of the state as loaded
     const MechMeta *mech_layers; // multi-layer: device array of n_layers mechanism-metadata blocks
 };
@@ -49,6 +50,7 @@ struct Ctx {
     EmcLayer layers[EMC_MAX_LAYERS];
     bool layer_tables[EMC_MAX_LAYERS] = {false, false, false, false};
     int obs_before = 0;           // emc_set_obs_phase
+    bool no_field_ahead = false;  // EMC_FIELD_AHEAD=0 in the environment (tuning)
     bool zonly_constant = false;  // dc.efield has Ex = Ey = +0
     bool zonly_groups = false;    // every field group has Ex = Ey = +0
     int batch_layer = 0;          // emc_select_layer: material of the single-function batches
