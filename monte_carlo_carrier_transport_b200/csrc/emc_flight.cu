@@ -168,6 +168,11 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 // field fits L1 (diode, 1024 cells: pure overhead) -- hence the run-time switch FlightArgs.field_ahead.
 #define EMC_FIELD_AHEAD 1
 #endif
+#ifndef EMC_DEFER_POP
+// 1: leave x, y, z, dtau of a popped particle in its queue slot until the flight segment (eight
+// registers fewer across the event math).  Measured slower: 1.152 vs 1.134 ms.
+#define EMC_DEFER_POP 0
+#endif
 #ifndef EMC_PREFETCH_BATCHES
 // refill batches to prefetch ahead into L2 (0 = off).  Measured: 0 -> 1.475 ms, 1 -> 1.409 ms,
 // 2 -> 1.411 ms, 4 -> 1.423 ms per 2.4e7-particle timestep.
@@ -521,17 +526,25 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             int &qlen = sel ? qn : qsc;
             act = lane < cnt;
             qlen -= cnt;
+            // DEFER: x, y, z, dte (and the field group) are not touched by the event math: they stay in
+            // the queue slot until the flight segment needs them, which frees eight registers across
+            // the register-hungriest block of the kernel (mesh-field modes need the position for the
+            // cell at once).  The slots are only overwritten by this pass's own pushes, after a
+            // __syncwarp that follows the deferred reads.
+            constexpr bool DEFER = EMC_DEFER_POP && !MESHF;
+            const int slot = qlen + lane;
             if (act) {
-                const int slot = qlen + lane;
                 p.kx = Qp.kx[slot]; p.ky = Qp.ky[slot]; p.kz = Qp.kz[slot];
-                p.x = Qp.x[slot]; p.y = Qp.y[slot]; p.z = Qp.z[slot];
-                p.dte = Qp.dte[slot];
+                if (!DEFER) {
+                    p.x = Qp.x[slot]; p.y = Qp.y[slot]; p.z = Qp.z[slot];
+                    p.dte = Qp.dte[slot];
+                    p.grp = Qp.grp[slot];
+                }
                 { const uint32_t w = Qp.off[slot]; p.off = w & 0x1fffffffu; p.val = (int32_t)(w >> 29); }
-                p.grp = Qp.grp[slot];
                 s0 = Qp.s0[slot];
                 if (!sel) { mech = WQ.sc_mech[slot]; e_np = WQ.sc_enp[slot]; r_az = WQ.sc_raz[slot]; }
             }
-            __syncwarp();
+            if (!DEFER) __syncwarp();
             if (act) {
                 i = wstart + p.off;
                 if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
@@ -574,6 +587,15 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 if (rng.overflow()) { f = EMC_FAULT_STREAM; park = false; }
                 if (f >= 0) { p.val = -(1 + f); tail = false; }  // frozen; dtau keeps dte
                 else p.val = v;
+            }
+            if (DEFER) {
+                asm volatile("" ::: "memory");                   // keep the reads below the event math
+                if (act) {
+                    p.x = Qp.x[slot]; p.y = Qp.y[slot]; p.z = Qp.z[slot];
+                    p.dte = Qp.dte[slot];
+                    p.grp = Qp.grp[slot];
+                }
+                __syncwarp();
             }
             if (tail) {
                 // the event happened: draw the next free flight and fly (main_.py:379-389)
