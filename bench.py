@@ -110,6 +110,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pcie_duplex_gbs(torch, device, nbytes=1 << 29, reps=4):
+    """Raw PCIe ceiling of the e2e arm: pinned host <-> device copies in BOTH directions at once
+    (HostStepper moves 60 B per particle each way per timestep), GB/s per direction."""
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    both()
+    torch.cuda.synchronize(device)
+    t = time.perf_counter()
+    for _ in range(reps):
+        both()
+    torch.cuda.synchronize(device)
+    return nbytes * reps / (time.perf_counter() - t) / 1e9
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -429,6 +452,7 @@ def run_ours(args):
 
     h2d_bytes, d2h_bytes = hs.h2d_bytes, hs.d2h_bytes
     del hs
+    pcie = pcie_duplex_gbs(torch, ctx.device) if rank == 0 else None
     coupled = coupled_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
     by_config = other_configs_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
     if by_config is not None:
@@ -467,7 +491,10 @@ def run_ours(args):
             "e2e": {"value": seg_e2e / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes,
-                    "api": "engine.HostStepper.step: pinned host (N,6) coords + valley + dtau in, same out"},
+                    "api": "engine.HostStepper.step: pinned host (N,6) coords + valley + dtau in, same out",
+                    "pcie_duplex_gbs_per_direction": pcie,
+                    "achieved_gbs_per_direction": world * h2d_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9 / world,
+                    "bound": "PCIe: the timestep moves 60 B per particle each way; the kernel is 3 % of it"},
             "gpu_launches": int(launches), "clocks": clk, "coupled": coupled, "by_config": by_config,
         }
         print(json.dumps(line))
