@@ -191,6 +191,20 @@ int emc_init_ensemble(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x
                       double *z, double *dtau, int32_t *valley, int64_t n, uint64_t seed,
                       uint64_t pid_offset, void *stream);
 
+/* ---- photo-excited carriers: init_.init_photoex (init_.py:244-280) + main_.py:345-351 ---------- */
+/* Draws n_candidates carriers -- depth z ~ Exp(z_scale) (the reference: min(1/alpha, slab)),
+ * x, y ~ Normal(0, xy_std) (laser_std), mono-energetic `energy` [eV] with Normal(0, 2 pi) angles,
+ * valley 0, first free flight (-1/gamma_first) log u (the reference: 1E15) -- DROPS the ones
+ * beyond the slab (init_.py:247-248) and writes the survivors, in candidate order, to the
+ * pointers given (the free tail of the caller's state arrays, room for `capacity` >= n_candidates
+ * particles).  *n_accepted (HOST) receives how many were written; synchronises the stream.
+ * Philox keyed by (seed, candidate_offset + candidate): independent of launch shape. */
+int emc_init_photoex(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y,
+                     double *z, double *dtau, int32_t *valley, int64_t capacity,
+                     int64_t n_candidates, double energy, double z_scale, double xy_std,
+                     double gamma_first, uint64_t seed, uint64_t candidate_offset,
+                     int64_t *n_accepted, void *stream);
+
 /* ---- the particle loop of one timestep: main_.py:360-397 --------------------------------- */
 /* free_flight (main_.py:114) + carrier_drift/cyclic_boundary/specular_refl (:125-213) +
  * scatter_.scatter (scatter_.py:986-1099), fused, one call per timestep for the whole

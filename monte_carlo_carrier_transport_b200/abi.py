@@ -80,6 +80,8 @@ SIGNATURES = {
     "emc_set_efield": (C.c_int, [_vp, _dp]),
     "emc_set_field_groups": (C.c_int, [_vp, _dp, _i32, _i64]),
     "emc_init_ensemble": (C.c_int, [_vp] + [_dp] * 7 + [_ip, _i64, _u64, _u64, _vp]),
+    "emc_init_photoex": (C.c_int, [_vp] + [_dp] * 7 + [_ip, _i64, _i64, _f64, _f64, _f64, _f64, _u64, _u64,
+                                   C.POINTER(_i64), _vp]),
     "emc_flight_scatter": (C.c_int, [_vp] + [_dp] * 7 + [_ip, _i64, _i32, _dp, _dp, _dp,
                                                         _u64, _u64, _u32, _vp, _lp, _vp]),
     "emc_flight_scatter_replay": (C.c_int, [_vp] + [_dp] * 7 + [_ip, _i64, _i32, _dp, _dp, _dp,

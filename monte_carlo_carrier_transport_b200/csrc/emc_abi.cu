@@ -444,6 +444,25 @@ extern "C" int emc_init_ensemble(EmcCtx *ctx, double *kx, double *ky, double *kz
     return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "init_ensemble launch");
 }
 
+extern "C" int emc_init_photoex(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                                double *dtau, int32_t *valley, int64_t capacity, int64_t n_candidates,
+                                double energy, double z_scale, double xy_std, double gamma_first, uint64_t seed,
+                                uint64_t candidate_offset, int64_t *n_accepted, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!n_accepted) return fail(c, EMC_ERR_INVALID, "emc_init_photoex: n_accepted is null");
+    *n_accepted = 0;
+    int r = check_state(c, kx, ky, kz, x, y, z, dtau, valley, n_candidates);
+    if (r) return r;
+    if (n_candidates == 0) return EMC_OK;
+    if (capacity < n_candidates) return fail(c, EMC_ERR_INVALID, "emc_init_photoex: capacity < n_candidates");
+    if (!(energy > 0) || !(z_scale > 0) || !(xy_std >= 0) || !(gamma_first > 0))
+        return fail(c, EMC_ERR_INVALID, "emc_init_photoex: energy, z_scale, gamma_first must be positive");
+    cudaError_t e = launch_init_photoex(c, kx, ky, kz, x, y, z, dtau, valley, n_candidates, energy, z_scale, xy_std,
+                                        gamma_first, seed, candidate_offset, n_accepted, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "init_photoex");
+}
+
 static int flight_common(Ctx *c, FlightArgs &A, bool replay, int32_t field_mode, const double *ex, const double *ey,
                          const double *ez, void *stream)
 {

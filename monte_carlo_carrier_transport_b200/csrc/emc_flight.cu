@@ -857,6 +857,151 @@ cudaError_t launch_init_ensemble(Ctx *ctx, double *kx, double *ky, double *kz, d
 }
 
 // ------------------------------------------------------------------------------------------
+// photo-excited carriers: init_.init_photoex (init_.py:244-280) + main_.py:349-351 (valley 0,
+// first free flight from free_flight(1E15)).  Of n_cand candidates the ones drawn beyond the slab
+// are dropped (init_.py:247-248) and the survivors are appended in candidate order (deterministic
+// compaction: per-block counts, one-block scan, ordered write).  Draws of candidate c (Philox step
+// word 0xFFFFFFFE, particle word = cand_offset + c):
+//   0      z = -scale * log(1 - u)                      np.random.exponential(scale)   (init_.py:246)
+//   1,2    x, y = std * BoxMuller(u1, u2)               np.random.normal(0, laser_std) (:249,:251)
+//   3,4    alpha, beta = 2 pi * BoxMuller(u3, u4)       Normal(0, 2 pi)                (:264-265)
+//   5      dtau = (-1/G_first) * log(u5)                free_flight(1E15)              (main_.py:351)
+// ------------------------------------------------------------------------------------------
+struct PhotoexArgs {
+    double *kx, *ky, *kz, *x, *y, *z, *dtau;
+    int32_t *valley;
+    int64_t n_cand;
+    double energy, z_scale, xy_std, neg_inv_gamma_first;
+    uint64_t seed, cand_offset;
+    int64_t *block_counts;       // [gridDim.x + 1]: counts, then (after the scan) exclusive offsets; last = total
+};
+
+__device__ __forceinline__ double photoex_depth(const PhotoexArgs &Q, int64_t c)
+{
+    PhiloxStream rng;
+    rng.init(Q.seed, Q.cand_offset + (uint64_t)c, 0xFFFFFFFEu);
+    return -Q.z_scale * log(1 - rng.next());
+}
+
+constexpr int PHOTOEX_THREADS = 256;
+constexpr int PHOTOEX_PER_BLOCK = 4096;
+
+__global__ void __launch_bounds__(PHOTOEX_THREADS)
+photoex_count_kernel(const __grid_constant__ DevConst P, const __grid_constant__ PhotoexArgs Q)
+{
+    __shared__ int warp_cnt[PHOTOEX_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * PHOTOEX_PER_BLOCK;
+    int cnt = 0;
+    for (int t = threadIdx.x; t < PHOTOEX_PER_BLOCK; t += PHOTOEX_THREADS) {
+        const int64_t c = base + t;
+        if (c < Q.n_cand) cnt += photoex_depth(Q, c) < P.tot_dim[2];          // init_.py:247
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < PHOTOEX_THREADS / 32; ++w) s += warp_cnt[w];
+        Q.block_counts[blockIdx.x] = s;
+    }
+}
+
+__global__ void photoex_scan_kernel(int64_t *block_counts, int n_blocks)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int64_t run = 0;
+        for (int b = 0; b < n_blocks; ++b) {
+            const int64_t v = block_counts[b];
+            block_counts[b] = run;
+            run += v;
+        }
+        block_counts[n_blocks] = run;
+    }
+}
+
+__global__ void __launch_bounds__(PHOTOEX_THREADS)
+photoex_write_kernel(const __grid_constant__ DevConst P, const __grid_constant__ PhotoexArgs Q)
+{
+    __shared__ int warp_off[PHOTOEX_THREADS / 32];
+    __shared__ int chunk_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * PHOTOEX_PER_BLOCK;
+    if (threadIdx.x == 0) chunk_base = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < PHOTOEX_PER_BLOCK; t0 += PHOTOEX_THREADS) {
+        const int64_t c = base + t0 + threadIdx.x;
+        double pz = 0.0;
+        bool keep = false;
+        if (c < Q.n_cand) {
+            pz = photoex_depth(Q, c);
+            keep = pz < P.tot_dim[2];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_off[warp] = __popc(m);
+        __syncthreads();
+        int before = chunk_base;
+        for (int w = 0; w < warp; ++w) before += warp_off[w];
+        if (keep) {
+            const int64_t o = Q.block_counts[blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
+            PhiloxStream rng;
+            rng.init(Q.seed, Q.cand_offset + (uint64_t)c, 0xFFFFFFFEu);
+            rng.next();                                           // draw 0: the depth above
+            double n0, n1, na, nb;
+            { const double a = rng.next(), b = rng.next(); box_muller(a, b, n0, n1); }
+            { const double a = rng.next(), b = rng.next(); box_muller(a, b, na, nb); }
+            int layer = 0;
+            if (P.n_layers > 1) { layer = where_am_i(P, pz); if (layer < 0) layer = P.n_layers - 1; }   // init_.py:262
+            const double k = sqrt(2 * P.mat[layer].mass[0] * P.q * Q.energy / (P.hbar * P.hbar));     // :263
+            const double alpha = 2 * 3.14159265358979323846 * na, beta = 2 * 3.14159265358979323846 * nb;
+            double sa, ca, sb, cb;
+            sincos(alpha, &sa, &ca);
+            sincos(beta, &sb, &cb);
+            Q.kx[o] = k * ca * sb;                                // :266-268
+            Q.ky[o] = k * sa * sb;
+            Q.kz[o] = k * cb;
+            Q.x[o] = Q.xy_std * n0;
+            Q.y[o] = Q.xy_std * n1;
+            Q.z[o] = pz;
+            Q.dtau[o] = Q.neg_inv_gamma_first * log(rng.next());  // main_.py:351
+            Q.valley[o] = 0;                                      // main_.py:349
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int s = 0;
+            for (int w = 0; w < PHOTOEX_THREADS / 32; ++w) s += warp_off[w];
+            chunk_base += s;
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_init_photoex(Ctx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                                double *dtau, int32_t *valley, int64_t n_cand, double energy, double z_scale,
+                                double xy_std, double gamma_first, uint64_t seed, uint64_t cand_offset,
+                                int64_t *n_accepted_host, cudaStream_t st)
+{
+    const int n_blocks = (int)((n_cand + PHOTOEX_PER_BLOCK - 1) / PHOTOEX_PER_BLOCK);
+    cudaError_t e;
+    int64_t *counts = nullptr;
+    if ((e = cudaMallocAsync(&counts, sizeof(int64_t) * (size_t)(n_blocks + 1), st)) != cudaSuccess) return e;
+    PhotoexArgs Q;
+    Q.kx = kx; Q.ky = ky; Q.kz = kz; Q.x = x; Q.y = y; Q.z = z; Q.dtau = dtau; Q.valley = valley;
+    Q.n_cand = n_cand; Q.energy = energy; Q.z_scale = z_scale; Q.xy_std = xy_std;
+    Q.neg_inv_gamma_first = -1 / gamma_first;
+    Q.seed = seed; Q.cand_offset = cand_offset; Q.block_counts = counts;
+    ctx->launches += 3;
+    photoex_count_kernel<<<n_blocks, PHOTOEX_THREADS, 0, st>>>(ctx->dc, Q);
+    photoex_scan_kernel<<<1, 32, 0, st>>>(counts, n_blocks);
+    photoex_write_kernel<<<n_blocks, PHOTOEX_THREADS, 0, st>>>(ctx->dc, Q);
+    if ((e = cudaGetLastError()) == cudaSuccess)
+        e = cudaMemcpyAsync(n_accepted_host, counts + n_blocks, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(counts, st);
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------
 // single-function batches
 // ------------------------------------------------------------------------------------------
 __global__ void calc_energy_kernel(const __grid_constant__ DevConst P, int layer, const double *kx, const double *ky,

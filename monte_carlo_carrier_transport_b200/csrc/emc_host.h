@@ -84,6 +84,10 @@ cudaError_t launch_observables(Ctx *ctx, const double *kx, const double *ky, con
 cudaError_t launch_init_ensemble(Ctx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,
                                  double *dtau, int32_t *valley, int64_t n, uint64_t seed, uint64_t pid_offset,
                                  cudaStream_t st);
+cudaError_t launch_init_photoex(Ctx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                                double *dtau, int32_t *valley, int64_t n_cand, double energy, double z_scale,
+                                double xy_std, double gamma_first, uint64_t seed, uint64_t cand_offset,
+                                int64_t *n_accepted_host, cudaStream_t st);
 cudaError_t launch_calc_energy(Ctx *ctx, const double *kx, const double *ky, const double *kz,
                                const int32_t *valley, int64_t n, double *e_np, int32_t *idx, int32_t *fault,
                                cudaStream_t st);

@@ -272,17 +272,68 @@ class Ensemble:
 
     ROWS = ("kx", "ky", "kz", "x", "y", "z", "dtau")
 
-    def __init__(self, ctx: Context, n: int, pid_offset: int = 0):
+    def __init__(self, ctx: Context, n: int, pid_offset: int = 0, capacity: int | None = None):
+        """``capacity`` >= n reserves room for carriers injected later (``inject_photoex``); the
+        ``state`` / ``valley`` attributes are always views of the first ``n`` particles."""
         torch = _torch()
         self.ctx, self.n, self.pid_offset = ctx, int(n), int(pid_offset)
-        self.state = torch.zeros((7, self.n), dtype=torch.float64, device=ctx.device)
-        self.valley = torch.zeros(self.n, dtype=torch.int32, device=ctx.device)
+        self.capacity = max(int(capacity or 0), self.n)
+        self._store = torch.zeros((7, self.capacity), dtype=torch.float64, device=ctx.device)
+        self._vstore = torch.zeros(self.capacity, dtype=torch.int32, device=ctx.device)
+        self._n_candidates = 0                       # photo-excitation candidates drawn so far (Philox ids)
+        self._views()
         self.obs = torch.zeros(11, dtype=torch.int64, device=ctx.device)    # one EmcObs (88 B)
         self._obs_cache = None
 
-    def _ptrs(self):
-        base, stride = self.state.data_ptr(), self.n * 8
-        return [base + r * stride for r in range(7)] + [self.valley.data_ptr()]
+    def _views(self):
+        self.state = self._store[:, :self.n]
+        self.valley = self._vstore[:self.n]
+
+    def _ptrs(self, first: int = 0):
+        base, stride = self._store.data_ptr(), self.capacity * 8
+        return [base + r * stride + first * 8 for r in range(7)] + [self._vstore.data_ptr() + first * 4]
+
+    def reserve(self, capacity: int):
+        """Grow the buffers (device-to-device copy) so that ``capacity`` particles fit."""
+        torch = _torch()
+        if capacity <= self.capacity:
+            return self
+        store = torch.zeros((7, capacity), dtype=torch.float64, device=self.ctx.device)
+        vstore = torch.zeros(capacity, dtype=torch.int32, device=self.ctx.device)
+        store[:, :self.n].copy_(self._store[:, :self.n])
+        vstore[:self.n].copy_(self._vstore[:self.n])
+        self._store, self._vstore, self.capacity = store, vstore, int(capacity)
+        self._views()
+        return self
+
+    def inject_photoex(self, n_candidates: int, seed: int, energy: float | None = None,
+                       z_scale: float | None = None, xy_std: float | None = None,
+                       gamma_first: float = 1E15) -> int:
+        """Append photo-excited carriers (init_.init_photoex, init_.py:244-280; main_.py:345-358) on
+        the device: ``n_candidates`` are drawn, the ones beyond the slab are dropped, the survivors
+        get valley 0 and a first free flight from ``free_flight(1E15)``.  Defaults: the reference's
+        laser (``1240/laser_ex - EG`` eV, depth scale ``min(1/alpha, slab)``, ``laser_std``).
+        Returns the number of carriers added (the reference adds ``n_candidates`` to its count and
+        breaks when a candidate was dropped: main_.py:347-358)."""
+        from . import init_
+        c = self.ctx
+        n_candidates = int(n_candidates)
+        if n_candidates <= 0:
+            return 0
+        G, las = init_.Device.Materials[0], init_.laser
+        energy = (1240 / las.laser_ex - G.EG) if energy is None else energy
+        z_scale = min(1 / G.alpha, float(c.params.tot_dim[2])) if z_scale is None else z_scale
+        xy_std = las.laser_std if xy_std is None else xy_std
+        self.reserve(self.n + n_candidates)
+        got = C.c_int64(0)
+        c.check(c.lib.emc_init_photoex(c.h, *self._ptrs(self.n), self.capacity - self.n, n_candidates,
+                                       float(energy), float(z_scale), float(xy_std), float(gamma_first),
+                                       seed, self._n_candidates, C.byref(got), c.stream))
+        self._n_candidates += n_candidates
+        self.n += int(got.value)
+        self._views()
+        self._obs_cache = None
+        return int(got.value)
 
     def row(self, name: str):
         return self.state[self.ROWS.index(name)]

@@ -7,8 +7,8 @@ keeps working; the heavy lifting (10^6..10^9-particle ensembles) happens on the 
 
 Reference map: Layer init_.py:15-32, where_am_i :36-56, Parameters :58-70, GaAs :73-105,
 Device :108-157, init_energy_df :160-166, init_elec_field :168-173, init_mesh :175-187,
-init_rho :189-191, init_coords :194-234.  ``laser``/``init_photoex`` (:236-280) are out
-of scope for this round (inactive in every benchmark config).
+init_rho :189-191, init_coords :194-234, ``laser``/``init_photoex`` :236-280 (host mirrors;
+the device-side injection is ``engine.Ensemble.inject_photoex``).
 """
 from __future__ import annotations
 
@@ -174,10 +174,8 @@ def init_coords(layers=None, num_carr=None, mean_nrg=None):
 
 
 class laser:
-    """Excitation pulse parameters, init_.py:236-242 (host-side mirror; photo-excitation is
-    not on the accelerated path: it is inactive in every benchmark configuration and the
-    reference's injection bookkeeping, main_.py:345-358, cannot run once a carrier is drawn
-    beyond the slab -- see DESIGN.md "Out of scope")."""
+    """Excitation pulse parameters, init_.py:236-242.  The accelerated injection is
+    ``engine.Ensemble.inject_photoex`` / ``main_.run(photoex=True)``."""
 
     laser_ex = 800
     laser_pow = 0.1E-3

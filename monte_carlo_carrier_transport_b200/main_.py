@@ -196,8 +196,16 @@ def poisson(elec_field, coords, dfmesh=None, rho=None, u0=None, order=abi.SOR_LE
     return ef
 
 
+def photoex_count(num_carr, t):
+    """Carriers to add at time ``t`` (main_.py:345):
+    ``int(num_carr*(1 + laser_eff*norm.cdf(t, t0 + 3*laser_t, laser_t)) - num_carr)``."""
+    from scipy import stats
+    las = init_.laser
+    return int(num_carr * (1 + las.laser_eff * stats.norm.cdf(t, las.t0 + 3 * las.laser_t, las.laser_t)) - num_carr)
+
+
 def run(num_carr=None, pts=None, seed=12345, elec_field=None, coords=None, valley=None, dtau=None,
-        ctx: engine.Context | None = None, history: bool = False):
+        ctx: engine.Context | None = None, history: bool = False, photoex: bool = False, t_start: float = 0.0):
     """The time loop of main_.py:325-403 on the GPU.
 
     Returns ``(rows, ensemble)``: ``rows[c]`` is the reference's per-step record
@@ -211,6 +219,25 @@ def run(num_carr=None, pts=None, seed=12345, elec_field=None, coords=None, valle
     n = int(dev.num_carr if num_carr is None else num_carr)
     pts = int(param.pts if pts is None else pts)
     ens = engine.Ensemble(ctx, n)
+    if photoex:
+        # main_.py:339-358: before every timestep dcarr photo-excited carriers are drawn and the
+        # ones inside the slab appended (device-side, engine.Ensemble.inject_photoex).  The
+        # reference counts all dcarr candidates as carriers (dev.num_carr += dcarr) although
+        # init_photoex dropped some, and then indexes past its coords array; here the ensemble
+        # grows by the carriers that exist.
+        if coords is not None:
+            ens.load(coords, valley if valley is not None else np.zeros(n, dtype=np.int32), dtau)
+        else:
+            ens.init(seed)
+        rows = []
+        for c in range(pts):
+            t = t_start + c * param.dt              # t_start: begin the run near the pulse (t0 + 3 laser_t = 1.8 ps)
+            added = ens.inject_photoex(photoex_count(ens.n, t), seed + 1)
+            ens.step(c, seed)
+            o = engine.summarize(ens.last_obs())
+            o.update(step=c, t_ps=t * 1e12, injected=added)
+            rows.append(o)
+        return rows, ens
     if coords is not None:
         ens.load(coords, valley if valley is not None else np.zeros(n, dtype=np.int32), dtau)
     else:

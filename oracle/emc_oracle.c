@@ -464,6 +464,47 @@ void orc_init_ensemble(const OrcParams *p, int64_t n, double *kx, double *ky, do
     }
 }
 
+/* init_.init_photoex (init_.py:244-280) + main_.py:349-351.  Candidates drawn beyond the slab
+ * are dropped (init_.py:247-248), survivors appended in candidate order.  Draws of candidate c
+ * (Philox step word 0xFFFFFFFE, particle word cand_offset + c):
+ *   0 z = -scale*log(1-u);  1,2 x,y = std*BoxMuller;  3,4 alpha,beta = 2 pi*BoxMuller;
+ *   5 dtau = (-1/gamma_first)*log(u).   Returns the number of carriers written.          */
+int64_t orc_init_photoex(const OrcParams *p, int64_t n_cand, double energy, double z_scale,
+                         double xy_std, double gamma_first, uint64_t seed, uint64_t cand_offset,
+                         double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                         double *dtau, int32_t *valley)
+{
+    int64_t o = 0;
+    for (int64_t c = 0; c < n_cand; ++c) {
+        double u[6];
+        for (uint32_t d = 0; d < 6; ++d)
+            u[d] = orc_philox_uniform(seed, cand_offset + (uint64_t)c, 0xFFFFFFFEu, d);
+        double pz = -z_scale * log(1 - u[0]);                 /* init_.py:246 */
+        if (!(pz < p->tot_dim[2])) continue;                  /* :247-248 */
+        double n0, n1, na, nb;
+        box_muller(u[1], u[2], &n0, &n1);
+        box_muller(u[3], u[4], &na, &nb);
+        const OrcParams *pm = p;
+        if (p->n_layers > 1) {
+            int layer = orc_where_am_i(p, pz);                /* :262 */
+            if (layer < 0) layer = p->n_layers - 1;
+            pm = mat_of(p, layer);
+        }
+        double k = sqrt(2 * pm->mass[0] * p->q * energy / (p->hbar * p->hbar));   /* :263 */
+        double alpha = 2 * M_PI * na, beta = 2 * M_PI * nb;
+        kx[o] = k * cos(alpha) * sin(beta);                   /* :266-268 */
+        ky[o] = k * sin(alpha) * sin(beta);
+        kz[o] = k * cos(beta);
+        x[o] = xy_std * n0;
+        y[o] = xy_std * n1;
+        z[o] = pz;
+        dtau[o] = (-1 / gamma_first) * log(u[5]);             /* main_.py:351 */
+        valley[o] = 0;                                        /* main_.py:349 */
+        ++o;
+    }
+    return o;
+}
+
 void orc_observables(const OrcParams *p, int64_t n, const double *kx, const double *ky,
                      const double *kz, const double *z, const int32_t *valley, OrcObs *obs)
 {

@@ -118,6 +118,12 @@ void   orc_init_ensemble(const OrcParams *p, int64_t n, double *kx, double *ky, 
                          double *x, double *y, double *z, double *dtau, int32_t *valley,
                          uint64_t seed, uint64_t pid_offset);
 
+/* init_.init_photoex (init_.py:244-280) + main_.py:349-351; returns the number written */
+int64_t orc_init_photoex(const OrcParams *p, int64_t n_cand, double energy, double z_scale,
+                         double xy_std, double gamma_first, uint64_t seed, uint64_t cand_offset,
+                         double *kx, double *ky, double *kz, double *x, double *y, double *z,
+                         double *dtau, int32_t *valley);
+
 /* observables only (main_.py:394-403) */
 void   orc_observables(const OrcParams *p, int64_t n, const double *kx, const double *ky,
                        const double *kz, const double *z, const int32_t *valley, OrcObs *obs);

@@ -104,6 +104,9 @@ def lib():
             ip, C.POINTER(OrcStream), C.POINTER(OrcObs), C.c_int]
         L.orc_init_ensemble.argtypes = [C.POINTER(OrcParams), C.c_int64] + [dp] * 7 + [
             ip, C.c_uint64, C.c_uint64]
+        L.orc_init_photoex.restype = C.c_int64
+        L.orc_init_photoex.argtypes = [C.POINTER(OrcParams), C.c_int64, C.c_double, C.c_double, C.c_double,
+                                       C.c_double, C.c_uint64, C.c_uint64] + [dp] * 7 + [ip]
         L.orc_fx_to_rho.argtypes = [C.c_int64, lp, C.c_double, C.c_double, dp]
         L.orc_div_const_mismatches.restype = C.c_int64
         L.orc_div_const_mismatches.argtypes = [C.c_double, C.c_int64, C.c_uint64, C.c_int, C.c_int]
@@ -210,6 +213,14 @@ class Oracle:
                                                        ("kx", "ky", "kz", "x", "y", "z", "dtau")],
                                  _ip(st["valley"]), seed, pid_offset)
         return st
+
+    def init_photoex(self, n_cand, energy, z_scale, xy_std, gamma_first, seed, cand_offset=0):
+        st = {k: np.zeros(n_cand, dtype=np.float64) for k in ("kx", "ky", "kz", "x", "y", "z", "dtau")}
+        st["valley"] = np.zeros(n_cand, dtype=np.int32)
+        m = self.L.orc_init_photoex(C.byref(self.p), n_cand, energy, z_scale, xy_std, gamma_first, seed,
+                                    cand_offset, *[_dp(st[k]) for k in ("kx", "ky", "kz", "x", "y", "z", "dtau")],
+                                    _ip(st["valley"]))
+        return {k: v[:m].copy() for k, v in st.items()}
 
     # -- single-particle functions (the reference's own signatures) ----------------
     def calc_energy(self, k, val):

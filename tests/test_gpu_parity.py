@@ -718,3 +718,51 @@ def test_observables_before_step_phase(ctx, torch_mod):
             assert abs(rows[s][key] - ref[s][key]) <= 1e-12 * abs(ref[s][key]), (s, key)
     ca, cb = a.coords(), b.coords()
     assert all(np.array_equal(x, y) for x, y in zip(ca, cb))      # the trajectories do not depend on the phase
+
+
+def test_photoex_injection_vs_oracle(ctx, torch_mod, oracle):
+    """init_.init_photoex + main_.py:349-351 on the device (emc_init_photoex): the survivors of the
+    exponential depth draw, in candidate order, vs the oracle consuming the same Philox layout; and
+    the distributions the reference draws from."""
+    from monte_carlo_carrier_transport_b200 import engine, init_
+    g = helpers.golden_params()["phys"]
+    n0, seed = 5000, 99
+    ens = engine.Ensemble(ctx, n0, capacity=n0 + 10).init(seed)          # capacity grows on demand
+    before = ens.state.clone(), ens.valley.clone()
+    energy = 1240 / init_.laser.laser_ex - init_.GaAs.EG
+    scale = min(1 / init_.GaAs.alpha, g["tot_dim"][2])
+    got = 0
+    ref_parts = []
+    for n_cand in (1, 37, 4096, 4097, 100_003):                          # ragged sizes, several blocks
+        off = ens._n_candidates
+        got += ens.inject_photoex(n_cand, seed + 1)
+        ref_parts.append(oracle.init_photoex(n_cand, energy, scale, init_.laser.laser_std, 1E15, seed + 1, off))
+    ref = {k: np.concatenate([r[k] for r in ref_parts]) for k in ref_parts[0]}
+    m = len(ref["z"])
+    assert got == m and ens.n == n0 + m
+    assert torch_mod.equal(ens.state[:, :n0], before[0]) and torch_mod.equal(ens.valley[:n0], before[1])
+    new = ens.state[:, n0:].cpu().numpy()
+    assert np.max(helpers.rel_err(new[5], ref["z"])) < 1e-14                       # depth
+    assert np.max(np.abs(new[3] - ref["x"])) < 1e-12 * init_.laser.laser_std * 10  # Box-Muller normals
+    assert np.max(np.abs(new[4] - ref["y"])) < 1e-12 * init_.laser.laser_std * 10
+    kref = np.stack([ref["kx"], ref["ky"], ref["kz"]], axis=1)
+    assert k_err(new[:3].T, kref) < 1e-7                                            # sincos of N(0, 2 pi) angles
+    assert np.max(helpers.rel_err(new[6], ref["dtau"])) < 1e-13
+    assert (ens.valley[n0:] == 0).all()
+    # the reference's distributions: truncated exponential depth, Gaussian x / y, one energy, fast first flight
+    z = new[5]
+    assert z.max() < g["tot_dim"][2] and z.min() >= 0
+    total_cand = 1 + 37 + 4096 + 4097 + 100_003
+    assert abs(m / total_cand - (1 - np.exp(-g["tot_dim"][2] / scale))) < 0.01
+    assert abs(new[3].std() / init_.laser.laser_std - 1) < 0.02 and abs(new[3].mean()) < 0.02 * init_.laser.laser_std
+    E = (np.linalg.norm(new[:3], axis=0) * g["hbar"]) ** 2 / (2 * g["mass"][0] * g["q"])
+    assert np.max(np.abs(E / energy - 1)) < 1e-12
+    assert abs(new[6].mean() * 1E15 - 1) < 0.02
+    # and the time loop with injection runs, grows and keeps every carrier accounted for
+    from monte_carlo_carrier_transport_b200 import main_
+    rows, e2 = main_.run(num_carr=2000, pts=6, seed=5, ctx=ctx, photoex=True, t_start=1.7e-12)
+    assert all(r["injected"] > 0 for r in rows) and rows[-1]["injected"] > rows[0]["injected"]
+    assert e2.n == 2000 + sum(r["injected"] for r in rows) and rows[-1]["n"] + rows[-1]["n_fault"] == e2.n
+    rows0, e0 = main_.run(num_carr=2000, pts=6, seed=5, ctx=ctx, photoex=True)
+    assert e0.n == 2000 and all(r["injected"] == 0 for r in rows0)    # the shipped run never reaches the pulse
+    assert rows[-1]["e"] > rows0[-1]["e"] + 0.002    # the 0.126 eV photo-carriers heat the ensemble
