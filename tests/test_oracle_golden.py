@@ -255,3 +255,29 @@ def test_poisson_sor_and_field_bit_exact():
     assert np.max(helpers.rel_err(hist, p["err_hist"])) < 1e-12
     ex, ey, ez = orc.field(seg, dl, u)
     assert np.array_equal(ex, p["ef_x"]) and np.array_equal(ey, p["ef_y"]) and np.array_equal(ez, p["ef_z"])
+
+
+def test_photoex_oracle_distributions():
+    """orc_init_photoex (init_.py:244-280 + main_.py:349-351): truncated exponential depth in
+    candidate order, Gaussian x / y, one energy, valley 0, free_flight(1E15); counter-based, so a
+    split call reproduces the whole."""
+    o = helpers.make_oracle()
+    g = helpers.golden_params()["phys"]
+    L = g["tot_dim"][2]
+    energy, scale, std = 1240 / 800 - 1.424, min(1 / 1.1E6, L), 0.5E-6
+    n = 40000
+    st = o.init_photoex(n, energy, scale, std, 1E15, 31, 0)
+    m = len(st["z"])
+    assert abs(m / n - (1 - np.exp(-L / scale))) < 0.01
+    assert st["z"].min() >= 0 and st["z"].max() < L and (st["valley"] == 0).all()
+    # mean of an exponential truncated at L
+    want = scale - L * np.exp(-L / scale) / (1 - np.exp(-L / scale))
+    assert abs(st["z"].mean() / want - 1) < 0.02
+    for k in ("x", "y"):
+        assert abs(st[k].std() / std - 1) < 0.02 and abs(st[k].mean()) < 0.02 * std
+    E = (st["kx"] ** 2 + st["ky"] ** 2 + st["kz"] ** 2) * g["hbar"] ** 2 / (2 * g["mass"][0] * g["q"])
+    assert np.max(np.abs(E / energy - 1)) < 1e-12
+    assert abs(st["dtau"].mean() * 1E15 - 1) < 0.02
+    a, b = o.init_photoex(15000, energy, scale, std, 1E15, 31, 0), o.init_photoex(n - 15000, energy, scale, std, 1E15, 31, 15000)
+    for k in st:
+        assert np.array_equal(np.concatenate([a[k], b[k]]), st[k]), k
