@@ -747,13 +747,29 @@ observables_kernel(const __grid_constant__ DevConst P, const double *kx, const d
     for (int k = 0; k < 5; ++k) acc.d[k] = 0.0;
     for (int k = 0; k < 6; ++k) acc.c[k] = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int val = valley[i], layer = 0;
-        if (P.n_layers > 1 && val >= 0) {         // main_.py:393
-            layer = where_am_i(P, z[i]);
-            if (layer < 0) { val = -(1 + EMC_FAULT_OUTSIDE); layer = 0; }
+    // four particles per iteration: their 20 loads are in flight together (the kernel streams
+    // 36 B per particle and is bound by memory-level parallelism otherwise)
+    constexpr int U = 4;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+        double a[U], b[U], c[U], zz[U];
+        int v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            const bool ok = i < n;
+            a[u] = ok ? kx[i] : 0.0; b[u] = ok ? ky[i] : 0.0; c[u] = ok ? kz[i] : 0.0; zz[u] = ok ? z[i] : 0.0;
+            v[u] = ok ? valley[i] : 0;
         }
-        obs_particle(P, P.mat[layer], acc, kx[i], ky[i], kz[i], z[i], val);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * stride >= n) break;
+            int val = v[u], layer = 0;
+            if (P.n_layers > 1 && val >= 0) {     // main_.py:393
+                layer = where_am_i(P, zz[u]);
+                if (layer < 0) { val = -(1 + EMC_FAULT_OUTSIDE); layer = 0; }
+            }
+            obs_particle(P, P.mat[layer], acc, a[u], b[u], c[u], zz[u], val);
+        }
     }
     obs_block_reduce_and_finish(acc, partials, ticket, out);
 }
