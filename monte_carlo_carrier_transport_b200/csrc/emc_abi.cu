@@ -405,6 +405,7 @@ extern "C" int emc_set_field_groups(EmcCtx *ctx, const double *efields, int32_t 
 {
     CTX_OR_FAIL(ctx);
     if (!efields || n_groups < 1 || group_size < 1) return fail(c, EMC_ERR_INVALID, "emc_set_field_groups: bad argument");
+    if (group_size >= (int64_t)1 << 31) return fail(c, EMC_ERR_UNSUPPORTED, "emc_set_field_groups: group_size must be < 2^31");
     if (c->d_groups) { cudaFree(c->d_groups); c->d_groups = nullptr; }
     cudaError_t e = cudaMalloc(&c->d_groups, sizeof(double) * 3 * (size_t)n_groups);
     if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(groups)");

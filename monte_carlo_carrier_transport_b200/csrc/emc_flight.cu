@@ -14,38 +14,75 @@ namespace emc {
 struct ObsAcc {
     double d[5];        // sum_z, sum_vz, sum_e, sum_vz2, sum_e2
     unsigned int c[6];  // n_valley[3], n_fault, n_segments, n_events
+    __device__ __forceinline__ void zero(double *)
+    {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) d[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c[k] = 0u;
+    }
+    template <int K> __device__ __forceinline__ void add(double v) { d[K] += v; }
+    template <int K> __device__ __forceinline__ double sum() const { return d[K]; }
+    __device__ __forceinline__ void count_valley(int val) { c[0] += (val == 0); c[1] += (val == 1); c[2] += (val == 2); }
+    __device__ __forceinline__ void count_fault() { c[3]++; }
+    __device__ __forceinline__ void count_segment() { c[4]++; }
+    __device__ __forceinline__ void count_event() { c[5]++; }
+    __device__ __forceinline__ long long counter(int k) const { return (long long)c[k]; }
 };
 
-__device__ __forceinline__ void obs_zero(ObsAcc &a)
-{
+// The same accumulators with a smaller register footprint (EMC_OBS_SMEM, for block shapes that
+// must fit 96 registers): the five double sums live in a per-thread column of shared memory
+// ([k][thread]: conflict-free), the three valley counts and the fault count are packed into two
+// words (16 bits each: a lane sees fewer than 65 536 particles per launch, checked by the launcher).
+struct ObsAccShared {
+    double *s;          // this thread's column: s[k * FLIGHT_THREADS]
+    unsigned int v01, v2f, seg, ev;
+    __device__ __forceinline__ void zero(double *column)
+    {
+        s = column;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) a.d[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) a.c[k] = 0u;
-}
+        for (int k = 0; k < 5; ++k) s[k * FLIGHT_THREADS] = 0.0;
+        v01 = v2f = seg = ev = 0u;
+    }
+    template <int K> __device__ __forceinline__ void add(double v) { s[K * FLIGHT_THREADS] += v; }
+    template <int K> __device__ __forceinline__ double sum() const { return s[K * FLIGHT_THREADS]; }
+    __device__ __forceinline__ void count_valley(int val)
+    {
+        v01 += (val == 0) + ((val == 1) << 16);
+        v2f += (val == 2);
+    }
+    __device__ __forceinline__ void count_fault() { v2f += 1u << 16; }
+    __device__ __forceinline__ void count_segment() { seg++; }
+    __device__ __forceinline__ void count_event() { ev++; }
+    __device__ __forceinline__ long long counter(int k) const
+    {
+        const unsigned int w[6] = {v01 & 0xffffu, v01 >> 16, v2f & 0xffffu, v2f >> 16, seg, ev};
+        return (long long)w[k];
+    }
+};
 
-__device__ __forceinline__ void obs_particle(const DevConst &P, const Mat &MT, ObsAcc &a, double kx, double ky,
+template <class Acc>
+__device__ __forceinline__ void obs_particle(const DevConst &P, const Mat &MT, Acc &a, double kx, double ky,
                                              double kz, double z, int val)
 {
-    if (val < 0) { a.c[3]++; return; }
+    if (val < 0) { a.count_fault(); return; }
     // main_.py:105,109,394-397 (MT = mat[mat_i] of the final position, main_.py:393)
     const double E = energy_parabolic(P, MT, kx, ky, kz, val);
     const double enp = energy_nonparabolic(MT, E, val);
     const double vz = div_const(kz * P.hbar, MT.mass[val], MT.r_mass[val]);
-    a.d[0] += z;
-    a.d[1] += vz;
-    a.d[2] += enp;
-    a.d[3] += vz * vz;
-    a.d[4] += enp * enp;
-    a.c[0] += (val == 0);
-    a.c[1] += (val == 1);
-    a.c[2] += (val == 2);
+    a.template add<0>(z);
+    a.template add<1>(vz);
+    a.template add<2>(enp);
+    a.template add<3>(vz * vz);
+    a.template add<4>(enp * enp);
+    a.count_valley(val);
 }
 
 // Deterministic two-level reduction: warp shuffles, then shared memory, one partial per block;
 // the last block to finish (ticket) folds the partials in a fixed order, so the result does
 // not depend on block scheduling.
-__device__ void obs_block_reduce_and_finish(const ObsAcc &acc, ObsPartial *partials, unsigned int *ticket, EmcObs *out)
+template <class Acc>
+__device__ void obs_block_reduce_and_finish(const Acc &acc, ObsPartial *partials, unsigned int *ticket, EmcObs *out)
 {
     __shared__ ObsPartial warp_part[32];
     __shared__ bool is_last;
@@ -53,9 +90,10 @@ __device__ void obs_block_reduce_and_finish(const ObsAcc &acc, ObsPartial *parti
     double d[5];
     long long c[6];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) d[k] = acc.d[k];
+    d[0] = acc.template sum<0>(); d[1] = acc.template sum<1>(); d[2] = acc.template sum<2>();
+    d[3] = acc.template sum<3>(); d[4] = acc.template sum<4>();
 #pragma unroll
-    for (int k = 0; k < 6; ++k) c[k] = (long long)acc.c[k];
+    for (int k = 0; k < 6; ++k) c[k] = acc.counter(k);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
@@ -167,6 +205,16 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 // gain: they are ~500 instructions ahead of their use anyway), and any of it on a mesh whose
 // field fits L1 (diode, 1024 cells: pure overhead) -- hence the run-time switch FlightArgs.field_ahead.
 #define EMC_FIELD_AHEAD 1
+#endif
+#ifndef EMC_OBS_SMEM
+// 1: the flight kernel keeps its observable sums in shared memory (ObsAccShared): ten registers
+// fewer, for block shapes that have to fit 96 registers (EMC_FLIGHT_THREADS=640)
+#define EMC_OBS_SMEM 0
+#endif
+#if EMC_OBS_SMEM
+typedef ObsAccShared FlightObsAcc;
+#else
+typedef ObsAcc FlightObsAcc;
 #endif
 #ifndef EMC_DEFER_POP
 // 1: leave x, y, z, dtau of a popped particle in its queue slot until the flight segment (eight
@@ -311,7 +359,7 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
 // retire a particle: write its state back, add it to the observables and the charge mesh
 template <bool REPLAY, bool DEPOSIT, bool ML>
 __device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, int64_t i, const Particle &p,
-                                       uint32_t cursor, ObsAcc &acc, unsigned int *smesh)
+                                       uint32_t cursor, FlightObsAcc &acc, unsigned int *smesh)
 {
     A.kx[i] = p.kx; A.ky[i] = p.ky; A.kz[i] = p.kz;
     A.x[i] = p.x; A.y[i] = p.y; A.z[i] = p.z;
@@ -364,7 +412,9 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     const bool AHEAD = AHEAD_OK && A.field_ahead;                 // warp-uniform (kernel argument)
     const size_t fs_bytes = AHEAD ? sizeof(FieldStage) : 0;
     FieldStage *fstages = reinterpret_cast<FieldStage *>(dyn_smem + sizeof(WarpQueues) * (FLIGHT_THREADS / 32));
-    unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes) * (FLIGHT_THREADS / 32));
+    constexpr size_t OBS_BYTES = EMC_OBS_SMEM ? sizeof(double) * 5 * FLIGHT_THREADS : 0;
+    double *obs_columns = reinterpret_cast<double *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes) * (FLIGHT_THREADS / 32));
+    unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes) * (FLIGHT_THREADS / 32) + OBS_BYTES);
     {
         const int nw = sizeof(MechMeta) / 4;
         uint32_t *dst = reinterpret_cast<uint32_t *>(&Ms[0]);
@@ -379,8 +429,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     }
     __syncthreads();
 
-    ObsAcc acc;
-    obs_zero(acc);
+    FlightObsAcc acc;
+    acc.zero(obs_columns + threadIdx.x);
 
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -393,9 +443,12 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     int64_t wstart = gw * slice;
     if (wstart > A.n) wstart = A.n;
     const int64_t wend = (wstart + slice < A.n) ? wstart + slice : A.n;
-    int64_t next = wstart;
+    // loop state in 32 bits (a warp's slice is shorter than 2^29 particles: the queues pack the
+    // valley above the slice offset): `next` and the slice length relative to wstart
+    uint32_t next = 0;
+    const uint32_t wlen = (uint32_t)(wend - wstart);
 #if EMC_STAGE_REFILL
-    stage_batch(WQ, A, next + lane, wend, lane);
+    stage_batch(WQ, A, wstart + next + lane, wend, lane);
 #endif
     int qn = 0, qsc = 0;                          // lengths of the event / scatter queues (warp-uniform)
     // EMC_FIELD_MESH_PACKED: a refill pass gathers the field record of the FOLLOWING batch (whose
@@ -407,11 +460,15 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
 
     // EMC_FIELD_GROUPS: group index / remainder of the slice's next particle, advanced without
     // a 64-bit division per particle
-    int64_t grp_next = 0, grp_rem = 0;
+    // (group_size < 2^31 and n_groups < 2^31: checked by emc_set_field_groups)
+    int32_t grp_next = 0;
+    uint32_t grp_rem = 0;
+    const uint32_t gsz = (uint32_t)P.group_size;
     if (FIELD == EMC_FIELD_GROUPS) {
         const uint64_t g0 = A.pid_offset + (uint64_t)wstart;
-        grp_next = (int64_t)(g0 / (uint64_t)P.group_size);
-        grp_rem = (int64_t)(g0 % (uint64_t)P.group_size);
+        const uint64_t gq = g0 / (uint64_t)P.group_size;
+        grp_next = (int32_t)(gq < (uint64_t)P.n_groups ? gq : (uint64_t)P.n_groups);
+        grp_rem = (uint32_t)(g0 % (uint64_t)P.group_size);
     }
 
     // The phases share ONE copy of the event tail, the flight segment, the retirement and the
@@ -426,7 +483,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         int phase;
         if (n_sc == 32) phase = PH_SCATTER;
         else if (n_sel == 32) phase = PH_SELECT;
-        else if (qn < 32 && next < wend) phase = PH_REFILL;
+        else if (qn < 32 && next < wlen) phase = PH_REFILL;
         else if (n_sel > 0 && n_sel >= n_sc) phase = PH_SELECT;
         else if (n_sc > 0) phase = PH_SCATTER;
         else break;
@@ -447,9 +504,9 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         bool ahead = false;
         if (phase == PH_REFILL) {
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
-            i = next + lane;
-            act = i < wend;
-            if (AHEAD && i + 32 < wend) {
+            i = wstart + next + lane;
+            act = next + lane < wlen;
+            if (AHEAD && next + lane + 32 < wlen) {
                 ahead = true;
                 nx_ = A.x[i + 32]; ny_ = A.y[i + 32]; nz_ = A.z[i + 32];
             }
@@ -472,9 +529,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 p.grp = 0;
                 if (REPLAY) s0 = (uint32_t)A.cursor[i];
                 if (FIELD == EMC_FIELD_GROUPS) {
-                    int64_t g = grp_next, r = grp_rem + lane;
-                    while (r >= P.group_size) { r -= P.group_size; ++g; }
-                    p.grp = (int32_t)(g >= P.n_groups ? P.n_groups - 1 : g);
+                    int32_t g = grp_next;
+                    uint32_t r = grp_rem + lane;
+                    while (r >= gsz) { r -= gsz; ++g; }
+                    p.grp = g >= P.n_groups ? P.n_groups - 1 : g;
                 }
                 if (MESHF && !(AHEAD && field_staged)) {     // else: staged by the previous refill
                     cell = mesh_cell(P, p);
@@ -498,7 +556,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             }
             next += 32;
 #if EMC_STAGE_REFILL
-            stage_batch(WQ, A, next + lane, wend, lane);
+            stage_batch(WQ, A, wstart + next + lane, wend, lane);
 #endif
 #if EMC_PREFETCH_BATCHES > 0
             {   // pull the state rows of a later refill batch into L2 while this one is processed:
@@ -506,8 +564,9 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 // valley row, so ONE prefetch instruction covers it -- lane l < 14 takes line l&1 of
                 // row l>>1, lane 14 the valley line (the row pointers are consecutive kernel
                 // parameters, indexed from the constant bank)
-                const int64_t j0 = next + (int64_t)(EMC_PREFETCH_BATCHES - 1) * 32;
-                if (j0 < wend && lane < 15 && (!(lane & 1) || lane == 14 || j0 + 16 < wend)) {
+                const uint32_t o0 = next + (uint32_t)(EMC_PREFETCH_BATCHES - 1) * 32u;
+                const int64_t j0 = wstart + o0;
+                if (o0 < wlen && lane < 15 && (!(lane & 1) || lane == 14 || o0 + 16 < wlen)) {
                     const char *base = reinterpret_cast<const char *>((&A.kx)[lane >> 1]);
                     const int64_t off = lane < 14 ? j0 * 8 + (lane & 1) * 128 : j0 * 4;
                     prefetch_l2(base + off);
@@ -516,7 +575,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
 #endif
             if (FIELD == EMC_FIELD_GROUPS) {
                 grp_rem += 32;
-                while (grp_rem >= P.group_size) { grp_rem -= P.group_size; ++grp_next; }
+                while (grp_rem >= gsz) { grp_rem -= gsz; ++grp_next; }
             }
         } else {
             // ---- an event, main_.py:375-389 / scatter_.py:986-1099, in one or two passes ---------
@@ -599,7 +658,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             }
             if (tail) {
                 // the event happened: draw the next free flight and fly (main_.py:379-389)
-                acc.c[5]++;
+                acc.count_event();
                 const double dte2 = p.dte;                        // :376
                 const double dt3 = P.neg_inv_gamma * (SPEC ? lg : fast_log(rng.free_flight()));    // :379
                 if (rng.overflow()) {
@@ -628,7 +687,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 carrier_drift<true>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             else
                 carrier_drift<false>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
-            acc.c[4]++;
+            acc.count_segment();
         }
         if (AHEAD && phase == PH_REFILL) {
             // the rs slots of this batch have been read (own lane, program order): gather the next one
@@ -637,7 +696,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 q.x = nx_; q.y = ny_; q.z = nz_;
                 field_stage(A, mesh_cell(P, q), FS, lane);
             }
-            field_staged = next < wend;           // `next` already points at that batch
+            field_staged = next < wlen;           // `next` already points at that batch
         }
         if (act && !pend && !park) retire<REPLAY, DEPOSIT, ML>(P, A, i, p, s0, acc, smesh);
         const unsigned pm = __ballot_sync(FULL, pend);
@@ -713,6 +772,12 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     const int64_t field_cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];
     A.field_ahead = EMC_FIELD_AHEAD && field_mode == EMC_FIELD_MESH_PACKED && field_cells >= 8192 && !ctx->no_field_ahead;
     if (A.field_ahead) smem += sizeof(FieldStage) * (FLIGHT_THREADS / 32);
+    if (EMC_OBS_SMEM) {
+        smem += sizeof(double) * 5 * FLIGHT_THREADS;
+        // ObsAccShared packs the valley / fault counts into 16 bits per lane and launch
+        const int64_t warps = (int64_t)(grid < ctx->sm_count ? grid : ctx->sm_count) * (FLIGHT_THREADS / 32);   // one wave at least
+        if ((A.n + warps - 1) / warps / 32 + 1 > 65535) return cudaErrorInvalidValue;
+    }
     A.smem_cells = 0;
     if (A.mesh) {
         const int64_t cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];
@@ -744,8 +809,7 @@ observables_kernel(const __grid_constant__ DevConst P, const double *kx, const d
                    unsigned int *ticket, EmcObs *out)
 {
     ObsAcc acc;
-    for (int k = 0; k < 5; ++k) acc.d[k] = 0.0;
-    for (int k = 0; k < 6; ++k) acc.c[k] = 0;
+    acc.zero(nullptr);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // four particles per iteration: their 20 loads are in flight together (the kernel streams
     // 36 B per particle and is bound by memory-level parallelism otherwise)
