@@ -221,6 +221,17 @@ int emc_flight_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, double *
                        uint64_t seed, uint64_t pid_offset, uint32_t step,
                        EmcObs *obs, int64_t *mesh, void *stream);
 
+/* n_steps consecutive timesteps (first_step, first_step + 1, ...) enqueued by ONE call: the time
+ * loop of main_.py:339 without a host round trip per step (a small ensemble -- the reference's
+ * 10^4 electrons take 12 us of GPU time per timestep -- is otherwise bound by the caller's own
+ * per-call overhead).  obs_rows: device array of n_steps EmcObs (or NULL), row s written by
+ * timestep first_step + s according to emc_set_obs_phase. */
+int emc_flight_scatter_steps(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x,
+                             double *y, double *z, double *dtau, int32_t *valley, int64_t n,
+                             int32_t field_mode, const double *ex, const double *ey,
+                             const double *ez, uint64_t seed, uint64_t pid_offset,
+                             uint32_t first_step, int32_t n_steps, EmcObs *obs_rows, void *stream);
+
 /* Replay mode: the same loop, but every np.random.uniform() of the reference is read from a
  * per-particle sequential stream: uniforms is a device (n, stride) row-major array, cursor a
  * device int32[n] read position that the call advances. */

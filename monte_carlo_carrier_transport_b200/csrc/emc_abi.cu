@@ -501,6 +501,27 @@ extern "C" int emc_flight_scatter(EmcCtx *ctx, double *kx, double *ky, double *k
     return flight_common(c, A, false, field_mode, ex, ey, ez, stream);
 }
 
+extern "C" int emc_flight_scatter_steps(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y,
+                                        double *z, double *dtau, int32_t *valley, int64_t n, int32_t field_mode,
+                                        const double *ex, const double *ey, const double *ez, uint64_t seed,
+                                        uint64_t pid_offset, uint32_t first_step, int32_t n_steps, EmcObs *obs_rows,
+                                        void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (n_steps < 0) return fail(c, EMC_ERR_INVALID, "emc_flight_scatter_steps: n_steps < 0");
+    int r = check_state(c, kx, ky, kz, x, y, z, dtau, valley, n);
+    if (r) return r;
+    for (int32_t s = 0; s < n_steps; ++s) {
+        FlightArgs A;
+        std::memset(&A, 0, sizeof(A));
+        A.kx = kx; A.ky = ky; A.kz = kz; A.x = x; A.y = y; A.z = z; A.dtau = dtau; A.valley = valley; A.n = n;
+        A.seed = seed; A.pid_offset = pid_offset; A.step = first_step + (uint32_t)s;
+        A.obs = obs_rows ? obs_rows + s : nullptr;
+        if ((r = flight_common(c, A, false, field_mode, ex, ey, ez, stream)) != EMC_OK) return r;
+    }
+    return EMC_OK;
+}
+
 extern "C" int emc_flight_scatter_replay(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y,
                                          double *z, double *dtau, int32_t *valley, int64_t n, int32_t field_mode,
                                          const double *ex, const double *ey, const double *ez, uint64_t pid_offset,

@@ -400,11 +400,24 @@ class Ensemble:
         was = c.obs_before
         c.set_obs_phase(True)
         try:
-            for k in range(n_steps):
-                if step_fn is not None:
-                    step_fn(first_step + k, hist[k])
-                else:
-                    self.step(first_step + k, seed, obs_out=hist[k], **step_kw)
+            if step_fn is None and not step_kw.get("deposit", False) and step_kw.get("observe", True):
+                # the whole loop in one C call (no Python / ctypes overhead per timestep)
+                field_mode, mesh = step_kw.get("field_mode", abi.FIELD_CONSTANT), step_kw.get("mesh")
+                ex = ey = ez = None
+                if field_mode == abi.FIELD_MESH:
+                    ex, ey, ez = mesh.ex.data_ptr(), mesh.ey.data_ptr(), mesh.ez.data_ptr()
+                elif field_mode == abi.FIELD_MESH_PACKED:
+                    ex = mesh.e4.data_ptr()
+                self._obs_cache = None
+                c.check(c.lib.emc_flight_scatter_steps(
+                    c.h, *self._ptrs(), self.n, field_mode, ex, ey, ez, seed, self.pid_offset,
+                    first_step, n_steps, hist.data_ptr(), c.stream))
+            else:
+                for k in range(n_steps):
+                    if step_fn is not None:
+                        step_fn(first_step + k, hist[k])
+                    else:
+                        self.step(first_step + k, seed, obs_out=hist[k], **step_kw)
         finally:
             c.set_obs_phase(was)
         p = self._ptrs()
