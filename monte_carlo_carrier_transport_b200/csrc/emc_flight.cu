@@ -216,11 +216,8 @@ typedef ObsAccShared FlightObsAcc;
 #else
 typedef ObsAcc FlightObsAcc;
 #endif
-#ifndef EMC_DEFER_POP
-// 1: leave x, y, z, dtau of a popped particle in its queue slot until the flight segment (eight
-// registers fewer across the event math).  Measured slower: 1.152 vs 1.134 ms.
-#define EMC_DEFER_POP 0
-#endif
+// (Tried: leaving x, y, z, dtau of a popped particle in its queue slot until the flight segment --
+// eight registers fewer across the event math -- measured slower, 1.152 vs 1.134 ms.)
 #ifndef EMC_PREFETCH_BATCHES
 // refill batches to prefetch ahead into L2 (0 = off).  Measured: 0 -> 1.475 ms, 1 -> 1.409 ms,
 // 2 -> 1.411 ms, 4 -> 1.423 ms per 2.4e7-particle timestep.
@@ -231,16 +228,19 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 constexpr int QCAP = 64;                    // a phase runs only if its pushes fit: <= 32 + 32
+// A queue entry is four 16-byte pairs (one 128-bit shared-memory access each, consecutive slots:
+// conflict-free) instead of seven 8-byte and three 4-byte fields: a pop is 4 loads, a push 4 stores.
 struct WarpQueue {
-    double kx[QCAP], ky[QCAP], kz[QCAP], x[QCAP], y[QCAP], z[QCAP], dte[QCAP];
-    uint32_t off[QCAP];                      // particle index relative to the warp's slice (< 2^29) | valley << 29
-    uint32_t s0[QCAP];                       // random-stream state: Philox event counter / replay cursor
-    int32_t grp[QCAP];                       // EMC_FIELD_GROUPS: field group of the particle
+    double2 k01[QCAP];                       // kx, ky
+    double2 k2x[QCAP];                       // kz, x
+    double2 yz[QCAP];                        // y, z
+    double2 tw[QCAP];                        // dte, { slice offset (< 2^29) | valley << 29 , random-stream state }
+    int32_t grp[QCAP];                       // EMC_FIELD_GROUPS only: field group of the particle
 };
 struct WarpQueues {
     WarpQueue ev;                            // particles waiting for their next event
     WarpQueue sc;                            // mid-event particles that drew a real mechanism ...
-    double sc_enp[QCAP], sc_raz[QCAP];       // ... with E_np (scatter_.py:1069) and the azimuth uniform
+    double2 sc_er[QCAP];                     // ... with E_np (scatter_.py:1069) and the azimuth uniform
     int32_t sc_mech[QCAP];
 #if EMC_STAGE_REFILL
     double stage[7][32];                     // next refill batch, landed here by cp.async (LDGSTS)
@@ -381,13 +381,27 @@ __device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, i
     }
 }
 
+template <int FIELD>
 __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particle &p, uint32_t s0)
 {
-    Q.kx[slot] = p.kx; Q.ky[slot] = p.ky; Q.kz[slot] = p.kz;
-    Q.x[slot] = p.x; Q.y[slot] = p.y; Q.z[slot] = p.z;
-    Q.dte[slot] = p.dte;
-    Q.off[slot] = p.off | ((uint32_t)p.val << 29); Q.grp[slot] = p.grp;      // only live particles (valley 0..2) are queued
-    Q.s0[slot] = s0;
+    Q.k01[slot] = make_double2(p.kx, p.ky);
+    Q.k2x[slot] = make_double2(p.kz, p.x);
+    Q.yz[slot] = make_double2(p.y, p.z);
+    // only live particles (valley 0..2) are queued
+    Q.tw[slot] = make_double2(p.dte, __hiloint2double((int)s0, (int)(p.off | ((uint32_t)p.val << 29))));
+    if (FIELD == EMC_FIELD_GROUPS) Q.grp[slot] = p.grp;
+}
+
+template <int FIELD>
+__device__ __forceinline__ void queue_pop(const WarpQueue &Q, int slot, Particle &p, uint32_t &s0)
+{
+    const double2 a = Q.k01[slot], b = Q.k2x[slot], c = Q.yz[slot], d = Q.tw[slot];
+    p.kx = a.x; p.ky = a.y; p.kz = b.x; p.x = b.y; p.y = c.x; p.z = c.y; p.dte = d.x;
+    const uint32_t w = (uint32_t)__double2loint(d.y);
+    p.off = w & 0x1fffffffu;
+    p.val = (int32_t)(w >> 29);
+    s0 = (uint32_t)__double2hiint(d.y);
+    p.grp = (FIELD == EMC_FIELD_GROUPS) ? Q.grp[slot] : 0;
 }
 
 // ML = multi-layer device (emc_set_layers): the layer of a particle is looked up from its z with
@@ -585,25 +599,15 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             int &qlen = sel ? qn : qsc;
             act = lane < cnt;
             qlen -= cnt;
-            // DEFER: x, y, z, dte (and the field group) are not touched by the event math: they stay in
-            // the queue slot until the flight segment needs them, which frees eight registers across
-            // the register-hungriest block of the kernel (mesh-field modes need the position for the
-            // cell at once).  The slots are only overwritten by this pass's own pushes, after a
-            // __syncwarp that follows the deferred reads.
-            constexpr bool DEFER = EMC_DEFER_POP && !MESHF;
             const int slot = qlen + lane;
             if (act) {
-                p.kx = Qp.kx[slot]; p.ky = Qp.ky[slot]; p.kz = Qp.kz[slot];
-                if (!DEFER) {
-                    p.x = Qp.x[slot]; p.y = Qp.y[slot]; p.z = Qp.z[slot];
-                    p.dte = Qp.dte[slot];
-                    p.grp = Qp.grp[slot];
+                queue_pop<FIELD>(Qp, slot, p, s0);
+                if (!sel) {
+                    const double2 er = WQ.sc_er[slot];
+                    mech = WQ.sc_mech[slot]; e_np = er.x; r_az = er.y;
                 }
-                { const uint32_t w = Qp.off[slot]; p.off = w & 0x1fffffffu; p.val = (int32_t)(w >> 29); }
-                s0 = Qp.s0[slot];
-                if (!sel) { mech = WQ.sc_mech[slot]; e_np = WQ.sc_enp[slot]; r_az = WQ.sc_raz[slot]; }
             }
-            if (!DEFER) __syncwarp();
+            __syncwarp();
             if (act) {
                 i = wstart + p.off;
                 if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
@@ -646,15 +650,6 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 if (rng.overflow()) { f = EMC_FAULT_STREAM; park = false; }
                 if (f >= 0) { p.val = -(1 + f); tail = false; }  // frozen; dtau keeps dte
                 else p.val = v;
-            }
-            if (DEFER) {
-                asm volatile("" ::: "memory");                   // keep the reads below the event math
-                if (act) {
-                    p.x = Qp.x[slot]; p.y = Qp.y[slot]; p.z = Qp.z[slot];
-                    p.dte = Qp.dte[slot];
-                    p.grp = Qp.grp[slot];
-                }
-                __syncwarp();
             }
             if (tail) {
                 // the event happened: draw the next free flight and fly (main_.py:379-389)
@@ -700,14 +695,14 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         }
         if (act && !pend && !park) retire<REPLAY, DEPOSIT, ML>(P, A, i, p, s0, acc, smesh);
         const unsigned pm = __ballot_sync(FULL, pend);
-        if (pend) queue_push(WQ.ev, qn + __popc(pm & lt_mask), p, s0);
+        if (pend) queue_push<FIELD>(WQ.ev, qn + __popc(pm & lt_mask), p, s0);
         qn += __popc(pm);
         if (phase == PH_SELECT) {
             const unsigned km = __ballot_sync(FULL, park);
             if (park) {
                 const int slot = qsc + __popc(km & lt_mask);
-                queue_push(WQ.sc, slot, p, s0);
-                WQ.sc_mech[slot] = mech; WQ.sc_enp[slot] = e_np; WQ.sc_raz[slot] = r_az;
+                queue_push<FIELD>(WQ.sc, slot, p, s0);
+                WQ.sc_mech[slot] = mech; WQ.sc_er[slot] = make_double2(e_np, r_az);
             }
             qsc += __popc(km);
         }
