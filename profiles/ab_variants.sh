@@ -4,8 +4,9 @@
 #       python -m monte_carlo_carrier_transport_b200.build --force        # one .so per variant (variants/ is git-ignored)
 #   gpurun -- 'bash profiles/ab_variants.sh nospec default'
 # Knobs: EMC_FAST_MATH_PATHS, EMC_FAST_SAMPLERS, EMC_SPEC_SELECT, EMC_BRANCHFREE_INDEX,
-# EMC_STAGE_REFILL, EMC_PREFETCH_BATCHES, EMC_FLIGHT_THREADS / EMC_FLIGHT_MIN_BLOCKS / EMC_FLIGHT_MAXNREG
-# (compile time), EMC_ZONLY=0 and `bench.py --obs-phase after` (run time).  Logs: profiles/r1*_ab_*.txt.
+# EMC_LOG_CONSTANT_BANK, EMC_STAGE_REFILL, EMC_PREFETCH_BATCHES, EMC_FIELD_AHEAD, EMC_OBS_SMEM,
+# EMC_FLIGHT_THREADS / EMC_FLIGHT_MIN_BLOCKS / EMC_FLIGHT_MAXNREG (compile time); EMC_ZONLY=0,
+# EMC_FIELD_AHEAD=0 and `bench.py --obs-phase after` (run time).  Logs: profiles/r1*_ab_*.txt.
 for v in "$@"; do
   if [ "$v" = default ]; then unset EMC_LIB; else export EMC_LIB=$PWD/variants/libemc_$v.so; fi
   for rep in 1 2; do
