@@ -143,15 +143,27 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_traffic():
-    """dram bytes per launch of the flight kernel from the committed ncu summary, if any."""
+def load_traffic(key="dram_bytes_per_launch"):
+    """dram bytes (or warp-instructions) per launch of the flight kernel from the committed ncu summary, if any."""
     p = os.path.join(ROOT, "profiles", "flight_kernel_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            return json.load(open(p)).get(key)
         except Exception:      # noqa: BLE001
             return None
     return None
+
+
+def issue_roofline(kernel_ms, sm_mhz, n_sms=148):
+    """What actually binds the kernel: warp-instructions per launch (ncu) against
+    the issue slots of the launch, 4 schedulers x 1 instruction per clock per SM."""
+    inst = load_traffic("warp_instructions_per_launch")
+    if not inst or not sm_mhz:
+        return None
+    slots = kernel_ms * 1e-3 * sm_mhz * 1e6 * 4 * n_sms
+    return {"bound": "issue slots (fp64 dependency chains at 4 warps per scheduler)", "warp_instructions_per_launch": inst,
+            "issue_slots_per_launch": slots, "frac": inst / slots,
+            "note": "the HBM roofline above is the contract's; this one explains why it is not reached"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -488,7 +500,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "flight_scatter_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
                          "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n},
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n,
+                         "issue": issue_roofline(kernel_ms, (clk or {}).get("sm_mhz"))},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d particles (24 field groups x 500000), %d timesteps, %.1f s"
                                        % (cpu_n, cpu_steps, cpu_dt)},

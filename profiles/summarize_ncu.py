@@ -85,9 +85,11 @@ def full(rep, out, kernel_filter="flight_scatter"):
     def num(k):
         v, u = vals[k]
         v = float(v.replace(",", ""))
-        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)   # "inst": 1
     traffic = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
     json.dump({"dram_bytes_per_launch": traffic, "source": os.path.basename(out),
+               "warp_instructions_per_launch": num("smsp__inst_executed.sum"),
+               "particles_per_launch": 24000000,
                "kernel": r[ki][:120]},
               open(os.path.join(HERE, "flight_kernel_traffic.json"), "w"), indent=1)
 
