@@ -160,6 +160,10 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
             return EMC_ERR_INVALID;
         }
     if (!(params->gamma > 0) || !(params->dt > 0)) { g_create_error = "gamma and dt must be positive"; return EMC_ERR_INVALID; }
+    if ((double)(params->seg[0] + 2) * (double)(params->seg[1] + 2) * (double)(params->seg[2] + 2) >= 2147483648.0) {
+        g_create_error = "mesh too large: fewer than 2^31 padded cells are supported";
+        return EMC_ERR_UNSUPPORTED;
+    }
     EmcCtx *h = new (std::nothrow) EmcCtx();
     if (!h) { g_create_error = "out of host memory"; return EMC_ERR_INVALID; }
     Ctx *c = &h->c;

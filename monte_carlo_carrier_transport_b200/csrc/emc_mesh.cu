@@ -4,6 +4,7 @@
 // rho.reshape(dev.tot_seg) in the reference.  Compiled with -fmad=false.
 #include <cooperative_groups.h>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "emc_host.h"
 
@@ -288,9 +289,12 @@ __global__ void mesh_to_rho_kernel(const __grid_constant__ DevConst P, const lon
     const int64_t total = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= total) return;
-    const int k = (int)(c % (nz + 2));
-    const int j = (int)((c / (nz + 2)) % (ny + 2));
-    const int i = (int)(c / ((int64_t)(nz + 2) * (ny + 2)));
+    // (32-bit index arithmetic: a 64-bit division costs ~80 instructions, and there are three per
+    // cell; emc_create refuses meshes of 2^31 padded cells or more)
+    const uint32_t c32 = (uint32_t)c, q32 = c32 / (uint32_t)(nz + 2);
+    const int k = (int)(c32 - q32 * (uint32_t)(nz + 2));
+    const int i = (int)(q32 / (uint32_t)(ny + 2));
+    const int j = (int)(q32 - (uint32_t)i * (uint32_t)(ny + 2));
     if (i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz) { rho_pad[c] = 0.0; return; }
     const long long m = mesh[((int64_t)(i - 1) * ny + (j - 1)) * nz + (k - 1)];
     if (background_z) background = background_z[k - 1];      // doping profile (emc_set_background_profile)
@@ -322,9 +326,10 @@ __global__ void field_kernel(const __grid_constant__ DevConst P, const double *_
     const int64_t total = (int64_t)(nx + 2) * sx;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= total) return;
-    const int k = (int)(c % (nz + 2));
-    const int j = (int)((c / (nz + 2)) % (ny + 2));
-    const int i = (int)(c / sx);
+    const uint32_t c32 = (uint32_t)c, q32 = c32 / (uint32_t)(nz + 2);
+    const int k = (int)(c32 - q32 * (uint32_t)(nz + 2));
+    const int i = (int)(q32 / (uint32_t)(ny + 2));
+    const int j = (int)(q32 - (uint32_t)i * (uint32_t)(ny + 2));
     if (i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz) {
         ex[c] = 0.0; ey[c] = 0.0; ez[c] = 0.0;
         return;
@@ -342,9 +347,10 @@ __global__ void field_packed_kernel(const __grid_constant__ DevConst P, const do
     const int64_t total = (int64_t)(nx + 2) * sx;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= total) return;
-    const int k = (int)(c % (nz + 2));
-    const int j = (int)((c / (nz + 2)) % (ny + 2));
-    const int i = (int)(c / sx);
+    const uint32_t c32 = (uint32_t)c, q32 = c32 / (uint32_t)(nz + 2);
+    const int k = (int)(c32 - q32 * (uint32_t)(nz + 2));
+    const int i = (int)(q32 / (uint32_t)(ny + 2));
+    const int j = (int)(q32 - (uint32_t)i * (uint32_t)(ny + 2));
     double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
     if (!(i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz)) {
         v.x = (-0.5 * (u[c + sx] - u[c - sx]) / P.dl[0]) * 1e-2;
@@ -507,9 +513,11 @@ sor_rb_kernel(const __grid_constant__ SorConst S, double *u, const double *__res
         double acc = 0.0;
         for (int colour = 0; colour < 2; ++colour) {
             for (int64_t t = gtid; t < work; t += gstride) {
-                const int kk = (int)(t % hz);
-                const int j = 1 + (int)((t / hz) % ny);
-                const int i = 1 + (int)(t / ((int64_t)hz * ny));
+                const uint32_t t32 = (uint32_t)t, q32 = t32 / (uint32_t)hz;
+                const int kk = (int)(t32 - q32 * (uint32_t)hz);
+                const int i0 = (int)(q32 / (uint32_t)ny);
+                const int j = 1 + (int)(q32 - (uint32_t)i0 * (uint32_t)ny);
+                const int i = 1 + i0;
                 const int k = 1 + 2 * kk + (((i + j + 1) & 1) != colour ? 1 : 0);
                 if (k <= nz) {
                     const double d = sor_update(S, u, rho, i * sx + j * sy + k, sx, sy, relx, diverged);
@@ -595,7 +603,12 @@ int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega
             int per_sm = 0;
             if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_kernel, 256, 0)) != cudaSuccess)
                 goto cuda_fail;
-            if (per_sm > 4) per_sm = 4;
+            {   // persistent blocks per SM of the red-black solver; EMC_SOR_BLOCKS_PER_SM tunes it
+                const int occ = per_sm;
+                if (per_sm > 4) per_sm = 4;
+                const char *env = std::getenv("EMC_SOR_BLOCKS_PER_SM");
+                if (env && std::atoi(env) > 0) per_sm = std::atoi(env) < occ ? std::atoi(env) : occ;
+            }
             const int64_t work = (int64_t)nx * ny * ((nz + 1) / 2);
             int grid = ctx->sm_count * per_sm;
             const int64_t want = (work + 255) / 256;
