@@ -307,6 +307,12 @@ int emc_mesh_allreduce_p2p(EmcCtx *ctx, const int64_t *const *in_ptrs, int64_t *
 int emc_mesh_to_rho(EmcCtx *ctx, const int64_t *mesh, int32_t scheme, double *rho_pad,
                     void *stream);
 
+/* The same, writing the interior cells only: for a rho_pad whose halo is already zero (any buffer a
+ * previous emc_mesh_to_rho filled).  A time loop calls the full version once, then this one: a
+ * third of the cells on an ny = 1 mesh. */
+int emc_mesh_to_rho_interior(EmcCtx *ctx, const int64_t *mesh, int32_t scheme, double *rho_pad,
+                             void *stream);
+
 /* ---- Poisson: poisson_.py:47-84 (twin main_.py:283-315) ------------------------------------ */
 /* u_pad: device (nx+2,ny+2,nz+2), holds the initial guess INCLUDING boundary values
  * (poisson_.py:47-52) and receives the solution.  Iterates until RMS(update) <= tol or
@@ -327,6 +333,9 @@ int emc_field(EmcCtx *ctx, const double *u_pad, double *ex, double *ey, double *
  * gather of EMC_FIELD_MESH applies): two 128-bit loads per flight segment instead of three
  * scattered 64-bit ones.  e4: device, 4 * (nx+2)(ny+2)(nz+2) doubles, 32-byte aligned. */
 int emc_field_packed(EmcCtx *ctx, const double *u_pad, double *e4, void *stream);
+/* interior records only (the halo records of e4 are already zero: any buffer a previous
+ * emc_field_packed filled) */
+int emc_field_packed_interior(EmcCtx *ctx, const double *u_pad, double *e4, void *stream);
 
 #ifdef __cplusplus
 }

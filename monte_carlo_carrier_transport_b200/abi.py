@@ -99,10 +99,12 @@ SIGNATURES = {
     "emc_soa_to_aos": (C.c_int, [_vp] + [_dp] * 6 + [_i64, _dp, _vp]),
     "emc_deposit": (C.c_int, [_vp, _dp, _dp, _dp, _i64, _lp, _i32, _vp]),
     "emc_mesh_to_rho": (C.c_int, [_vp, _lp, _i32, _dp, _vp]),
+    "emc_mesh_to_rho_interior": (C.c_int, [_vp, _lp, _i32, _dp, _vp]),
     "emc_poisson_sor": (C.c_int, [_vp, _dp, _dp, _f64, _f64, _i32, _i32, C.POINTER(_i32),
                                   C.POINTER(_f64), _dp, _vp]),
     "emc_mesh_allreduce_p2p": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp]),
     "emc_field_packed": (C.c_int, [_vp, _dp, _dp, _vp]),
+    "emc_field_packed_interior": (C.c_int, [_vp, _dp, _dp, _vp]),
     "emc_poisson_last": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_f64), _vp]),
     "emc_field": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _vp]),
 }

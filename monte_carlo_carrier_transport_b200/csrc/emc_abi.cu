@@ -688,6 +688,23 @@ extern "C" int emc_mesh_to_rho(EmcCtx *ctx, const int64_t *mesh, int32_t scheme,
     return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "mesh_to_rho launch");
 }
 
+extern "C" int emc_mesh_to_rho_interior(EmcCtx *ctx, const int64_t *mesh, int32_t scheme, double *rho_pad, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!mesh || !rho_pad) return fail(c, EMC_ERR_INVALID, "emc_mesh_to_rho_interior: null");
+    if (scheme != EMC_DEPOSIT_NGP && scheme != EMC_DEPOSIT_CIC) return fail(c, EMC_ERR_INVALID, "unknown deposit scheme");
+    cudaError_t e = launch_mesh_to_rho(c, mesh, scheme, rho_pad, (cudaStream_t)stream, true);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "mesh_to_rho launch");
+}
+
+extern "C" int emc_field_packed_interior(EmcCtx *ctx, const double *u_pad, double *e4, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!u_pad || !e4 || ((uintptr_t)e4 & 31) != 0) return fail(c, EMC_ERR_INVALID, "emc_field_packed_interior: null or unaligned");
+    cudaError_t e = launch_field_packed(c, u_pad, e4, (cudaStream_t)stream, true);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "field_packed launch");
+}
+
 extern "C" int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad, double omega0, double tol,
                                int32_t max_sweeps, int32_t order, int32_t *sweeps_out, double *err_out,
                                double *err_hist, void *stream)

@@ -109,7 +109,8 @@ cudaError_t launch_deposit(Ctx *ctx, const double *x, const double *y, const dou
                            int scheme, cudaStream_t st);
 cudaError_t launch_selftest_accumulate(Ctx *ctx, int64_t n, uint64_t seed, int max_count, unsigned long long *bad_dev,
                                        cudaStream_t st);
-cudaError_t launch_mesh_to_rho(Ctx *ctx, const int64_t *mesh, int scheme, double *rho_pad, cudaStream_t st);
+cudaError_t launch_mesh_to_rho(Ctx *ctx, const int64_t *mesh, int scheme, double *rho_pad, cudaStream_t st,
+                               bool interior_only = false);
 cudaError_t launch_field(Ctx *ctx, const double *u_pad, double *ex, double *ey, double *ez, cudaStream_t st);
 // returns 0 / EMC_ERR_*; fills sweeps/err; synchronises
 int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega0, double tol, int max_sweeps,
@@ -117,7 +118,7 @@ int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega
 
 cudaError_t launch_mesh_allreduce_p2p(Ctx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs, int world,
                                       int rank, int64_t n_cells, cudaStream_t st);
-cudaError_t launch_field_packed(Ctx *ctx, const double *u_pad, double *e4, cudaStream_t st);
+cudaError_t launch_field_packed(Ctx *ctx, const double *u_pad, double *e4, cudaStream_t st, bool interior_only = false);
 int poisson_last(Ctx *ctx, int32_t *sweeps_out, double *err_out, cudaStream_t st);
 
 }  // namespace emc

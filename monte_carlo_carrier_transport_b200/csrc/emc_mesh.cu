@@ -283,19 +283,33 @@ cudaError_t launch_selftest_accumulate(Ctx *ctx, int64_t n, uint64_t seed, int m
 // rho_pad: zero halo (np.pad, poisson_.py:53); interior = background + charge
 __global__ void mesh_to_rho_kernel(const __grid_constant__ DevConst P, const long long *__restrict__ mesh, int scheme,
                                    double background, const double *__restrict__ background_z, double increment,
-                                   double *rho_pad)
+                                   double *rho_pad, int interior_only)
 {
     const int nx = P.seg[0], ny = P.seg[1], nz = P.seg[2];
-    const int64_t total = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total) return;
     // (32-bit index arithmetic: a 64-bit division costs ~80 instructions, and there are three per
     // cell; emc_create refuses meshes of 2^31 padded cells or more)
-    const uint32_t c32 = (uint32_t)c, q32 = c32 / (uint32_t)(nz + 2);
-    const int k = (int)(c32 - q32 * (uint32_t)(nz + 2));
-    const int i = (int)(q32 / (uint32_t)(ny + 2));
-    const int j = (int)(q32 - (uint32_t)i * (uint32_t)(ny + 2));
-    if (i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz) { rho_pad[c] = 0.0; return; }
+    int i, j, k;
+    int64_t c;
+    if (interior_only) {
+        // the halo is already zero (a buffer this context has written before): one thread per
+        // interior cell, a third of the padded cells on an ny = 1 mesh
+        const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= (int64_t)nx * ny * nz) return;
+        const uint32_t t32 = (uint32_t)t, q32 = t32 / (uint32_t)nz;
+        k = 1 + (int)(t32 - q32 * (uint32_t)nz);
+        i = 1 + (int)(q32 / (uint32_t)ny);
+        j = 1 + (int)(q32 - (uint32_t)(i - 1) * (uint32_t)ny);
+        c = ((int64_t)i * (ny + 2) + j) * (nz + 2) + k;
+    } else {
+        const int64_t total = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
+        c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (c >= total) return;
+        const uint32_t c32 = (uint32_t)c, q32 = c32 / (uint32_t)(nz + 2);
+        k = (int)(c32 - q32 * (uint32_t)(nz + 2));
+        i = (int)(q32 / (uint32_t)(ny + 2));
+        j = (int)(q32 - (uint32_t)i * (uint32_t)(ny + 2));
+        if (i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz) { rho_pad[c] = 0.0; return; }
+    }
     const long long m = mesh[((int64_t)(i - 1) * ny + (j - 1)) * nz + (k - 1)];
     if (background_z) background = background_z[k - 1];      // doping profile (emc_set_background_profile)
     double r = background;                                   // poisson_.py:27
@@ -307,13 +321,15 @@ __global__ void mesh_to_rho_kernel(const __grid_constant__ DevConst P, const lon
     rho_pad[c] = r;
 }
 
-cudaError_t launch_mesh_to_rho(Ctx *ctx, const int64_t *mesh, int scheme, double *rho_pad, cudaStream_t st)
+cudaError_t launch_mesh_to_rho(Ctx *ctx, const int64_t *mesh, int scheme, double *rho_pad, cudaStream_t st,
+                               bool interior_only)
 {
-    const int64_t total = (int64_t)(ctx->dc.seg[0] + 2) * (ctx->dc.seg[1] + 2) * (ctx->dc.seg[2] + 2);
+    const int64_t total = interior_only ? (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2]
+                                        : (int64_t)(ctx->dc.seg[0] + 2) * (ctx->dc.seg[1] + 2) * (ctx->dc.seg[2] + 2);
     ctx->launches++;
     mesh_to_rho_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
         ctx->dc, reinterpret_cast<const long long *>(mesh), scheme, ctx->params.rho_background,
-        ctx->d_background_z, ctx->params.rho_increment, rho_pad);
+        ctx->d_background_z, ctx->params.rho_increment, rho_pad, interior_only ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -340,17 +356,30 @@ __global__ void field_kernel(const __grid_constant__ DevConst P, const double *_
 }
 
 // the same differences, packed (ex, ey, ez, 0) per cell and pre-scaled V/m -> V/cm
-__global__ void field_packed_kernel(const __grid_constant__ DevConst P, const double *__restrict__ u, double4 *e4)
+__global__ void field_packed_kernel(const __grid_constant__ DevConst P, const double *__restrict__ u, double4 *e4,
+                                    int interior_only)
 {
     const int nx = P.seg[0], ny = P.seg[1], nz = P.seg[2];
     const int64_t sy = nz + 2, sx = (int64_t)(ny + 2) * (nz + 2);
-    const int64_t total = (int64_t)(nx + 2) * sx;
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total) return;
-    const uint32_t c32 = (uint32_t)c, q32 = c32 / (uint32_t)(nz + 2);
-    const int k = (int)(c32 - q32 * (uint32_t)(nz + 2));
-    const int i = (int)(q32 / (uint32_t)(ny + 2));
-    const int j = (int)(q32 - (uint32_t)i * (uint32_t)(ny + 2));
+    int i, j, k;
+    int64_t c;
+    if (interior_only) {                          // halo records already zero: interior cells only
+        const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= (int64_t)nx * ny * nz) return;
+        const uint32_t t32 = (uint32_t)t, q32 = t32 / (uint32_t)nz;
+        k = 1 + (int)(t32 - q32 * (uint32_t)nz);
+        i = 1 + (int)(q32 / (uint32_t)ny);
+        j = 1 + (int)(q32 - (uint32_t)(i - 1) * (uint32_t)ny);
+        c = (int64_t)i * sx + (int64_t)j * sy + k;
+    } else {
+        const int64_t total = (int64_t)(nx + 2) * sx;
+        c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (c >= total) return;
+        const uint32_t c32 = (uint32_t)c, q32 = c32 / (uint32_t)(nz + 2);
+        k = (int)(c32 - q32 * (uint32_t)(nz + 2));
+        i = (int)(q32 / (uint32_t)(ny + 2));
+        j = (int)(q32 - (uint32_t)i * (uint32_t)(ny + 2));
+    }
     double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
     if (!(i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz)) {
         v.x = (-0.5 * (u[c + sx] - u[c - sx]) / P.dl[0]) * 1e-2;
@@ -360,11 +389,13 @@ __global__ void field_packed_kernel(const __grid_constant__ DevConst P, const do
     e4[c] = v;
 }
 
-cudaError_t launch_field_packed(Ctx *ctx, const double *u_pad, double *e4, cudaStream_t st)
+cudaError_t launch_field_packed(Ctx *ctx, const double *u_pad, double *e4, cudaStream_t st, bool interior_only)
 {
-    const int64_t total = (int64_t)(ctx->dc.seg[0] + 2) * (ctx->dc.seg[1] + 2) * (ctx->dc.seg[2] + 2);
+    const int64_t total = interior_only ? (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2]
+                                        : (int64_t)(ctx->dc.seg[0] + 2) * (ctx->dc.seg[1] + 2) * (ctx->dc.seg[2] + 2);
     ctx->launches++;
-    field_packed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->dc, u_pad, reinterpret_cast<double4 *>(e4));
+    field_packed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->dc, u_pad, reinterpret_cast<double4 *>(e4),
+                                                                        interior_only ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -507,6 +507,7 @@ class Mesh:
         self.ey = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.ez = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.e4 = torch.zeros(pad + (4,), dtype=torch.float64, device=ctx.device)   # (ex, ey, ez, 0) in V/cm
+        self._rho_halo_done = self._e4_halo_done = False
         self.set_initial_guess(None)
 
     def set_initial_guess(self, u0):
@@ -563,8 +564,12 @@ class Mesh:
         parallel.allreduce_counts(self.counts, group)
 
     def to_rho(self):
+        """rho_pad from the (all-reduced) charge mesh.  The first call writes the zero halo too, later
+        ones only the interior cells (the halo of this Mesh's own buffer stays zero)."""
         c = self.ctx
-        c.check(c.lib.emc_mesh_to_rho(c.h, self.total.data_ptr(), self.scheme, self.rho_pad.data_ptr(), c.stream))
+        fn = c.lib.emc_mesh_to_rho_interior if self._rho_halo_done else c.lib.emc_mesh_to_rho
+        c.check(fn(c.h, self.total.data_ptr(), self.scheme, self.rho_pad.data_ptr(), c.stream))
+        self._rho_halo_done = True
 
     def solve(self, omega0: float = 1.5, tol: float = 1e-6, max_sweeps: int = 10000,
               order: int = abi.SOR_RED_BLACK, history: bool = False):
@@ -601,7 +606,9 @@ class Mesh:
     def field_packed(self):
         """The same field as one 32-byte record per cell (the flight kernel's FIELD_MESH_PACKED)."""
         c = self.ctx
-        c.check(c.lib.emc_field_packed(c.h, self.u_pad.data_ptr(), self.e4.data_ptr(), c.stream))
+        fn = c.lib.emc_field_packed_interior if self._e4_halo_done else c.lib.emc_field_packed
+        c.check(fn(c.h, self.u_pad.data_ptr(), self.e4.data_ptr(), c.stream))
+        self._e4_halo_done = True
 
 
 class CoupledStepper:

@@ -766,3 +766,27 @@ def test_photoex_injection_vs_oracle(ctx, torch_mod, oracle):
     rows0, e0 = main_.run(num_carr=2000, pts=6, seed=5, ctx=ctx, photoex=True)
     assert e0.n == 2000 and all(r["injected"] == 0 for r in rows0)    # the shipped run never reaches the pulse
     assert rows[-1]["e"] > rows0[-1]["e"] + 0.002    # the 0.126 eV photo-carriers heat the ensemble
+
+
+def test_interior_only_mesh_updates(torch_mod):
+    """emc_mesh_to_rho_interior / emc_field_packed_interior == the full versions on a buffer whose
+    halo is zero (what engine.Mesh does from its second timestep on); the full versions clean a
+    dirty halo."""
+    torch = torch_mod
+    from monte_carlo_carrier_transport_b200 import engine
+    c = mesh_context((40, 2, 30), torch)
+    rng = np.random.RandomState(4)
+    m = engine.Mesh(c)
+    m.rho_pad.fill_(7.0)
+    m.e4.fill_(-3.0)                                   # dirty halos
+    for rep in range(3):
+        m.counts.copy_(torch.from_numpy(rng.randint(0, 30, 40 * 2 * 30).astype(np.int64)).cuda())
+        m.set_initial_guess(rng.random_sample((40, 2, 30)))
+        m.to_rho()                                     # rep 0: full, then interior only
+        m.field_packed()
+        ref_rho, ref_e4 = torch.empty_like(m.rho_pad).fill_(9.0), torch.empty_like(m.e4).fill_(9.0)
+        c.check(c.lib.emc_mesh_to_rho(c.h, m.total.data_ptr(), m.scheme, ref_rho.data_ptr(), c.stream))
+        c.check(c.lib.emc_field_packed(c.h, m.u_pad.data_ptr(), ref_e4.data_ptr(), c.stream))
+        assert torch.equal(m.rho_pad, ref_rho) and torch.equal(m.e4, ref_e4), rep
+    assert float(m.rho_pad[0].abs().max()) == 0.0 and float(m.e4[:, 0].abs().max()) == 0.0
+    c.close()
