@@ -290,7 +290,8 @@ struct Particle {
 __device__ __forceinline__ int64_t mesh_cell(const DevConst &P, const Particle &p)
 {
     const int ci = axis_cell(p.x, P.seg[0], P.dl[0], P.inv_dl[0]) + 1;
-    const int cj = axis_cell(p.y, P.seg[1], P.dl[1], P.inv_dl[1]) + 1;
+    // a single-cell axis (the reference's ny = 1 meshes): the clamp sends every y to cell 0
+    const int cj = P.seg[1] == 1 ? 1 : axis_cell(p.y, P.seg[1], P.dl[1], P.inv_dl[1]) + 1;
     const int ck = axis_cell(p.z, P.seg[2], P.dl[2], P.inv_dl[2]) + 1;
     return ((int64_t)ci * (P.seg[1] + 2) + cj) * (P.seg[2] + 2) + ck;
 }
