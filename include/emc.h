@@ -172,6 +172,16 @@ int emc_upload_tables_layer(EmcCtx *ctx, int32_t layer, const double *ek, int32_
  * of at particle retirement (17 of 32 on average): a time loop gets the same rows one launch later
  * and reads the last one with emc_observables. */
 int emc_set_obs_phase(EmcCtx *ctx, int32_t before_step);
+/* Composition of the inverse-trigonometric round trips of scatter_.py:1061-1062 and the polar
+ * samplers (:811-872).  0 (default; EMC_EXACT_LIBM=1 in the environment makes 1 the default): the
+ * algebraic equivalents cos(acos c) = c, sin(acos c) = sqrt((1-c)(1+c)), cos(2 atan t) = (1-t^2)/(1+t^2);
+ * 1: acos / asin / atan / sin / cos composed exactly like the reference (about twice the fp64 work;
+ * 6x fewer particles beyond 1e-9 in the ill-conditioned corner). */
+int emc_set_exact_libm(EmcCtx *ctx, int32_t on);
+/* Writes a one-line description of the run-time knobs that select kernels on this context
+ * ("exact_libm=0 zonly=1 field_ahead=1 waves=1 ...", NUL-terminated, at most cap bytes) into buf
+ * (HOST): what bench.py records next to its numbers.  Returns the length written. */
+int emc_describe(const EmcCtx *ctx, char *buf, int32_t cap);
 /* Material (layer) used by the single-function batches emc_calc_energy / emc_scatter: the `mat` /
  * `mat_i` argument of scatter_.calc_energy (scatter_.py:19) and scatter_.scatter (:986).  Default 0. */
 int emc_select_layer(EmcCtx *ctx, int32_t layer);
@@ -323,8 +333,9 @@ int emc_mesh_to_rho_interior(EmcCtx *ctx, const int64_t *mesh, int32_t scheme, d
 int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad, double omega0, double tol,
                     int32_t max_sweeps, int32_t order, int32_t *sweeps_out, double *err_out,
                     double *err_hist, void *stream);
-/* sweep count / last RMS update / divergence (EMC_ERR_DIVERGED) of the most recent
- * emc_poisson_sor on this context; synchronises the stream */
+/* sweep count / last RMS update of the most recent emc_poisson_sor on this context, and divergence
+ * (EMC_ERR_DIVERGED) of ANY solve since the previous emc_poisson_last (sticky device flag: solves that
+ * were only enqueued are not lost); synchronises the stream */
 int emc_poisson_last(EmcCtx *ctx, int32_t *sweeps_out, double *err_out, void *stream);
 /* E = -central difference on interior cells (poisson_.py:88-96); padded outputs, V/m */
 int emc_field(EmcCtx *ctx, const double *u_pad, double *ex, double *ey, double *ez, void *stream);

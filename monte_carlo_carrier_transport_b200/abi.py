@@ -75,6 +75,8 @@ SIGNATURES = {
     "emc_set_layers": (C.c_int, [_vp, C.POINTER(EmcLayer), _i32]),
     "emc_upload_tables_layer": (C.c_int, [_vp, _i32, _dp, _i32, _dp, _dp, _dp, _ip, _dp, _ip, _ip]),
     "emc_select_layer": (C.c_int, [_vp, _i32]),
+    "emc_set_exact_libm": (C.c_int, [_vp, _i32]),
+    "emc_describe": (C.c_int, [_vp, C.c_char_p, _i32]),
     "emc_set_obs_phase": (C.c_int, [_vp, _i32]),
     "emc_set_background_profile": (C.c_int, [_vp, _dp, _i32]),
     "emc_set_efield": (C.c_int, [_vp, _dp]),

@@ -2,6 +2,7 @@
 // Argument validation, context lifetime, table upload; every compute entry point is a thin
 // wrapper over a kernel launcher in emc_flight.cu / emc_mesh.cu.  No exception crosses the ABI.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -196,6 +197,7 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
     if ((e = cudaMalloc(&c->d_obs, sizeof(EmcObs))) != cudaSuccess) goto fail_cuda_create;
     if ((e = cudaMalloc(&c->d_sor_scalars, sizeof(double) * 8)) != cudaSuccess) goto fail_cuda_create;
     if ((e = cudaMalloc(&c->d_sor_flags, sizeof(int32_t) * 4)) != cudaSuccess) goto fail_cuda_create;
+    if ((e = cudaMemset(c->d_sor_flags, 0, sizeof(int32_t) * 4)) != cudaSuccess) goto fail_cuda_create;
     if ((e = cudaMalloc(&c->d_sor_partials, sizeof(double) * 4096)) != cudaSuccess) goto fail_cuda_create;
     *out = h;
     return EMC_OK;
@@ -374,6 +376,27 @@ extern "C" int emc_set_obs_phase(EmcCtx *ctx, int32_t before_step)
     return EMC_OK;
 }
 
+extern "C" int emc_set_exact_libm(EmcCtx *ctx, int32_t on)
+{
+    CTX_OR_FAIL(ctx);
+    c->exact_libm = on != 0;
+    return EMC_OK;
+}
+
+extern "C" int emc_describe(const EmcCtx *ctx, char *buf, int32_t cap)
+{
+    if (!ctx || !buf || cap < 1) return EMC_ERR_INVALID;
+    const Ctx *c = &ctx->c;
+    const char *sor = std::getenv("EMC_SOR_BLOCKS_PER_SM");
+    const int n = std::snprintf(buf, (size_t)cap,
+                                "exact_libm=%d zonly_constant=%d zonly_groups=%d field_ahead=%d waves=%d max_grid=%d "
+                                "obs_before=%d n_layers=%d literal_scan=%d sor_blocks_per_sm=%s flight_threads=%d",
+                                (int)c->exact_libm, (int)c->zonly_constant, (int)c->zonly_groups,
+                                (int)!c->no_field_ahead, c->waves, c->max_grid, c->obs_before, c->dc.n_layers,
+                                c->dc.literal_scan, sor ? sor : "auto", FLIGHT_THREADS);
+    return n < cap ? n : cap - 1;
+}
+
 extern "C" int emc_select_layer(EmcCtx *ctx, int32_t layer)
 {
     CTX_OR_FAIL(ctx);
@@ -478,8 +501,8 @@ static int flight_common(Ctx *c, FlightArgs &A, bool replay, int32_t field_mode,
     if (field_mode == EMC_FIELD_MESH_PACKED && (!ex || ((uintptr_t)ex & 31) != 0))
         return fail(c, EMC_ERR_INVALID, "EMC_FIELD_MESH_PACKED needs a 32-byte aligned packed field in ex");
     if (field_mode < 0 || field_mode > EMC_FIELD_MESH_PACKED) return fail(c, EMC_ERR_INVALID, "unknown field_mode");
-    if (c->dc.n_layers > 1 && (c->exact_libm || A.mesh))
-        return fail(c, EMC_ERR_UNSUPPORTED, "multi-layer devices: no EMC_EXACT_LIBM, no fused deposit (use emc_deposit)");
+    if (c->dc.n_layers > 1 && A.mesh)
+        return fail(c, EMC_ERR_UNSUPPORTED, "multi-layer devices: no fused deposit (use emc_deposit)");
     A.ex = ex; A.ey = ey; A.ez = ez;
     A.obs_before = c->obs_before;
     c->dc.zonly = (field_mode == EMC_FIELD_CONSTANT && c->zonly_constant) ||

@@ -748,8 +748,10 @@ static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid
 template <class Stream, int FIELD>
 static cudaError_t launch_flight_t(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
-    // multi-layer devices: default libm composition, separate deposit kernel (checked by the caller)
-    if (ctx->dc.n_layers > 1) return launch_flight_k<Stream, FIELD, false, false, true>(ctx, A, grid, smem, st);
+    // multi-layer devices: separate deposit kernel (checked by the caller)
+    if (ctx->dc.n_layers > 1)
+        return ctx->exact_libm ? launch_flight_k<Stream, FIELD, true, false, true>(ctx, A, grid, smem, st)
+                               : launch_flight_k<Stream, FIELD, false, false, true>(ctx, A, grid, smem, st);
     if (ctx->exact_libm)
         return A.mesh ? launch_flight_k<Stream, FIELD, true, true, false>(ctx, A, grid, smem, st)
                       : launch_flight_k<Stream, FIELD, true, false, false>(ctx, A, grid, smem, st);

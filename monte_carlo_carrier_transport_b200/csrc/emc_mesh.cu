@@ -116,6 +116,14 @@ deposit_cic_kernel(const __grid_constant__ DevConst P, const double *__restrict_
     }
 }
 
+// NGP on a mesh that does not fit one block's shared memory
+static cudaError_t launch_deposit_large(Ctx *ctx, const double *x, const double *y, const double *z, int64_t n,
+                                        unsigned long long *m, int64_t cells, int grid, cudaStream_t st)
+{
+    deposit_ngp_kernel<false><<<grid, 256, 0, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_deposit(Ctx *ctx, const double *x, const double *y, const double *z, int64_t n, int64_t *mesh,
                            int scheme, cudaStream_t st)
 {
@@ -125,16 +133,32 @@ cudaError_t launch_deposit(Ctx *ctx, const double *x, const double *y, const dou
     if (grid < 1) grid = 1;
     unsigned long long *m = reinterpret_cast<unsigned long long *>(mesh);
     ctx->launches++;
+    // dynamic shared memory above 48 KB needs the per-kernel opt-in (once per kernel and device)
+    static bool optin_ngp[16], optin_cic[16];
+    const int dev = ctx->device & 15;
+    cudaError_t e;
     if (scheme == EMC_DEPOSIT_NGP) {
-        if (cells * 4 <= SMEM_MESH_BYTES)
+        if (cells * 4 <= SMEM_MESH_BYTES) {
+            if (cells * 4 > 48 * 1024 && !optin_ngp[dev]) {
+                if ((e = cudaFuncSetAttribute(deposit_ngp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              SMEM_MESH_BYTES)) != cudaSuccess) return e;
+                optin_ngp[dev] = true;
+            }
             deposit_ngp_kernel<true><<<grid, 256, (size_t)cells * 4, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
-        else
-            deposit_ngp_kernel<false><<<grid, 256, 0, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
+        } else {
+            return launch_deposit_large(ctx, x, y, z, n, m, cells, grid, st);
+        }
     } else {
-        if (cells * 8 <= SMEM_MESH_BYTES)
+        if (cells * 8 <= SMEM_MESH_BYTES) {
+            if (cells * 8 > 48 * 1024 && !optin_cic[dev]) {
+                if ((e = cudaFuncSetAttribute(deposit_cic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              SMEM_MESH_BYTES)) != cudaSuccess) return e;
+                optin_cic[dev] = true;
+            }
             deposit_cic_kernel<true><<<grid, 256, (size_t)cells * 8, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
-        else
+        } else {
             deposit_cic_kernel<false><<<grid, 256, 0, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
+        }
     }
     return cudaGetLastError();
 }
@@ -517,6 +541,7 @@ sor_lex_kernel(const __grid_constant__ SorConst S, double *u_g, const double *rh
         scalars[1] = relx;
         flags[0] = num;
         flags[1] = s_div;
+        if (s_div) flags[2] = 1;
     }
 }
 
@@ -561,7 +586,7 @@ sor_rb_kernel(const __grid_constant__ SorConst S, double *u, const double *__res
         const double bs = block_sum(acc, scratch);
         if (threadIdx.x == 0) {
             partials[blockIdx.x] = bs;
-            if (diverged) atomicExch(&flags[1], 1);
+            if (diverged) { atomicExch(&flags[1], 1); atomicExch(&flags[2], 1); }
         }
         grid.sync();
         // every block folds the partials in the same fixed order -> identical err everywhere
@@ -614,7 +639,8 @@ int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega
         if ((e = cudaMalloc(&ctx->d_err_hist, sizeof(double) * (size_t)max_sweeps)) != cudaSuccess) goto cuda_fail;
         ctx->err_hist_cap = max_sweeps;
     }
-    if ((e = cudaMemsetAsync(ctx->d_sor_flags, 0, 4 * sizeof(int32_t), st)) != cudaSuccess) goto cuda_fail;
+    // flags: [0] sweeps, [1] diverged (this solve), [2] diverged (sticky until emc_poisson_last reads it)
+    if ((e = cudaMemsetAsync(ctx->d_sor_flags, 0, 2 * sizeof(int32_t), st)) != cudaSuccess) goto cuda_fail;
     {
         const int64_t total = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
         ctx->launches++;
@@ -686,17 +712,18 @@ cuda_fail:
 int poisson_last(Ctx *ctx, int32_t *sweeps_out, double *err_out, cudaStream_t st)
 {
     double scal[2];
-    int32_t fl[2];
+    int32_t fl[3];
     cudaError_t e;
     if ((e = cudaMemcpyAsync(scal, ctx->d_sor_scalars, sizeof(scal), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
         (e = cudaMemcpyAsync(fl, ctx->d_sor_flags, sizeof(fl), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaMemsetAsync(ctx->d_sor_flags + 2, 0, sizeof(int32_t), st)) != cudaSuccess ||
         (e = cudaStreamSynchronize(st)) != cudaSuccess) {
         ctx->last_error = std::string("CUDA: ") + cudaGetErrorString(e);
         return EMC_ERR_CUDA;
     }
     if (sweeps_out) *sweeps_out = fl[0];
     if (err_out) *err_out = scal[0];
-    if (fl[1]) {
+    if (fl[1] || fl[2]) {       // this solve, or any enqueued-only solve since the last query
         ctx->last_error = "Too large du (poisson_.py:78-80)";
         return EMC_ERR_DIVERGED;
     }

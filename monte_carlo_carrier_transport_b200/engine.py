@@ -230,6 +230,17 @@ class Context:
         self.check(self.lib.emc_set_obs_phase(self.h, int(bool(before_step))))
         self.obs_before = bool(before_step)
 
+    def set_exact_libm(self, on: bool) -> None:
+        """``True``: compose acos / asin / atan exactly like scatter_.py:1061-1062 and the samplers
+        (:811-872) instead of their algebraic equivalents (``emc_set_exact_libm``)."""
+        self.check(self.lib.emc_set_exact_libm(self.h, int(bool(on))))
+
+    def describe(self) -> dict:
+        """Run-time knobs that select kernels on this context (``emc_describe``) as a dict."""
+        buf = C.create_string_buffer(512)
+        self.lib.emc_describe(self.h, buf, 512)
+        return dict(kv.split("=", 1) for kv in buf.value.decode().split())
+
     def select_layer(self, layer: int) -> None:
         """Material used by ``emc_calc_energy`` / ``emc_scatter`` (their ``mat`` / ``mat_i`` argument)."""
         self.check(self.lib.emc_select_layer(self.h, int(layer)))
@@ -352,6 +363,9 @@ class Ensemble:
         c = self.ctx
         co = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).to(c.device)
         assert co.shape == (self.n, 6)
+        dtau = np.ascontiguousarray(dtau, dtype=np.float64)
+        if dtau.shape != (self.n,):              # None would broadcast NaN into every free flight
+            raise ValueError("dtau must have shape (%d,), got %s" % (self.n, dtau.shape))
         p = self._ptrs()
         c.check(c.lib.emc_aos_to_soa(c.h, co.data_ptr(), self.n, *p[:6], c.stream))
         self.state[6].copy_(torch.from_numpy(np.ascontiguousarray(dtau, dtype=np.float64)))
@@ -674,11 +688,28 @@ class CoupledStepper:
         self._solve()
         self.n_steps += 1
 
-    def run_steps(self, n_steps: int):
+    def run_steps(self, n_steps: int, check_every: int = 0):
         """``n_steps`` coupled timesteps; rows[c] = observables after step c (``Ensemble.run_steps``:
-        reduced in the load phase of the next launch, no host round trip inside the loop)."""
-        return self.ens.run_steps(self.n_steps, n_steps, self.seed,
-                                  step_fn=lambda _c, out: self.step(observe=True, obs_out=out))
+        reduced in the load phase of the next launch, no host round trip inside the loop).
+
+        The Poisson solves are only enqueued, so a diverged solve (the reference's ``'Too large du'``
+        ValueError, poisson_.py:78-80 / main_.py:303) would go unnoticed: the solver keeps a STICKY
+        divergence flag on the device, which is read back (one synchronisation) every
+        ``check_every`` steps if that is > 0 and always at the end of the loop; ``EmcError``
+        (``ERR_DIVERGED``) is raised then."""
+        def one(c, out):
+            self.step(observe=True, obs_out=out)
+            if check_every > 0 and (c + 1 - first) % check_every == 0:
+                self.check_solver()
+        first = self.n_steps
+        rows = self.ens.run_steps(self.n_steps, n_steps, self.seed, step_fn=one)
+        self.check_solver()
+        return rows
+
+    def check_solver(self):
+        """(sweeps, err) of the latest solve; raises ``EmcError(ERR_DIVERGED)`` if ANY solve since
+        the last check diverged (synchronises the stream)."""
+        return self.mesh.last_solve()
 
 
 class HostStepper:

@@ -76,11 +76,11 @@ def calc_energy(k, val, mat_):
     return _calc_energy_gpu(k, val, mat_)
 
 
-def free_flight(G0=None):
-    """Free-flight duration -ln(r)/G0 with r from np.random.uniform (main_.py:114-123)."""
+def free_flight(G0=3E14):
+    """Free-flight duration -ln(r)/G0 with r from np.random.uniform (main_.py:114-123; the same
+    default G0 = 3E14 as the reference's signature)."""
     import torch
     ctx = default_context()
-    G0 = dev.Materials[0].tot_scat if G0 is None else G0
     r1 = np.random.uniform(0, 1)
     rd = _dev([r1], np.float64)
     out = torch.empty(1, dtype=torch.float64, device=ctx.device)
@@ -204,6 +204,17 @@ def photoex_count(num_carr, t):
     return int(num_carr * (1 + las.laser_eff * stats.norm.cdf(t, las.t0 + 3 * las.laser_t, las.laser_t)) - num_carr)
 
 
+def _first_flights(n, dtau):
+    """``dtau`` as given, or -- like main_.py:337, which always draws them itself -- one free flight
+    per carrier from the global numpy stream: ``[free_flight(mat[0].tot_scat) for i in range(num_carr)]``."""
+    if dtau is None:
+        return (-1 / dev.Materials[0].tot_scat) * np.log(np.random.uniform(0, 1, int(n)))
+    dtau = np.ascontiguousarray(dtau, dtype=np.float64)
+    if dtau.shape != (int(n),):
+        raise ValueError("dtau must have shape (%d,), got %s" % (n, dtau.shape))
+    return dtau
+
+
 def run(num_carr=None, pts=None, seed=12345, elec_field=None, coords=None, valley=None, dtau=None,
         ctx: engine.Context | None = None, history: bool = False, photoex: bool = False, t_start: float = 0.0):
     """The time loop of main_.py:325-403 on the GPU.
@@ -226,7 +237,7 @@ def run(num_carr=None, pts=None, seed=12345, elec_field=None, coords=None, valle
         # init_photoex dropped some, and then indexes past its coords array; here the ensemble
         # grows by the carriers that exist.
         if coords is not None:
-            ens.load(coords, valley if valley is not None else np.zeros(n, dtype=np.int32), dtau)
+            ens.load(coords, valley if valley is not None else np.zeros(n, dtype=np.int32), _first_flights(n, dtau))
         else:
             ens.init(seed)
         rows = []
@@ -239,7 +250,7 @@ def run(num_carr=None, pts=None, seed=12345, elec_field=None, coords=None, valle
             rows.append(o)
         return rows, ens
     if coords is not None:
-        ens.load(coords, valley if valley is not None else np.zeros(n, dtype=np.int32), dtau)
+        ens.load(coords, valley if valley is not None else np.zeros(n, dtype=np.int32), _first_flights(n, dtau))
     else:
         ens.init(seed)
     rows = []

@@ -69,10 +69,42 @@ def test_struct_layouts_match_the_header(lib, tmp_path):
 
 
 def test_sass_is_sm100a_and_has_no_local_spills_in_hot_kernel():
+    """sm_100a code only, no kernel with a LOCAL segment, and no local-memory load/store (LDL / STL:
+    what a register spill compiles to) inside the body of any default-path flight kernel.  The only
+    local accesses allowed are the ones in libdevice's out-of-line sincos range reduction (its scratch
+    array; reached for |x| > 1e5 only), which sit after the kernel's last EXIT."""
     from monte_carlo_carrier_transport_b200 import abi, build
     build.build()
     out = subprocess.run(["cuobjdump", "-lelf", abi.LIB_PATH], capture_output=True, text=True).stdout
-    assert "sm_100a" in out
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+    res = subprocess.run(["cuobjdump", "-res-usage", abi.LIB_PATH], capture_output=True, text=True).stdout
+    usage = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:\d+ LOCAL:(\d+)", res)
+    assert len(usage) > 40
+    for name, reg, stack, local in usage:
+        assert int(local) == 0, name
+        if "flight_scatter_kernel" in name:
+            assert int(reg) <= 128 and int(stack) <= 96, (name, reg, stack)     # 512 threads x 128 registers = one SM
+    sass = subprocess.run(["cuobjdump", "-sass", abi.LIB_PATH], capture_output=True, text=True).stdout
+    cur, last_exit, local_ops, seen = None, {}, {}, 0
+    for line in sass.splitlines():
+        m = re.match(r"\s+Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+        if not (cur and m):
+            continue
+        addr, op = int(m.group(1), 16), m.group(2)
+        if op == "EXIT":
+            last_exit[cur] = addr
+        elif op.startswith(("LDL", "STL")):
+            local_ops.setdefault(cur, []).append(addr)
+    for fn, end in last_exit.items():
+        # default path: EXACT = false (Lb0 after the field mode), no fused deposit
+        if "flight_scatter_kernel" in fn and re.search(r"ELi\dELb0ELb0ELb[01]E", fn):
+            seen += 1
+            assert all(a > end for a in local_ops.get(fn, [])), (fn, local_ops[fn], end)
+    assert seen >= 16          # 2 streams x 4 field modes x (single-layer, multi-layer)
 
 
 def test_no_cpu_fallback_without_a_gpu(lib):

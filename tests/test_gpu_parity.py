@@ -534,6 +534,37 @@ def test_deposit_and_sor_other_meshes(torch_mod, seg):
         c.close()
 
 
+@pytest.mark.parametrize("seg", [(128, 1, 128), (90, 1, 90), (64, 2, 96), (1024, 1, 1024)])
+def test_deposit_shared_memory_windows(torch_mod, seg):
+    """Every size class of the deposit launcher against the oracle, bit for bit: NGP counts that need
+    MORE than the 48 KB default of dynamic shared memory (128 x 1 x 128 = 64 KB: ADVICE r1, the launch
+    used to fail), CIC counts in the same window (90 x 1 x 90 and 64 x 2 x 96 cells x 8 B), and a mesh
+    far beyond one block's shared memory (1024 x 1 x 1024: the tiled / direct-atomic path)."""
+    torch = torch_mod
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    c = mesh_context(seg, torch)
+    try:
+        g = helpers.golden_params()["phys"]
+        rng = np.random.RandomState(18)
+        n = 300000
+        dl = np.array(c.params.dl[:])
+        pos = rng.uniform(0, 1, (n, 3)) * np.array(g["tot_dim"])
+        pos[:500] = np.round(pos[:500] / dl) * dl                     # on cell faces / edges / corners
+        pos[500:600, 2] = 0.0                                         # on the z = 0 wall
+        pos[600:700, 2] = g["tot_dim"][2]                             # on the far wall
+        coords = np.zeros((n, 6))
+        coords[:, 3:] = pos
+        ens = engine.Ensemble(c, n).load(coords, np.zeros(n, np.int32), np.ones(n))
+        for scheme, ofn in ((abi.DEPOSIT_NGP, orc.deposit_ngp), (abi.DEPOSIT_CIC, orc.deposit_cic)):
+            mesh = engine.Mesh(c, scheme)
+            for rep in range(2):                                      # ADDS to the mesh: twice = doubled
+                mesh.deposit(ens)
+            want = ofn(pos[:, 0], pos[:, 1], pos[:, 2], np.array(seg), dl)
+            assert np.array_equal(mesh.counts.cpu().numpy(), 2 * want), scheme
+    finally:
+        c.close()
+
+
 def test_fused_deposit_and_mesh_field_vs_oracle(torch_mod):
     """Coupled step: flight kernel gathers the mesh field (EMC_FIELD_MESH) and deposits its
     end-of-step positions in the same launch; both against the oracle."""
