@@ -54,7 +54,67 @@ def workload_config(n_gpus):
             "global_particles": N_FIELDS * PER_FIELD * n_gpus,
             "parallelism": "particle slices per rank, no data-path collective",
             "l2_policy": "inputs larger than L2 (1.44 GB of particle state per GPU vs 126 MB L2)",
-            "observables": "main_.py:394-403 reduced for every timestep inside the timed region"}
+            "observables": "main_.py:394-403 reduced for every timestep inside the timed region",
+            "reference_arm": "--impl reference times the oracle's C port of main_.py:360-397 (OpenMP, all host "
+                             "threads) on the SAME 2.4e7-particle ensemble (24 field groups x 1e6), one "
+                             "timestep per step; rates are per flight segment"}
+
+
+def python_reference_static():
+    """The REAL reference loop (unmodified main_.py:339-403, exec'd in the build container by
+    tests/golden/generate_golden.py) cannot travel to the GPU box: its recorded wall time is
+    carried as a labelled static field so that the Python original stays visible next to the C port."""
+    p = os.path.join(ROOT, "tests", "golden", "free_running_c1.json")
+    try:
+        g = json.load(open(p))
+        pts, n, wall = int(g["pts"]), int(g["num_carr"]), float(g["wall_s"])
+        seg_per_pt = 1.8                               # 1 + Gamma*dt flight segments per particle-timestep
+        return {"kind": "static: recorded in the build container, NOT measured in this run",
+                "source": "tests/golden/free_running_c1.json (unmodified reference, numpy %s)" % g["versions"]["numpy"],
+                "particles": n, "timesteps": pts, "wall_s": wall, "cores": int(g.get("cores", 1)),
+                "particle_timesteps_per_s": n * pts / wall, "steps_per_s": seg_per_pt * n * pts / wall, "unit": UNIT}
+    except Exception:      # noqa: BLE001
+        return None
+
+
+def active_knobs(ctx=None):
+    """Every EMC_* environment variable that is set, plus the context's own description of the
+    run-time switches that select kernels (emc_describe)."""
+    k = {"env": {n: v for n, v in sorted(os.environ.items()) if n.startswith("EMC_")}}
+    if ctx is not None:
+        try:
+            k["context"] = ctx.describe()
+        except Exception as exc:      # noqa: BLE001
+            k["context"] = repr(exc)
+    return k
+
+
+def bind_rank_to_cores(torch, local, world_local):
+    """One process per GPU: keep each rank on its own cores, on the NUMA node of its GPU when the
+    box has more than one (pinned buffers are first-touched there).  Returns a description."""
+    try:
+        all_cpus = sorted(os.sched_getaffinity(0))
+        node, cpus = None, all_cpus
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+            if node >= 0:
+                txt = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+                ids = []
+                for part in txt.split(","):
+                    a, _, b = part.partition("-")
+                    ids += list(range(int(a), int(b or a) + 1))
+                cpus = [c for c in ids if c in all_cpus] or all_cpus
+        except Exception:      # noqa: BLE001
+            node = None
+        per = max(1, len(cpus) // max(world_local, 1))
+        mine = cpus[(local * per) % len(cpus):][:per] or cpus
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, len(mine)))
+        return {"numa_node": node, "cpus": "%d-%d (%d)" % (mine[0], mine[-1], len(mine)), "host_cpus": len(all_cpus)}
+    except Exception as exc:      # noqa: BLE001
+        return {"error": repr(exc)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -200,14 +260,15 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_per_field = 500_000
-    value, dt, done, n = cpu_port_run(n_per_field, args.steps, args.warmup, threads)
-    sample = "%d particles (24 field groups x %d), %d timesteps" % (n, n_per_field, done)
+    n_per_field = PER_FIELD                       # the same 2.4e7-particle ensemble as the GPU arm
+    value, dt, done, n = cpu_port_run(n_per_field, args.steps, min(args.warmup, 2), threads, budget_s=150.0)
+    sample = "%d particles (24 field groups x %d), %d timesteps, %.1f s" % (n, n_per_field, done, dt)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_reference_python": python_reference_static(),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -396,6 +457,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    binding = bind_rank_to_cores(torch, local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     n = N_FIELDS * PER_FIELD
     ctx = engine.Context(device=local)             # init_ / scatter_ module state -> EmcParams + tables
     # global particle id = rank*n + i keys the Philox streams (rank-count invariant); every rank
@@ -465,10 +527,26 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    # the whole time loop as ONE call on the host arrays (main_.py:339-403: coords cross PCIe once each
+    # way per loop, K timesteps stay in HBM, K observable rows come back): K = the reference's pts = 50
+    loop_k, loop_calls = args.e2e_loop_steps, 2
+    hs.run(20_000, loop_k, SEED, field_mode=abi.FIELD_GROUPS)          # warm-up (row buffers)
+    barrier()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    seg_loop = 0
+    for r in range(loop_calls):
+        seg_loop += sum(row["n_segments"] for row in hs.run(30_000 + r * loop_k, loop_k, SEED, field_mode=abi.FIELD_GROUPS))
+    l1.record()
+    barrier()
+    loop_ms = l0.elapsed_time(l1)
 
     h2d_bytes, d2h_bytes = hs.h2d_bytes, hs.d2h_bytes
+    loop_h2d, loop_d2h = hs.run_h2d_bytes(loop_k), hs.run_d2h_bytes(loop_k)
     del hs
-    pcie = pcie_duplex_gbs(torch, ctx.device) if rank == 0 else None
+    barrier()
+    pcie = pcie_duplex_gbs(torch, ctx.device)      # all ranks at once: what the HOST sustains with N GPUs copying
+    barrier()
     coupled = coupled_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
     by_config = other_configs_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
     if by_config is not None:
@@ -476,19 +554,24 @@ def run_ours(args):
             diode_bench(torch, dist, engine, abi, local, rank, world, barrier)
 
     # ---- max over ranks, totals over ranks ---------------------------------------------------
-    t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=ctx.device)
-    c = torch.tensor([segments, seg_e2e, events, faults], dtype=torch.int64, device=ctx.device)
+    t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms, loop_ms, -pcie], dtype=torch.float64, device=ctx.device)
+    c = torch.tensor([segments, seg_e2e, events, faults, seg_loop], dtype=torch.int64, device=ctx.device)
+    per_rank = torch.zeros((world, 2), dtype=torch.float64, device=ctx.device)
+    per_rank[rank, 0], per_rank[rank, 1] = kernel_ms, elapsed_ms / steps
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms, kernel_ms = (float(v) for v in t.cpu())
-    segments, seg_e2e, events, faults = (int(v) for v in c.cpu())
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms, kernel_ms, loop_ms, neg_pcie = (float(v) for v in t.cpu())
+    pcie_min = -neg_pcie
+    segments, seg_e2e, events, faults, seg_loop = (int(v) for v in c.cpu())
+    per_rank = per_rank.cpu().numpy()
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = ALGO_BYTES_PER_PARTICLE_STEP * n / (kernel_ms * 1e-3) / 1e9
         threads = os.cpu_count() or 1
-        cpu_value, cpu_dt, cpu_steps, cpu_n = cpu_port_run(500_000, 400, 2, threads, budget_s=12.0)
+        cpu_value, cpu_dt, cpu_steps, cpu_n = cpu_port_run(PER_FIELD, 400, 1, threads, budget_s=12.0)
         line = {
             "metric": METRIC, "value": segments / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": elapsed_ms / steps, "higher_is_better": True,
@@ -499,20 +582,39 @@ def run_ours(args):
             "events_per_particle_timestep": events / (world * n * steps), "faulted_particles": faults,
             "roofline": {"bound": "hbm", "kernel": "flight_scatter_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
+                         "traffic_source": "static: ncu --set full capture committed as profiles/%s (dram__bytes_read.sum + "
+                                           "dram__bytes_write.sum of one launch), NOT measured in this run" % load_traffic("source"),
                          "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "kernel_ms_per_rank": {"min": float(per_rank[:, 0].min()), "median": float(np.median(per_rank[:, 0])),
+                                                "max": float(per_rank[:, 0].max()),
+                                                "all": [round(float(v), 4) for v in per_rank[:, 0]]},
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n,
                          "issue": issue_roofline(kernel_ms, (clk or {}).get("sm_mhz"))},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d particles (24 field groups x 500000), %d timesteps, %.1f s"
-                                       % (cpu_n, cpu_steps, cpu_dt)},
-            "e2e": {"value": seg_e2e / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes,
-                    "api": "engine.HostStepper.step: pinned host (N,6) coords + valley + dtau in, same out",
-                    "pcie_duplex_gbs_per_direction": pcie,
-                    "achieved_gbs_per_direction": world * h2d_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9 / world,
-                    "bound": "PCIe: the timestep moves 60 B per particle each way; the kernel is 3 % of it"},
-            "gpu_launches": int(launches), "clocks": clk, "coupled": coupled, "by_config": by_config,
+                             "sample": "%d particles (24 field groups x %d, the full workload), %d timesteps, %.1f s"
+                                       % (cpu_n, PER_FIELD, cpu_steps, cpu_dt)},
+            "cpu_reference_python": python_reference_static(),
+            # e2e = the reference's time loop (main_.py:339-403, pts = 50 timesteps) through the host-array
+            # API: the caller's pinned (N,6) coords / valley / dtau go in once, 50 timesteps run in HBM,
+            # the arrays and 50 observable rows come back.  The one-call-per-timestep API is kept beside it.
+            "e2e": {"value": seg_loop / (loop_ms * 1e-3), "unit": UNIT, "steps": loop_k * loop_calls,
+                    "steps_per_call": loop_k, "calls": loop_calls,
+                    "ms_per_step": loop_ms / (loop_k * loop_calls),
+                    "h2d_bytes_per_step": loop_h2d / loop_k, "d2h_bytes_per_step": loop_d2h / loop_k,
+                    "h2d_bytes_per_call": loop_h2d, "d2h_bytes_per_call": loop_d2h,
+                    "api": "engine.HostStepper.run(first_step, %d, seed): the whole time loop on pinned host (N,6) "
+                           "coords + valley + dtau, in place, one observable row per timestep" % loop_k,
+                    "per_step_api": {
+                        "value": seg_e2e / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
+                        "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes,
+                        "api": "engine.HostStepper.step: one timestep per call, host arrays in and out every call",
+                        "achieved_gbs_per_direction_per_gpu": h2d_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                        "bound": "PCIe / host DRAM: 60 B per particle each way per timestep; the kernel is 3 % of it"},
+                    "pcie_duplex_gbs_per_direction_per_gpu_all_ranks_copying": pcie_min,
+                    "host_binding": binding},
+            "gpu_launches": int(launches), "clocks": clk, "knobs": active_knobs(ctx),
+            "coupled": coupled, "by_config": by_config,
         }
         print(json.dumps(line))
     ctx.close()
@@ -527,6 +629,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-coupled", action="store_true", help="skip the coupled MC+Poisson sub-benchmark")
+    ap.add_argument("--e2e-loop-steps", type=int, default=50,
+                    help="timesteps per HostStepper.run call of the e2e arm (the reference's pts = 50, init_.py:61)")
     ap.add_argument("--obs-phase", default="before", choices=["before", "after"],
                     help="per-step observables reduced while loading the next step's state (default) or at retirement")
     args = ap.parse_args()

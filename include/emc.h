@@ -256,6 +256,13 @@ int emc_flight_scatter_replay(EmcCtx *ctx, double *kx, double *ky, double *kz, d
 int emc_observables(EmcCtx *ctx, const double *kx, const double *ky, const double *kz,
                     const double *z, const int32_t *valley, int64_t n, EmcObs *out, void *stream);
 
+/* The same reduction, only ENQUEUED: out_dev is a DEVICE pointer to one EmcObs, nothing is copied
+ * to the host and the stream is not synchronised (pipelines that read the row later, e.g. the
+ * chunked host-array time loop). */
+int emc_observables_async(EmcCtx *ctx, const double *kx, const double *ky, const double *kz,
+                          const double *z, const int32_t *valley, int64_t n, EmcObs *out_dev,
+                          void *stream);
+
 /* ---- single-function batches (the reference's per-particle signatures, n particles) -------- */
 /* scatter_.calc_energy (scatter_.py:19-54): e_np[n], idx[n], fault[n] (-1 = ok) */
 int emc_calc_energy(EmcCtx *ctx, const double *kx, const double *ky, const double *kz,

@@ -91,6 +91,7 @@ SIGNATURES = {
     "emc_flight_scatter_replay": (C.c_int, [_vp] + [_dp] * 7 + [_ip, _i64, _i32, _dp, _dp, _dp,
                                                                _u64, _dp, _i64, _ip, _vp, _lp, _vp]),
     "emc_observables": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip, _i64, C.POINTER(EmcObs), _vp]),
+    "emc_observables_async": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip, _i64, _vp, _vp]),
     "emc_calc_energy": (C.c_int, [_vp, _dp, _dp, _dp, _ip, _i64, _dp, _ip, _ip, _vp]),
     "emc_free_flight": (C.c_int, [_vp, _f64, _dp, _i64, _dp, _vp]),
     "emc_carrier_drift": (C.c_int, [_vp] + [_dp] * 6 + [_dp, _dp, _dp, _i64, _vp]),

@@ -583,6 +583,16 @@ extern "C" int emc_observables(EmcCtx *ctx, const double *kx, const double *ky, 
     return EMC_OK;
 }
 
+extern "C" int emc_observables_async(EmcCtx *ctx, const double *kx, const double *ky, const double *kz,
+                                     const double *z, const int32_t *valley, int64_t n, EmcObs *out_dev, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!out_dev || n < 0 || (n > 0 && (!kx || !ky || !kz || !z || !valley)))
+        return fail(c, EMC_ERR_INVALID, "emc_observables_async: bad argument");
+    cudaError_t e = launch_observables(c, kx, ky, kz, z, valley, n, out_dev, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "observables launch");
+}
+
 extern "C" int emc_calc_energy(EmcCtx *ctx, const double *kx, const double *ky, const double *kz,
                                const int32_t *valley, int64_t n, double *e_np, int32_t *idx, int32_t *fault,
                                void *stream)

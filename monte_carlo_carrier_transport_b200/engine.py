@@ -755,6 +755,88 @@ class HostStepper:
     def d2h_bytes(self) -> int:
         return self.n * (48 + 4 + 8) + self.n_chunks * 88
 
+    def run(self, first_step: int, n_steps: int, seed: int, field_mode: int = abi.FIELD_CONSTANT) -> list:
+        """The WHOLE time loop of main_.py:339-403 on the pinned host arrays, in place: the reference
+        needs ``coords`` on the host only before and after the loop and seven scalars per timestep,
+        so every chunk crosses PCIe once in each direction -- H2D, ``n_steps`` launches that keep the
+        chunk in HBM (``emc_flight_scatter_steps``, per-step EmcObs rows reduced on the device in the
+        load phase of the next launch + one enqueued reduction of the final state), D2H -- and the
+        three stages of consecutive chunks overlap on three streams.  Returns one observable dict
+        per timestep (``rows[c]`` = the ensemble after step ``first_step + c``, like
+        ``Ensemble.run_steps``).  Bytes moved per timestep: ``run_h2d_bytes(n_steps) / n_steps``."""
+        torch = _torch()
+        c, lib = self.ctx, self.ctx.lib
+        n_steps = int(n_steps)
+        if n_steps < 1:
+            return []
+        rows_dev = getattr(self, "_rows_dev", None)
+        if rows_dev is None or rows_dev.shape[1] < n_steps + 1:
+            self._rows_dev = rows_dev = torch.zeros((len(self.bufs), n_steps + 1, 11), dtype=torch.int64, device=c.device)
+            self._rows_pinned = torch.zeros((self.n_chunks, n_steps + 1, 11), dtype=torch.int64).pin_memory()
+        rows_pinned = self._rows_pinned
+        cur = torch.cuda.current_stream(c.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(cur)
+        was = c.obs_before
+        c.set_obs_phase(True)
+        try:
+            for ci in range(self.n_chunks):
+                lo = ci * self.chunk
+                m = min(self.chunk, self.n - lo)
+                bi = ci % len(self.bufs)
+                b = self.bufs[bi]
+                with torch.cuda.stream(self.s_in):
+                    if ci >= len(self.bufs):
+                        self.s_in.wait_event(b["free"])
+                    b["aos"][:m].copy_(self.coords_t[lo:lo + m], non_blocking=True)
+                    b["soa"][6, :m].copy_(self.dtau_t[lo:lo + m], non_blocking=True)
+                    b["valley"][:m].copy_(self.valley_t[lo:lo + m], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(self.s_in)
+                with torch.cuda.stream(self.s_run):
+                    self.s_run.wait_event(ev_in)
+                    st = C.c_void_p(self.s_run.cuda_stream)
+                    base, stride = b["soa"].data_ptr(), self.chunk * 8
+                    ptrs = [base + r * stride for r in range(7)] + [b["valley"].data_ptr()]
+                    rows = rows_dev[bi]
+                    c.check(lib.emc_aos_to_soa(c.h, b["aos"].data_ptr(), m, *ptrs[:6], st))
+                    c.check(lib.emc_flight_scatter_steps(c.h, *ptrs, m, field_mode, None, None, None, seed,
+                                                         self.pid_offset + lo, first_step, n_steps,
+                                                         rows.data_ptr(), st))
+                    c.check(lib.emc_observables_async(c.h, ptrs[0], ptrs[1], ptrs[2], ptrs[5], ptrs[7], m,
+                                                      rows.data_ptr() + n_steps * 88, st))
+                    c.check(lib.emc_soa_to_aos(c.h, *ptrs[:6], m, b["aos"].data_ptr(), st))
+                    b["done"].record(self.s_run)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(b["done"])
+                    self.coords_t[lo:lo + m].copy_(b["aos"][:m], non_blocking=True)
+                    self.dtau_t[lo:lo + m].copy_(b["soa"][6, :m], non_blocking=True)
+                    self.valley_t[lo:lo + m].copy_(b["valley"][:m], non_blocking=True)
+                    rows_pinned[ci, :n_steps + 1].copy_(rows[:n_steps + 1], non_blocking=True)
+                    b["free"].record(self.s_out)
+        finally:
+            c.set_obs_phase(was)
+        self.s_out.synchronize()
+        cur.wait_stream(self.s_out)
+        raw = rows_pinned.numpy()[:, :n_steps + 1]
+        d = raw[:, :, :5].copy().view(np.float64).sum(axis=0)         # (n_steps + 1, 5): sums over the chunks
+        k = raw[:, :, 5:].sum(axis=0)
+        out = []
+        for s in range(n_steps):
+            # row s holds the WORK of step s (segments, events) and the state BEFORE it; the state after
+            # step s is what row s + 1 (or the final reduction) saw
+            out.append(dict(sum_z=float(d[s + 1, 0]), sum_vz=float(d[s + 1, 1]), sum_e=float(d[s + 1, 2]),
+                            sum_vz2=float(d[s + 1, 3]), sum_e2=float(d[s + 1, 4]),
+                            n_valley=[int(k[s + 1, 0]), int(k[s + 1, 1]), int(k[s + 1, 2])],
+                            n_fault=int(k[s + 1, 3]), n_segments=int(k[s, 4]), n_events=int(k[s, 5])))
+        return out
+
+    def run_h2d_bytes(self, n_steps: int) -> int:
+        return self.h2d_bytes
+
+    def run_d2h_bytes(self, n_steps: int) -> int:
+        return self.n * (48 + 4 + 8) + self.n_chunks * 88 * (int(n_steps) + 1)
+
     def step(self, step: int, seed: int, field_mode: int = abi.FIELD_CONSTANT) -> dict:
         """One timestep on the pinned host arrays, in place; returns the observables."""
         torch = _torch()

@@ -421,6 +421,35 @@ def test_host_stepper_matches_device_path(ctx, torch_mod):
     assert abs(tot["sum_e"] - od["sum_e"]) < 1e-10 * abs(od["sum_e"])
 
 
+def test_host_stepper_whole_loop_matches_device_path(ctx, torch_mod):
+    """HostStepper.run: the whole time loop with ONE host round trip per chunk gives the state of
+    K single host-array timesteps bit for bit and the same K observable rows (counts identical,
+    sums to rounding: the chunks are reduced separately)."""
+    from monte_carlo_carrier_transport_b200 import engine
+    g = helpers.golden_params()["phys"]
+    n, K = 50001, 7
+    coords, v, dtau = hot_ensemble(n, 35, g)
+    ens = engine.Ensemble(ctx, n, pid_offset=11).load(coords, v, dtau)
+    want = []
+    for s in range(K):
+        ens.step(100 + s, 98)
+        want.append(ens.last_obs())
+    for chunk in (7000, 1 << 21):
+        hs = engine.HostStepper(ctx, n, chunk=chunk, pid_offset=11)
+        hs.coords[:], hs.valley[:], hs.dtau[:] = coords, v, dtau
+        rows = hs.run(100, K, 98)
+        co, val, dt_ = ens.coords()
+        assert np.array_equal(hs.coords, co) and np.array_equal(hs.valley, val) and np.array_equal(hs.dtau, dt_)
+        assert len(rows) == K
+        for got, ref in zip(rows, want):
+            for key in ("n_valley", "n_fault", "n_segments", "n_events"):
+                assert got[key] == ref[key], key
+            for key in ("sum_z", "sum_vz", "sum_e", "sum_vz2", "sum_e2"):
+                assert abs(got[key] - ref[key]) <= 1e-11 * abs(ref[key]), key
+        assert hs.run_d2h_bytes(K) == n * 60 + hs.n_chunks * 88 * (K + 1)
+    assert not ctx.obs_before                                   # the phase switch is restored
+
+
 # ------------------------------------------------------------------------------------------
 def poisson_inputs():
     p = helpers.golden_npz("poisson")
