@@ -188,6 +188,10 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
         c->max_grid = c->sm_count * per_sm;
         const char *fa = std::getenv("EMC_FIELD_AHEAD");
         c->no_field_ahead = fa && std::atoi(fa) == 0;
+        const char *ln = std::getenv("EMC_LEAN");
+        c->no_lean = ln && std::atoi(ln) == 0;
+        const char *br = std::getenv("EMC_BULK_REFILL");
+        c->no_bulk_refill = br && std::atoi(br) == 0;
         const char *ex = std::getenv("EMC_EXACT_LIBM");
         c->exact_libm = ex && std::atoi(ex) != 0;
     }
@@ -325,6 +329,21 @@ static int upload_tables_layer(Ctx *c, int layer, const double *ek, int32_t n_en
     c->dc.inv_ek_step = 1 / step;
     c->dc.e_max = ek[n_energy - 1];
     c->layer_tables[layer] = true;
+    {   // the lean flight kernel's assumption (select_self_spec<LEAN>): in every valley of every layer the
+        // last column is the ONLY self-scattering mechanism, changes neither energy nor valley
+        bool ok = true;
+        for (int l = 0; l < c->dc.n_layers && ok; ++l) {
+            if (!c->layer_tables[l]) continue;
+            const MechMeta &mm = c->mech_layers[l];
+            for (int v = 0; v < 3 && ok; ++v)
+                for (int j = 0; j < c->dc.n_mech[v]; ++j) {
+                    const bool last = j == c->dc.n_mech[v] - 1;
+                    if ((mm.sampler[v][j] == EMC_SAMPLER_SELF) != last) ok = false;
+                    if (last && (mm.dE[v][j] != 0.0 || mm.trans[v][j] != v)) ok = false;
+                }
+        }
+        c->self_last = ok;
+    }
     c->have_tables = true;
     for (int l = 0; l < c->dc.n_layers; ++l) c->have_tables = c->have_tables && c->layer_tables[l];
     return EMC_OK;
@@ -389,10 +408,10 @@ extern "C" int emc_describe(const EmcCtx *ctx, char *buf, int32_t cap)
     const Ctx *c = &ctx->c;
     const char *sor = std::getenv("EMC_SOR_BLOCKS_PER_SM");
     const int n = std::snprintf(buf, (size_t)cap,
-                                "exact_libm=%d zonly_constant=%d zonly_groups=%d field_ahead=%d waves=%d max_grid=%d "
+                                "exact_libm=%d zonly_constant=%d zonly_groups=%d field_ahead=%d bulk_refill=%d lean=%d waves=%d max_grid=%d "
                                 "obs_before=%d n_layers=%d literal_scan=%d sor_blocks_per_sm=%s flight_threads=%d",
                                 (int)c->exact_libm, (int)c->zonly_constant, (int)c->zonly_groups,
-                                (int)!c->no_field_ahead, c->waves, c->max_grid, c->obs_before, c->dc.n_layers,
+                                (int)!c->no_field_ahead, (int)!c->no_bulk_refill, (int)(!c->no_lean && c->self_last), c->waves, c->max_grid, c->obs_before, c->dc.n_layers,
                                 c->dc.literal_scan, sor ? sor : "auto", FLIGHT_THREADS);
     return n < cap ? n : cap - 1;
 }
@@ -501,6 +520,8 @@ static int flight_common(Ctx *c, FlightArgs &A, bool replay, int32_t field_mode,
     if (field_mode == EMC_FIELD_MESH_PACKED && (!ex || ((uintptr_t)ex & 31) != 0))
         return fail(c, EMC_ERR_INVALID, "EMC_FIELD_MESH_PACKED needs a 32-byte aligned packed field in ex");
     if (field_mode < 0 || field_mode > EMC_FIELD_MESH_PACKED) return fail(c, EMC_ERR_INVALID, "unknown field_mode");
+    if (A.n >= ((int64_t)1 << 32) - 64)
+        return fail(c, EMC_ERR_UNSUPPORTED, "at most 2^32 - 65 particles per call: slice the ensemble (pid_offset keeps the random streams global)");
     if (c->dc.n_layers > 1 && A.mesh)
         return fail(c, EMC_ERR_UNSUPPORTED, "multi-layer devices: no fused deposit (use emc_deposit)");
     A.ex = ex; A.ey = ey; A.ez = ez;

@@ -2,6 +2,8 @@
 // (main_.py:360-397), its observables (main_.py:394-403), the ensemble initialiser
 // (init_.py:194-234) and the single-function batch kernels behind the reference's
 // per-particle signatures.  sm_100a; compiled with -fmad=false (see emc_device.cuh).
+#include <cstddef>
+#include <type_traits>
 #include "emc_host.h"
 
 namespace emc {
@@ -227,6 +229,64 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+#ifndef EMC_BULK_REFILL
+// 1: the next refill batch (32 particles: 256 B of each of the seven fp64 rows + 128 B of valleys) is
+// brought into a per-warp shared-memory tile by EIGHT bulk async copies issued by one lane
+// (cp.async.bulk.shared.global, SASS UBLKCP, completion on an mbarrier) right after the previous
+// batch has been read out of the tile -- a whole pass (thousands of cycles) before it is needed.
+// The refill phase then reads shared memory instead of waiting for HBM: in profiles/r1w the first
+// use of the refill loads was 10.7 % of all stall samples (long scoreboard) although the rows had
+// been prefetched into L2, and the per-lane loads plus the prefetch address arithmetic were ~55
+// instructions per batch.  Needs 16-byte aligned rows (checked by the launcher, FlightArgs.bulk);
+// the ragged last batch of a slice and unaligned callers take the per-lane loads below.
+#define EMC_BULK_REFILL 1
+#endif
+struct alignas(16) RefillTile {              // bulk-copy destinations are 16-byte aligned: the size is a multiple of 16
+    double row[7][32];                       // kx ky kz x y z dtau of the next batch
+    int32_t val[32];
+    unsigned long long bar;                  // mbarrier: one arrival (the issuing lane) + 1920 bytes
+};
+static_assert(sizeof(RefillTile) % 16 == 0, "RefillTile must keep the next tile 16-byte aligned");
+constexpr uint32_t REFILL_TILE_BYTES = 7 * 256 + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one lane of the (converged) warp, chosen by the hardware: code under `if (elect_one())` compiles to
+// straight uniform-datapath instructions (an `if (lane == 0)` makes ptxas wrap every bulk copy in a
+// uniformisation loop)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    return leader != 0;
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// one lane: arm the tile's mbarrier with the byte count and issue the eight row copies of the batch at `j`
+__device__ __forceinline__ void refill_issue(RefillTile &T, const FlightArgs &A, uint32_t j)
+{
+    const uint32_t bar = smem_u32(&T.bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(REFILL_TILE_BYTES) : "memory");
+    const uint32_t t0 = smem_u32(&T.row[0][0]);
+#pragma unroll
+    for (int r = 0; r < 7; ++r) bulk_g2s(t0 + r * 256, (&A.kx)[r] + j, 256u, bar);
+    bulk_g2s(smem_u32(&T.val[0]), A.valley + j, 128u, bar);
+}
+
+__device__ __forceinline__ void refill_wait(RefillTile &T, uint32_t parity)
+{
+    const uint32_t bar = smem_u32(&T.bar);
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
 constexpr int QCAP = 64;                    // a phase runs only if its pushes fit: <= 32 + 32
 // A queue entry is four 16-byte pairs (one 128-bit shared-memory access each, consecutive slots:
 // conflict-free) instead of seven 8-byte and three 4-byte fields: a pop is 4 loads, a push 4 stores.
@@ -327,7 +387,7 @@ __device__ __forceinline__ void field_stage(const FlightArgs &A, int64_t c, Fiel
     asm volatile("cp.async.commit_group;");
 }
 
-template <int FIELD>
+template <int FIELD, bool ZON = false>
 __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A, const Particle &p, int64_t c,
                                          double &efx, double &efy, double &efz, FieldStage &FS, int lane,
                                          bool staged = false)
@@ -336,7 +396,7 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
         efx = P.efield[0]; efy = P.efield[1]; efz = P.efield[2];
     } else if (FIELD == EMC_FIELD_GROUPS) {
         efz = __ldg(P.field_groups + 3 * p.grp + 2);
-        if (P.zonly) { efx = 0.0; efy = 0.0; }
+        if (ZON || P.zonly) { efx = 0.0; efy = 0.0; }
         else { efx = __ldg(P.field_groups + 3 * p.grp); efy = __ldg(P.field_groups + 3 * p.grp + 1); }
     } else {
         // nearest-cell gather from the padded (nx+2,ny+2,nz+2) field of emc_field, V/m -> V/cm
@@ -359,7 +419,7 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
 
 // retire a particle: write its state back, add it to the observables and the charge mesh
 template <bool REPLAY, bool DEPOSIT, bool ML>
-__device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, int64_t i, const Particle &p,
+__device__ __forceinline__ void retire(const DevConst &P, const FlightArgs &A, uint32_t i, const Particle &p,
                                        uint32_t cursor, FlightObsAcc &acc, unsigned int *smesh)
 {
     A.kx[i] = p.kx; A.ky[i] = p.ky; A.kz[i] = p.kz;
@@ -393,6 +453,50 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
     if (FIELD == EMC_FIELD_GROUPS) Q.grp[slot] = p.grp;
 }
 
+#ifndef EMC_LEAN_KERNEL
+#define EMC_LEAN_KERNEL 1
+#endif
+#ifndef EMC_PREDICATED_TAIL
+// 1: the write-back of a finished particle and the queue pushes are predicated stores instead of
+// branches around them.  The loop tail ran at 130 stall samples per instruction against 43 in the
+// select block (profiles/r1w source page): BSSY / BRA / BSYNC triples around a handful of stores,
+// each with its branch-resolution bubble, on a kernel that is bound by per-warp latency.
+#define EMC_PREDICATED_TAIL 1
+#endif
+// the same push as predicated shared-memory stores (no branch around them); `on` is the lane's predicate
+template <int FIELD>
+__device__ __forceinline__ void queue_push_if(WarpQueue &Q, int slot, const Particle &p, uint32_t s0, bool on)
+{
+    const uint32_t a = smem_u32(&Q.k01[0]) + (uint32_t)slot * 16u;
+    const double w = __hiloint2double((int)s0, (int)(p.off | ((uint32_t)p.val << 29)));
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+                 "@q st.shared.v2.f64 [%0], {%1, %2};\n\t"
+                 "@q st.shared.v2.f64 [%0+1024], {%3, %4};\n\t"
+                 "@q st.shared.v2.f64 [%0+2048], {%5, %6};\n\t"
+                 "@q st.shared.v2.f64 [%0+3072], {%7, %8};\n\t}"
+                 ::"r"(a), "d"(p.kx), "d"(p.ky), "d"(p.kz), "d"(p.x), "d"(p.y), "d"(p.z), "d"(p.dte), "d"(w),
+                 "r"((uint32_t)on) : "memory");
+    if (FIELD == EMC_FIELD_GROUPS) {
+        const uint32_t g = smem_u32(&Q.grp[0]) + (uint32_t)slot * 4u;
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u32 [%0], %1;\n\t}"
+                     ::"r"(g), "r"(p.grp), "r"((uint32_t)on) : "memory");
+    }
+}
+static_assert(offsetof(WarpQueue, k2x) == 1024 && offsetof(WarpQueue, yz) == 2048 && offsetof(WarpQueue, tw) == 3072,
+              "queue_push_if hard-codes the WarpQueue layout");
+
+// write-back of a finished particle as eight predicated global stores
+__device__ __forceinline__ void retire_stores_if(const FlightArgs &A, uint32_t i, const Particle &p, int val, bool on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %16, 0;\n\t"
+                 "@q st.global.f64 [%0], %8;\n\t@q st.global.f64 [%1], %9;\n\t@q st.global.f64 [%2], %10;\n\t"
+                 "@q st.global.f64 [%3], %11;\n\t@q st.global.f64 [%4], %12;\n\t@q st.global.f64 [%5], %13;\n\t"
+                 "@q st.global.f64 [%6], %14;\n\t@q st.global.u32 [%7], %15;\n\t}"
+                 ::"l"(A.kx + i), "l"(A.ky + i), "l"(A.kz + i), "l"(A.x + i), "l"(A.y + i), "l"(A.z + i), "l"(A.dtau + i),
+                 "l"(A.valley + i), "d"(p.kx), "d"(p.ky), "d"(p.kz), "d"(p.x), "d"(p.y), "d"(p.z), "d"(p.dte), "r"(val),
+                 "r"((uint32_t)on) : "memory");
+}
+
 template <int FIELD>
 __device__ __forceinline__ void queue_pop(const WarpQueue &Q, int slot, Particle &p, uint32_t &s0)
 {
@@ -414,12 +518,20 @@ __device__ __forceinline__ void queue_pop(const WarpQueue &Q, int slot, Particle
 #else
 #define EMC_FLIGHT_BOUNDS __launch_bounds__(FLIGHT_THREADS, EMC_FLIGHT_MIN_BLOCKS)
 #endif
-template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML>
+// LEAN: the instantiation for the common production launch -- free-running Philox, default libm
+// composition, no fused deposit, observables (if any) in the before-step phase, padded tables whose last
+// column is self-scattering, and for the constant / group field modes Ex = Ey = +0 -- with every
+// alternative of those run-time switches compiled OUT.  The kernel is sensitive to the size of its
+// loop (three copies of the flight code cost 50 %, profiles/ab_r2g): 270 instructions and 9 registers
+// fewer are 2.4 % (profiles/ab_r2h).  launch_flight picks it whenever the conditions hold.
+template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML, bool LEAN = false>
 __global__ void EMC_FLIGHT_BOUNDS
 flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg,
                       const __grid_constant__ FlightArgs A)
 {
     constexpr bool REPLAY = Stream::is_replay;
+    constexpr bool ZON = LEAN && (FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS);   // zonly known at compile time
+    static_assert(!LEAN || (!REPLAY && !EXACT && !DEPOSIT), "LEAN is the Philox / default-libm / no-deposit kernel");
     __shared__ MechMeta Ms[ML ? EMC_MAX_LAYERS : 1];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     WarpQueues *queues = reinterpret_cast<WarpQueues *>(dyn_smem);
@@ -428,8 +540,11 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     const size_t fs_bytes = AHEAD ? sizeof(FieldStage) : 0;
     FieldStage *fstages = reinterpret_cast<FieldStage *>(dyn_smem + sizeof(WarpQueues) * (FLIGHT_THREADS / 32));
     constexpr size_t OBS_BYTES = EMC_OBS_SMEM ? sizeof(double) * 5 * FLIGHT_THREADS : 0;
-    double *obs_columns = reinterpret_cast<double *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes) * (FLIGHT_THREADS / 32));
-    unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes) * (FLIGHT_THREADS / 32) + OBS_BYTES);
+    const bool BULK = EMC_BULK_REFILL && A.bulk;                  // warp-uniform (kernel argument)
+    const size_t rt_bytes = BULK ? sizeof(RefillTile) : 0;
+    RefillTile *rtiles = reinterpret_cast<RefillTile *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes) * (FLIGHT_THREADS / 32));
+    double *obs_columns = reinterpret_cast<double *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes + rt_bytes) * (FLIGHT_THREADS / 32));
+    unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes + rt_bytes) * (FLIGHT_THREADS / 32) + OBS_BYTES);
     {
         const int nw = sizeof(MechMeta) / 4;
         uint32_t *dst = reinterpret_cast<uint32_t *>(&Ms[0]);
@@ -448,7 +563,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     acc.zero(obs_columns + threadIdx.x);
 
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the warp index through a full-mask shuffle from lane 0: the compiler then KNOWS it is warp-uniform
+    // and keeps everything derived from it (slice bounds, queue and tile addresses, the operands of the
+    // bulk copies) in uniform registers
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const unsigned lt_mask = (1u << lane) - 1u;
     WarpQueues &WQ = queues[warp];
     FieldStage &FS = fstages[AHEAD ? warp : 0];                   // only dereferenced when AHEAD
@@ -462,6 +580,19 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     // valley above the slice offset): `next` and the slice length relative to wstart
     uint32_t next = 0;
     const uint32_t wlen = (uint32_t)(wend - wstart);
+    const uint32_t w0 = (uint32_t)wstart;
+    RefillTile &RT = rtiles[BULK ? warp : 0];                     // only dereferenced when BULK
+    uint32_t rt_parity = 0;                                       // phase of the tile's mbarrier the next wait expects
+    bool rt_pending = false;                                      // a full batch at `next` is in flight / has landed
+    if (BULK) {
+        if (elect_one()) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&RT.bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        rt_pending = wlen >= 32u;
+        if (rt_pending && elect_one()) refill_issue(RT, A, w0);
+    }
 #if EMC_STAGE_REFILL
     stage_batch(WQ, A, wstart + next + lane, wend, lane);
 #endif
@@ -505,7 +636,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         Particle p;
         Stream rng;
         uint32_t s0 = 0;
-        int64_t i = 0;
+        // particle index inside the launch in 32 bits (launch_flight refuses n >= 2^32 - 64): every
+        // state access is then ONE IMAD.WIDE.U32 off the row pointer in the constant bank instead of a
+        // 64-bit add per row
+        uint32_t i = 0;
         int mech = 0;
         double e_np = 0.0, r_az = 0.0;
         bool act, pend = false, fly = false, park = false, tail = false;
@@ -519,28 +653,34 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         bool ahead = false;
         if (phase == PH_REFILL) {
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
-            i = wstart + next + lane;
+            i = w0 + next + lane;
             act = next + lane < wlen;
             if (AHEAD && next + lane + 32 < wlen) {
                 ahead = true;
-                nx_ = A.x[i + 32]; ny_ = A.y[i + 32]; nz_ = A.z[i + 32];
+                nx_ = A.x[i + 32u]; ny_ = A.y[i + 32u]; nz_ = A.z[i + 32u];
             }
 #if EMC_STAGE_REFILL
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
-            if (act) {
-#if EMC_STAGE_REFILL
-                p.kx = WQ.stage[0][lane]; p.ky = WQ.stage[1][lane]; p.kz = WQ.stage[2][lane];
-                p.x = WQ.stage[3][lane]; p.y = WQ.stage[4][lane]; p.z = WQ.stage[5][lane];
-                p.dte = WQ.stage[6][lane];
-                p.val = WQ.stage_val[lane];
-#else
+            if (BULK && rt_pending) {
+                // the whole batch sits in the tile (issued one refill ago): act is true for every lane
+                refill_wait(RT, rt_parity);
+                rt_parity ^= 1u;
+                p.kx = RT.row[0][lane]; p.ky = RT.row[1][lane]; p.kz = RT.row[2][lane];
+                p.x = RT.row[3][lane]; p.y = RT.row[4][lane]; p.z = RT.row[5][lane];
+                p.dte = RT.row[6][lane];
+                p.val = RT.val[lane];
+                __syncwarp();                                     // every lane has read its slot: the tile may be refilled
+                rt_pending = next + 64u <= wlen;                  // the following batch is a full one, too
+                if (rt_pending && elect_one()) refill_issue(RT, A, w0 + next + 32u);
+            } else if (act) {
                 p.kx = A.kx[i]; p.ky = A.ky[i]; p.kz = A.kz[i];
                 p.x = A.x[i]; p.y = A.y[i]; p.z = A.z[i];
                 p.dte = A.dtau[i];
                 p.val = A.valley[i];
-#endif
-                p.off = (uint32_t)(i - wstart);
+            }
+            if (act) {
+                p.off = next + lane;
                 p.grp = 0;
                 if (REPLAY) s0 = (uint32_t)A.cursor[i];
                 if (FIELD == EMC_FIELD_GROUPS) {
@@ -581,7 +721,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 // parameters, indexed from the constant bank)
                 const uint32_t o0 = next + (uint32_t)(EMC_PREFETCH_BATCHES - 1) * 32u;
                 const int64_t j0 = wstart + o0;
-                if (o0 < wlen && lane < 15 && (!(lane & 1) || lane == 14 || o0 + 16 < wlen)) {
+                if (!BULK && o0 < wlen && lane < 15 && (!(lane & 1) || lane == 14 || o0 + 16 < wlen)) {
                     const char *base = reinterpret_cast<const char *>((&A.kx)[lane >> 1]);
                     const int64_t off = lane < 14 ? j0 * 8 + (lane & 1) * 128 : j0 * 4;
                     prefetch_l2(base + off);
@@ -610,7 +750,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             }
             __syncwarp();
             if (act) {
-                i = wstart + p.off;
+                i = w0 + p.off;
                 if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
                 if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
                 else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
@@ -623,7 +763,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     layer = 0;
                 } else if (sel && SPEC) {
                     bool is_self;
-                    f = select_self_spec(P, MT, M, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
+                    f = select_self_spec<Stream, LEAN>(P, MT, M, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
                     if (f < 0) {
                         if (is_self) tail = true;
                         else { park = true; s0 = rng.state(); }
@@ -676,16 +816,16 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         if (AHEAD_OK && AHEAD && phase == PH_REFILL) asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (fly) {                                                // :367 / :373 / :388
             double efx, efy, efz;
-            field_at<FIELD>(P, A, p, cell, efx, efy, efz, FS, lane, AHEAD_OK && AHEAD && phase == PH_REFILL);
+            field_at<FIELD, ZON>(P, A, p, cell, efx, efy, efz, FS, lane, AHEAD_OK && AHEAD && phase == PH_REFILL);
             const Mat &MT = P.mat[ML ? layer : 0];
             const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
-            if ((FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) && P.zonly)
+            if ((FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) && (ZON || P.zonly))
                 carrier_drift<true>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             else
                 carrier_drift<false>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             acc.count_segment();
         }
-        if (AHEAD && phase == PH_REFILL) {
+        if (phase == PH_REFILL && AHEAD) {
             // the rs slots of this batch have been read (own lane, program order): gather the next one
             if (ahead) {
                 Particle q;
@@ -694,6 +834,41 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             }
             field_staged = next < wlen;           // `next` already points at that batch
         }
+#if EMC_PREDICATED_TAIL
+        {
+            const bool done = act && !pend && !park;
+            int val = p.val, lay = 0;
+            if (ML && val >= 0) {                     // main_.py:393: the layer of the final position
+                lay = where_am_i(P, p.z);
+                if (lay < 0) { val = -(1 + EMC_FAULT_OUTSIDE); lay = 0; }
+            }
+            retire_stores_if(A, i, p, val, done);
+            if (REPLAY && done) A.cursor[i] = (int32_t)s0;
+            if (!LEAN && A.obs && !A.obs_before) {    // warp-uniform: the default phase reduces at load time
+                if (done) obs_particle(P, P.mat[lay], acc, p.kx, p.ky, p.kz, p.z, val);
+            }
+            if (DEPOSIT && done) {
+                if (A.smem_cells > 0)
+                    deposit_ngp_particle(P, p.x, p.y, p.z, [&](int64_t c) { atomicAdd(&smesh[c], 1u); });
+                else
+                    deposit_ngp_particle(P, p.x, p.y, p.z, [&](int64_t c) {
+                        atomicAdd(reinterpret_cast<unsigned long long *>(A.mesh) + c, 1ull); });
+            }
+        }
+        const unsigned pm = __ballot_sync(FULL, pend);
+        queue_push_if<FIELD>(WQ.ev, qn + __popc(pm & lt_mask), p, s0, pend);
+        qn += __popc(pm);
+        if (phase == PH_SELECT) {
+            const unsigned km = __ballot_sync(FULL, park);
+            const int slot = qsc + __popc(km & lt_mask);
+            queue_push_if<FIELD>(WQ.sc, slot, p, s0, park);
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.u32 [%0], %1;\n\t"
+                         "@q st.shared.v2.f64 [%2], {%3, %4};\n\t}"
+                         ::"r"(smem_u32(&WQ.sc_mech[0]) + (uint32_t)slot * 4u), "r"(mech),
+                         "r"(smem_u32(&WQ.sc_er[0]) + (uint32_t)slot * 16u), "d"(e_np), "d"(r_az), "r"((uint32_t)park) : "memory");
+            qsc += __popc(km);
+        }
+#else
         if (act && !pend && !park) retire<REPLAY, DEPOSIT, ML>(P, A, i, p, s0, acc, smesh);
         const unsigned pm = __ballot_sync(FULL, pend);
         if (pend) queue_push<FIELD>(WQ.ev, qn + __popc(pm & lt_mask), p, s0);
@@ -707,8 +882,9 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             }
             qsc += __popc(km);
         }
+#endif
         __syncwarp();
-    }
+        }
 
     if (DEPOSIT && A.smem_cells > 0) {
         __syncthreads();
@@ -720,10 +896,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     if (A.obs) obs_block_reduce_and_finish(acc, A.partials, A.ticket, A.obs);
 }
 
-template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML>
+template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML, bool LEAN = false>
 static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
-    auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT, ML>;
+    auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT, ML, LEAN>;
     // persistent grid: exactly the blocks that are resident at once (one wave), unless the
     // ensemble is too small to give every block a full tile.  The attribute / occupancy queries
     // are cached per kernel variant and device (they cost tens of microseconds per launch).
@@ -748,6 +924,14 @@ static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid
 template <class Stream, int FIELD>
 static cudaError_t launch_flight_t(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
+    if constexpr (!Stream::is_replay) {
+        // the lean instantiation (see flight_scatter_kernel) whenever its compile-time assumptions hold
+        const bool zon_ok = (FIELD != EMC_FIELD_CONSTANT && FIELD != EMC_FIELD_GROUPS) || ctx->dc.zonly;
+        if (EMC_LEAN_KERNEL && !ctx->no_lean && !ctx->exact_libm && !A.mesh && !(A.obs && !A.obs_before) &&
+            !ctx->dc.literal_scan && ctx->self_last && zon_ok)
+            return ctx->dc.n_layers > 1 ? launch_flight_k<Stream, FIELD, false, false, true, true>(ctx, A, grid, smem, st)
+                                        : launch_flight_k<Stream, FIELD, false, false, false, true>(ctx, A, grid, smem, st);
+    }
     // multi-layer devices: separate deposit kernel (checked by the caller)
     if (ctx->dc.n_layers > 1)
         return ctx->exact_libm ? launch_flight_k<Stream, FIELD, true, false, true>(ctx, A, grid, smem, st)
@@ -761,6 +945,7 @@ static cudaError_t launch_flight_t(const Ctx *ctx, const FlightArgs &A, int grid
 
 cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, cudaStream_t st)
 {
+    if (A.n >= ((int64_t)1 << 32) - 64) return cudaErrorInvalidValue;   // 32-bit particle index inside a launch (checked by the ABI)
     // one warp needs at least a few refills of work; small ensembles use fewer blocks
     const int64_t blocks_needed = (A.n + FLIGHT_THREADS - 1) / FLIGHT_THREADS;
     int grid = (int)(blocks_needed < (int64_t)ctx->max_grid ? blocks_needed : ctx->max_grid);
@@ -770,6 +955,15 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     const int64_t field_cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];
     A.field_ahead = EMC_FIELD_AHEAD && field_mode == EMC_FIELD_MESH_PACKED && field_cells >= 8192 && !ctx->no_field_ahead;
     if (A.field_ahead) smem += sizeof(FieldStage) * (FLIGHT_THREADS / 32);
+    {   // bulk-async refill: every state row 16-byte aligned (the copies are 256-B slices at multiples of 32 particles)
+        uintptr_t bits = (uintptr_t)A.valley;
+        for (int r = 0; r < 7; ++r) bits |= (uintptr_t)(&A.kx)[r];
+        // (not for the mesh-field modes: the tiles' 31 KB of shared memory come out of the L1 that the
+        // field gathers live on -- measured 0.745 ms with, 0.721 ms without on 1024 x 1 x 1024, profiles/ab_r2e)
+        const bool mesh_field = field_mode == EMC_FIELD_MESH || field_mode == EMC_FIELD_MESH_PACKED;
+        A.bulk = EMC_BULK_REFILL && (bits & 15) == 0 && !ctx->no_bulk_refill && !replay && !mesh_field;
+        if (A.bulk) smem += sizeof(RefillTile) * (FLIGHT_THREADS / 32);
+    }
     if (EMC_OBS_SMEM) {
         smem += sizeof(double) * 5 * FLIGHT_THREADS;
         // ObsAccShared packs the valley / fault counts into 16 bits per lane and launch
@@ -794,7 +988,13 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     case EMC_FIELD_MESH_PACKED: return launch_flight_t<STREAM, EMC_FIELD_MESH_PACKED>(ctx, A, grid, smem, st); \
     default: return cudaErrorInvalidValue;                                                       \
     }
+#ifdef EMC_PROBE_ONLY
+    // static-analysis builds (profiles/sass_static.py): only the configs[1] instantiation, compiled in seconds
+    if (replay || field_mode != EMC_FIELD_GROUPS || ctx->dc.n_layers > 1 || ctx->exact_libm || A.mesh) return cudaErrorInvalidValue;
+    return launch_flight_k<PhiloxStream, EMC_FIELD_GROUPS, false, false, false, EMC_LEAN_KERNEL != 0>(ctx, A, grid, smem, st);
+#else
     if (replay) { EMC_DISPATCH(ReplayStream) } else { EMC_DISPATCH(PhiloxStream) }
+#endif
 #undef EMC_DISPATCH
 }
 

@@ -38,6 +38,7 @@ struct FlightArgs {
     int32_t smem_cells;
     int32_t field_ahead;         // EMC_FIELD_MESH_PACKED: stage the next refill batch's field records (launch_flight decides)
     int32_t obs_before;          // emc_set_obs_phase: reduce the observables of the state as loaded
+    int32_t bulk;                // refill batches arrive by bulk async copies (launch_flight decides: aligned rows)
     const MechMeta *mech_layers; // multi-layer: device array of n_layers mechanism-metadata blocks
 };
 
@@ -51,6 +52,9 @@ struct Ctx {
     bool layer_tables[EMC_MAX_LAYERS] = {false, false, false, false};
     int obs_before = 0;           // emc_set_obs_phase
     bool no_field_ahead = false;  // EMC_FIELD_AHEAD=0 in the environment (tuning)
+    bool no_bulk_refill = false;  // EMC_BULK_REFILL=0 in the environment (tuning)
+    bool no_lean = false;         // EMC_LEAN=0 in the environment: always the general flight kernel (A/B, tests)
+    bool self_last = false;       // every uploaded table: last column = the one self-scattering mechanism, dE 0, same valley
     bool zonly_constant = false;  // dc.efield has Ex = Ey = +0
     bool zonly_groups = false;    // every field group has Ex = Ey = +0
     int batch_layer = 0;          // emc_select_layer: material of the single-function batches
