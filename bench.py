@@ -279,72 +279,121 @@ COUPLED_MESH = (1024, 1, 1024)          # BASELINE configs[3]: 1024 x 1024 Poiss
 COUPLED_PER_GPU = 12_500_000            # 1e8 particles over 8 GPUs
 
 
-def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=20, warmup=5):
-    """Metric (ii): ms per coupled MC+Poisson timestep = flight in the mesh field with the NGP
-    deposit fused in -> int64 charge all-reduce (NCCL, world > 1) -> rho -> red-black SOR to the
-    reference's tolerance (warm-started) -> field.  Median over `steps` timesteps, CUDA events."""
-    p = engine.params_from_reference_modules(num_carr=COUPLED_PER_GPU * world)
+def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=20, warmup=5, order=None,
+                  n_per_gpu=COUPLED_PER_GPU, label="weak"):
+    """Metric (ii): ms per coupled MC+Poisson timestep = flight in the mesh field -> NGP deposit -> int64
+    charge all-reduce over the ranks (NVLink peer-memory kernel / NCCL) -> rho -> Poisson solve (warm
+    start from the previous potential) -> field.  Median over `steps` timesteps, CUDA events, every
+    stage timed on every rank (min / median / max over the ranks are reported).
+
+    order: abi.SOR_RED_BLACK  = the reference's solver semantics: SOR until RMS(update) <= 1e-6 (poisson_.py:63,82)
+           abi.SOR_MULTIGRID  = the same tolerance tested on the TRUE residual, V(2,2) cycles (self-consistent)"""
+    order = abi.SOR_RED_BLACK if order is None else order
+    p = engine.params_from_reference_modules(num_carr=n_per_gpu * world)
     for a in range(3):
         p.seg[a] = COUPLED_MESH[a]
         p.dl[a] = p.tot_dim[a] / COUPLED_MESH[a]
     p.rho_background = -1e16 * p.dl[0] * p.dl[1] * p.dl[2] * 1e6          # init_.py:189-191
     ctx = engine.Context(p, device=local)
-    n = COUPLED_PER_GPU
+    n = n_per_gpu
     ens = engine.Ensemble(ctx, n, pid_offset=rank * n).init(SEED + 1)
-    cs = engine.CoupledStepper(ctx, ens, seed=SEED + 1, max_sweeps=200)
-    cs.prime(max_sweeps=50_000)                   # cold start solved to tolerance; the loop below is warm-started
-    prime_sweeps = cs.mesh.last_solve()[0]
+    mg = order == abi.SOR_MULTIGRID
+    cs = engine.CoupledStepper(ctx, ens, seed=SEED + 1, max_sweeps=30 if mg else 200, order=order)
+    # cold start: SOR to the reference's stopping rule (thousands of sweeps that stop ~1e6 sweeps short of
+    # the solution), or multigrid to a 1e-8 reduction of the true residual
+    m = cs.mesh
+    m.zero_counts()
+    m.deposit(ens)
+    m.allreduce()
+    m.to_rho()
+    r_cold0 = m.residual()[0]
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    if mg:
+        m.solve_mg(tol_residual=1e-8 * r_cold0, max_cycles=30, sync=False)
+    else:
+        m.solve_async(tol=cs.tol, max_sweeps=50_000, order=order)
+    c1.record()
+    torch.cuda.synchronize()
+    cold_ms = c0.elapsed_time(c1)
+    prime_sweeps = m.last_solve()[0]
+    r_cold1 = m.residual()[0]
+    m.field_packed()
     for _ in range(warmup):
         cs.step()
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    stage = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
-    sweeps = []
+    names = ("flight", "deposit", "allreduce", "to_rho", "solve", "field")
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(steps)]
     launches0 = ctx.launch_count()
     obs_hist = torch.zeros((steps, 11), dtype=torch.int64, device=ctx.device)
     ctx.set_obs_phase(True)       # per-step observables reduced while the next step loads the state
     barrier()
-    ev[0].record()
     for s in range(steps):
-        m = cs.mesh
+        e = ev[s]
         m.zero_counts()
+        e[0].record()
         ens.step(cs.n_steps, cs.seed, field_mode=cs.field_mode, mesh=m, observe=True, deposit=False,
                  obs_out=obs_hist[s])
+        e[1].record()
         m.deposit(ens)
-        stage[s][0].record()
+        e[2].record()
         m.allreduce()
-        stage[s][1].record()
+        e[3].record()
         m.to_rho()
-        m.solve_async(tol=cs.tol, max_sweeps=cs.max_sweeps, order=cs.order)
+        e[4].record()
+        m.solve_async(tol=cs.tol, max_sweeps=cs.max_sweeps, order=order)
+        e[5].record()
         m.field_packed()
-        stage[s][2].record()
+        e[6].record()
         cs.n_steps += 1
-        ev[s + 1].record()
     ens.observables()             # the last step's observables (stand-alone reduction)
     barrier()
     ctx.set_obs_phase(False)
     launches = ctx.launch_count() - launches0
-    sweeps.append(cs.mesh.last_solve()[0])
-    per = np.array([ev[s].elapsed_time(ev[s + 1]) for s in range(steps)])
-    flight = np.array([ev[s].elapsed_time(stage[s][0]) for s in range(steps)])
-    allred = np.array([stage[s][0].elapsed_time(stage[s][1]) for s in range(steps)])
-    solve = np.array([stage[s][1].elapsed_time(stage[s][2]) for s in range(steps)])
-    t = torch.tensor([np.median(per), np.median(flight), np.median(allred), np.median(solve)],
-                     dtype=torch.float64, device=ctx.device)
+    sweeps_last = m.last_solve()[0]
+    # a few more steps with the true residual of every solve recorded (outside the timed loop)
+    res_dev = torch.zeros((5, 2), dtype=torch.float64, device=ctx.device)
+    sw = []
+    for s in range(5):
+        cs.step()
+        m.residual(out=res_dev[s])
+        sw.append(m.last_solve()[0])
+    cs.check_solver()
+    residuals = [float(v) for v in res_dev[:, 0].cpu()]
+    per = np.array([ev[s][0].elapsed_time(ev[s][6]) for s in range(steps)])
+    stage = np.array([[ev[s][k].elapsed_time(ev[s][k + 1]) for k in range(len(names))] for s in range(steps)])
+    mine = torch.tensor([np.median(per)] + [float(v) for v in np.median(stage, axis=0)], dtype=torch.float64, device=ctx.device)
+    allr = torch.zeros((world, mine.numel()), dtype=torch.float64, device=ctx.device)
+    allr[rank] = mine
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(allr, op=dist.ReduceOp.SUM)
+    allr = allr.cpu().numpy()
     obs = engine._obs_from_raw(obs_hist[-1].cpu().numpy())
+    p2p, p2p_err = cs.mesh.p2p is not None, cs.mesh.p2p_error
     ctx.close()
-    t = [float(v) for v in t.cpu()]
-    return {"metric": "ms per coupled MC+Poisson timestep", "ms_per_timestep": t[0], "flight_deposit_ms": t[1],
-            "charge_allreduce_ms": t[2], "rho_sor_field_ms": t[3], "sor_sweeps_last_step": sweeps[-1],
+    del ens, cs, m
+    torch.cuda.empty_cache()
+    spread = {nme: {"min": float(allr[:, 1 + k].min()), "median": float(np.median(allr[:, 1 + k])), "max": float(allr[:, 1 + k].max())}
+              for k, nme in enumerate(names)}
+    return {"metric": "ms per coupled MC+Poisson timestep", "scaling": label,
+            "ms_per_timestep": float(allr[:, 0].max()), "ms_per_timestep_per_rank": [round(float(v), 4) for v in allr[:, 0]],
+            "stages_ms_over_ranks": spread,
+            "flight_deposit_ms": spread["flight"]["max"] + spread["deposit"]["max"],
+            "charge_allreduce_ms": spread["allreduce"]["max"],
+            "rho_sor_field_ms": spread["to_rho"]["max"] + spread["solve"]["max"] + spread["field"]["max"],
+            "solver": ("geometric multigrid V(2,2), true residual / |e| <= 1e-6 (the reference's tolerance, truthfully "
+                       "evaluated), warm start" if mg else
+                       "red-black SOR, RMS update <= 1e-6 (poisson_.py:63,82: the reference's stopping rule), warm start"),
+            "solver_iterations_last_step": sweeps_last, "solver_iterations_next_steps": sw,
+            "true_residual_rms_volts_next_steps": residuals,
+            "cold_start": {"ms": cold_ms, "iterations": prime_sweeps, "true_residual_before": r_cold0,
+                           "true_residual_after": r_cold1},
             "charge_allreduce": ("none (1 rank)" if world == 1 else
-                                 "emc_mesh_allreduce_p2p over NVLink symmetric memory" if cs.mesh.p2p is not None
-                                 else "NCCL all_reduce (%s)" % (cs.mesh.p2p_error or "EMC_P2P=0")),
-            "sor_sweeps_cold_start": prime_sweeps, "ms_per_timestep_mean": float(np.mean(per)),
-            "mesh": "x".join(str(v) for v in COUPLED_MESH), "particles_per_gpu": n, "n_gpus": world,
-            "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
-            "sor": "red-black, tol 1e-6 RMS update (poisson_.py:63), warm start from the previous potential",
+                                 "emc_mesh_allreduce_p2p over NVLink symmetric memory" if p2p
+                                 else "NCCL all_reduce (%s)" % (p2p_err or "EMC_P2P=0")),
+            "mesh": "x".join(str(v) for v in COUPLED_MESH), "particles_per_gpu": n, "global_particles": n * world,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
             "segments_last_step": obs["n_segments"]}
 
 
@@ -547,7 +596,15 @@ def run_ours(args):
     barrier()
     pcie = pcie_duplex_gbs(torch, ctx.device)      # all ranks at once: what the HOST sustains with N GPUs copying
     barrier()
-    coupled = coupled_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
+    coupled = coupled_mg = coupled_strong = None
+    if not args.no_coupled:
+        # configs[3] weak-scaled (1.25e7 particles per GPU: the named 1e8 at 8 GPUs) with the reference's
+        # solver semantics, the same with the multigrid solver (self-consistent field), and the named 1e8
+        # particles in total at ANY rank count (strong scaling)
+        coupled = coupled_bench(torch, dist, engine, abi, local, rank, world, barrier)
+        coupled_mg = coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, order=abi.SOR_MULTIGRID)
+        coupled_strong = coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, order=abi.SOR_MULTIGRID,
+                                       n_per_gpu=100_000_000 // world, label="strong (1e8 particles in total)", steps=10, warmup=3)
     by_config = other_configs_bench(torch, dist, engine, abi, local, rank, world, barrier) if not args.no_coupled else None
     if by_config is not None:
         by_config["configs[2] n+-n-n+ diode, 3 layers, 1e7 super-particles, Poisson every timestep"] = \
@@ -614,7 +671,7 @@ def run_ours(args):
                     "pcie_duplex_gbs_per_direction_per_gpu_all_ranks_copying": pcie_min,
                     "host_binding": binding},
             "gpu_launches": int(launches), "clocks": clk, "knobs": active_knobs(ctx),
-            "coupled": coupled, "by_config": by_config,
+            "coupled": coupled, "coupled_multigrid": coupled_mg, "coupled_strong_1e8": coupled_strong, "by_config": by_config,
         }
         print(json.dumps(line))
     ctx.close()

@@ -69,7 +69,10 @@ enum { EMC_DEPOSIT_NGP = 0,      /* poisson_.py:30-38 (inclusive box test, face 
 
 /* Poisson sweep orders */
 enum { EMC_SOR_LEXICOGRAPHIC = 0, /* poisson_.py:74 order, executed as hyperplane wavefronts: bit-identical iterates */
-       EMC_SOR_RED_BLACK = 1 };   /* same fixed point, parallel colouring (the fast path) */
+       EMC_SOR_RED_BLACK = 1,     /* same fixed point, parallel colouring */
+       EMC_SOR_MULTIGRID = 2 };   /* same equation and fixed point, geometric multigrid V(2,2) cycles (emc_poisson_mg):
+                                     `tol` is tested on the TRUE residual / |e| (= the Gauss-Seidel update the reference's
+                                     rule looks at, poisson_.py:76,82), max_sweeps counts V-cycles, omega0 is unused */
 
 /* field sources of the flight kernel */
 enum { EMC_FIELD_CONSTANT = 0,   /* dev.elec_field, main_.py:367,373,388 */
@@ -344,6 +347,23 @@ int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad, double om
  * (EMC_ERR_DIVERGED) of ANY solve since the previous emc_poisson_last (sticky device flag: solves that
  * were only enqueued are not lost); synchronises the stream */
 int emc_poisson_last(EmcCtx *ctx, int32_t *sweeps_out, double *err_out, void *stream);
+/* Geometric multigrid on the SAME discrete problem (poisson_.py:55-60,76: 7-point stencil, zero halo,
+ * z-min face at its Dirichlet value as found in u_pad): cell-centred coarsening along the strongly
+ * coupled axes (never an odd or < 4 cell axis, e.g. the reference's ny = 1), red-black Gauss-Seidel
+ * V(nu1, nu2) cycles, residual averaging / linear prolongation, one cooperative launch for the whole
+ * solve.  Stops when the RMS of the true residual  dl0^2 rho/eps - A u  (volts) <= tol_residual or after
+ * max_cycles.  cycles_out / res_out / res_hist (HOST, may be NULL; res_hist: max_cycles doubles, RMS
+ * residual after every cycle): if all three are NULL the solve is only enqueued (emc_poisson_last then
+ * reports cycles and RMS residual).  EMC_ERR_UNSUPPORTED for a mesh that cannot be coarsened at all. */
+int emc_poisson_mg(EmcCtx *ctx, double *u_pad, const double *rho_pad, double tol_residual,
+                   int32_t max_cycles, int32_t nu1, int32_t nu2, int32_t *cycles_out, double *res_out,
+                   double *res_hist, void *stream);
+/* RMS and maximum of the TRUE residual  dl0^2 rho/eps - [neighbour sum - 2(1 + xy + xz) u]  (volts) of any
+ * potential over the interior cells -- what the reference's stopping rule (RMS of the update) does not
+ * bound.  rms_out / max_out: HOST (synchronises the stream if either is given); out_dev: DEVICE pointer
+ * to two doubles (rms, max) or NULL, written in stream order. */
+int emc_poisson_residual(EmcCtx *ctx, const double *u_pad, const double *rho_pad, double *rms_out,
+                         double *max_out, double *out_dev, void *stream);
 /* E = -central difference on interior cells (poisson_.py:88-96); padded outputs, V/m */
 int emc_field(EmcCtx *ctx, const double *u_pad, double *ex, double *ey, double *ez, void *stream);
 /* The same field as one record (ex, ey, ez, 0) of four doubles per padded cell, already in the

@@ -18,7 +18,7 @@ ABI_VERSION = 1
 # enums of include/emc.h
 FIELD_CONSTANT, FIELD_GROUPS, FIELD_MESH, FIELD_MESH_PACKED = 0, 1, 2, 3
 DEPOSIT_NGP, DEPOSIT_CIC = 0, 1
-SOR_LEXICOGRAPHIC, SOR_RED_BLACK = 0, 1
+SOR_LEXICOGRAPHIC, SOR_RED_BLACK, SOR_MULTIGRID = 0, 1, 2
 ERR_INVALID, ERR_CUDA, ERR_NO_TABLES, ERR_DIVERGED, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 FAULT_NAMES = ["nan", "zero_energy", "no_mechanism", "domain", "negative_energy", "zero_k", "stream", "outside"]
 
@@ -105,6 +105,8 @@ SIGNATURES = {
     "emc_mesh_to_rho_interior": (C.c_int, [_vp, _lp, _i32, _dp, _vp]),
     "emc_poisson_sor": (C.c_int, [_vp, _dp, _dp, _f64, _f64, _i32, _i32, C.POINTER(_i32),
                                   C.POINTER(_f64), _dp, _vp]),
+    "emc_poisson_mg": (C.c_int, [_vp, _dp, _dp, _f64, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_f64), _dp, _vp]),
+    "emc_poisson_residual": (C.c_int, [_vp, _dp, _dp, C.POINTER(_f64), C.POINTER(_f64), _dp, _vp]),
     "emc_mesh_allreduce_p2p": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp]),
     "emc_field_packed": (C.c_int, [_vp, _dp, _dp, _vp]),
     "emc_field_packed_interior": (C.c_int, [_vp, _dp, _dp, _vp]),

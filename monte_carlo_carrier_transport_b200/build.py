@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libemc_b200.so")
-SOURCES = ["emc_abi.cu", "emc_flight.cu", "emc_mesh.cu"]
+SOURCES = ["emc_abi.cu", "emc_flight.cu", "emc_mesh.cu", "emc_multigrid.cu"]
 HEADERS = ["emc_device.cuh", "emc_host.h", os.path.join("..", "..", "include", "emc.h")]
 
 NVCC_FLAGS = [

@@ -229,6 +229,7 @@ extern "C" void emc_destroy(EmcCtx *ctx)
     if (c->d_sor_flags) cudaFree(c->d_sor_flags);
     if (c->d_sor_partials) cudaFree(c->d_sor_partials);
     if (c->d_err_hist) cudaFree(c->d_err_hist);
+    mg_release(c);
     delete ctx;
 }
 
@@ -767,6 +768,24 @@ extern "C" int emc_poisson_sor(EmcCtx *ctx, double *u_pad, const double *rho_pad
     if (!u_pad || !rho_pad) return fail(c, EMC_ERR_INVALID, "emc_poisson_sor: null");
     return run_poisson_sor(c, u_pad, rho_pad, omega0, tol, max_sweeps, order, sweeps_out, err_out, err_hist,
                            (cudaStream_t)stream);
+}
+
+extern "C" int emc_poisson_mg(EmcCtx *ctx, double *u_pad, const double *rho_pad, double tol_residual, int32_t max_cycles,
+                              int32_t nu1, int32_t nu2, int32_t *cycles_out, double *res_out, double *res_hist,
+                              void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!u_pad || !rho_pad) return fail(c, EMC_ERR_INVALID, "emc_poisson_mg: null");
+    return run_poisson_mg(c, u_pad, rho_pad, tol_residual, max_cycles, nu1, nu2, cycles_out, res_out, res_hist,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int emc_poisson_residual(EmcCtx *ctx, const double *u_pad, const double *rho_pad, double *rms_out,
+                                    double *max_out, double *out_dev, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!u_pad || !rho_pad || (!rms_out && !max_out && !out_dev)) return fail(c, EMC_ERR_INVALID, "emc_poisson_residual: null");
+    return run_poisson_residual(c, u_pad, rho_pad, rms_out, max_out, out_dev, (cudaStream_t)stream);
 }
 
 extern "C" int emc_mesh_allreduce_p2p(EmcCtx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs,

@@ -77,6 +77,7 @@ struct Ctx {
     int err_hist_cap = 0;
     double *d_sor_partials = nullptr;
     int32_t *d_sor_flags = nullptr;
+    void *mg = nullptr;           // multigrid buffers (emc_multigrid.cu), created on first use
     int64_t launches = 0;
     std::string last_error;
 };
@@ -124,5 +125,12 @@ cudaError_t launch_mesh_allreduce_p2p(Ctx *ctx, const int64_t *const *in_ptrs, i
                                       int rank, int64_t n_cells, cudaStream_t st);
 cudaError_t launch_field_packed(Ctx *ctx, const double *u_pad, double *e4, cudaStream_t st, bool interior_only = false);
 int poisson_last(Ctx *ctx, int32_t *sweeps_out, double *err_out, cudaStream_t st);
+
+// emc_multigrid.cu
+int run_poisson_mg(Ctx *ctx, double *u_pad, const double *rho_pad, double tol_residual, int max_cycles, int nu1, int nu2,
+                   int32_t *cycles_out, double *res_out, double *res_hist, cudaStream_t st);
+int run_poisson_residual(Ctx *ctx, const double *u_pad, const double *rho_pad, double *rms_out, double *max_out,
+                         double *out_dev, cudaStream_t st);
+void mg_release(Ctx *ctx);
 
 }  // namespace emc

@@ -677,6 +677,21 @@ int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega
             void *args[] = {(void *)&S, (void *)&u_pad, (void *)&rho_pad, (void *)&eh, (void *)&sc, (void *)&fl,
                             (void *)&pt};
             e = cudaLaunchCooperativeKernel((void *)sor_rb_kernel, dim3(grid), dim3(256), args, 0, st);
+        } else if (order == EMC_SOR_MULTIGRID) {
+            // tol keeps the meaning of poisson_.py:63,82 -- the RMS of one Gauss-Seidel UPDATE -- but is
+            // evaluated on the true residual: an update is residual / |e| (poisson_.py:76)
+            ctx->launches--;
+            const double ae = std::fabs(S.e);
+            int32_t cyc = 0;
+            double res = 0.0;
+            const bool want = sweeps_out || err_out || err_hist;
+            const int r = run_poisson_mg(ctx, u_pad, rho_pad, tol * ae, max_sweeps, 2, 2, want ? &cyc : nullptr,
+                                         want ? &res : nullptr, err_hist, st);
+            if (r != EMC_OK) return r;
+            if (sweeps_out) *sweeps_out = cyc;
+            if (err_out) *err_out = res / ae;
+            if (err_hist) for (int k = 0; k < cyc; ++k) err_hist[k] /= ae;
+            return EMC_OK;
         } else {
             ctx->last_error = "unknown SOR order";
             return EMC_ERR_INVALID;

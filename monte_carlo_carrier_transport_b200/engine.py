@@ -605,6 +605,38 @@ class Mesh:
         c.check(c.lib.emc_poisson_sor(c.h, self.u_pad.data_ptr(), self.rho_pad.data_ptr(), omega0, tol,
                                       max_sweeps, order, None, None, None, c.stream))
 
+    def solve_mg(self, tol_residual: float = 1e-8, max_cycles: int = 30, nu1: int = 2, nu2: int = 2,
+                 history: bool = False, sync: bool = True):
+        """Geometric multigrid on the same discrete problem (``emc_poisson_mg``): V(nu1, nu2) cycles
+        until the RMS of the TRUE residual (volts) <= ``tol_residual``.  Returns (cycles, rms_residual
+        [, per-cycle history]); ``sync=False`` only enqueues the solve (``last_solve`` reports)."""
+        c = self.ctx
+        if not sync:
+            c.check(c.lib.emc_poisson_mg(c.h, self.u_pad.data_ptr(), self.rho_pad.data_ptr(), tol_residual, max_cycles,
+                                         nu1, nu2, None, None, None, c.stream))
+            return None
+        n, res = C.c_int32(0), C.c_double(0.0)
+        hist = np.zeros(max_cycles, dtype=np.float64) if history else None
+        c.check(c.lib.emc_poisson_mg(c.h, self.u_pad.data_ptr(), self.rho_pad.data_ptr(), tol_residual, max_cycles,
+                                     nu1, nu2, C.byref(n), C.byref(res), hist.ctypes.data if history else None, c.stream))
+        if history:
+            return n.value, res.value, hist[:n.value].copy()
+        return n.value, res.value
+
+    def residual(self, out=None):
+        """(RMS, max) of the true residual ``dl0^2 rho/eps - A u`` (volts) of the current potential
+        (``emc_poisson_residual``): what the reference's stopping rule does not bound.  With ``out`` (a
+        2-element float64 device tensor) the numbers are written there in stream order, no sync."""
+        c = self.ctx
+        if out is not None:
+            c.check(c.lib.emc_poisson_residual(c.h, self.u_pad.data_ptr(), self.rho_pad.data_ptr(), None, None,
+                                               out.data_ptr(), c.stream))
+            return None
+        rms, mx = C.c_double(0.0), C.c_double(0.0)
+        c.check(c.lib.emc_poisson_residual(c.h, self.u_pad.data_ptr(), self.rho_pad.data_ptr(), C.byref(rms),
+                                           C.byref(mx), None, c.stream))
+        return rms.value, mx.value
+
     def last_solve(self):
         """(sweeps, err) of the most recent solve; raises EmcError(ERR_DIVERGED) like poisson_.py:78-80."""
         c = self.ctx
