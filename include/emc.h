@@ -310,6 +310,13 @@ int emc_soa_to_aos(EmcCtx *ctx, const double *kx, const double *ky, const double
  * independent of the order particles are visited in (and of the number of ranks). */
 int emc_deposit(EmcCtx *ctx, const double *x, const double *y, const double *z, int64_t n,
                 int64_t *mesh, int32_t scheme, void *stream);
+/* NGP on meshes too large for one block's shared memory (> 24576 cells): which kernel emc_deposit uses.
+ *   1 direct: one 64-bit L2 reduction per particle straight into the mesh;
+ *   2 tiled:  the cell ids are counting-sorted by mesh tile (4096 cells), every tile is accumulated in a
+ *             shared-memory partial mesh and committed with one 64-bit add per touched cell;
+ *   0 auto (default): the measured winner (profiles/r2_deposit_ab.txt).
+ * Both are integer and give bit-identical meshes. */
+int emc_set_deposit_mode(EmcCtx *ctx, int32_t mode);
 /* Multi-GPU: sum the charge meshes of `world` ranks over NVLink peer memory in ONE kernel
  * (reduce-scatter + all-gather): this rank sums its 1/world slice over all ranks' input meshes
  * with peer loads and stores the totals into every rank's output mesh.  in_ptrs / out_ptrs:

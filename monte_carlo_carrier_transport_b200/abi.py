@@ -101,6 +101,7 @@ SIGNATURES = {
     "emc_aos_to_soa": (C.c_int, [_vp, _dp, _i64] + [_dp] * 6 + [_vp]),
     "emc_soa_to_aos": (C.c_int, [_vp] + [_dp] * 6 + [_i64, _dp, _vp]),
     "emc_deposit": (C.c_int, [_vp, _dp, _dp, _dp, _i64, _lp, _i32, _vp]),
+    "emc_set_deposit_mode": (C.c_int, [_vp, _i32]),
     "emc_mesh_to_rho": (C.c_int, [_vp, _lp, _i32, _dp, _vp]),
     "emc_mesh_to_rho_interior": (C.c_int, [_vp, _lp, _i32, _dp, _vp]),
     "emc_poisson_sor": (C.c_int, [_vp, _dp, _dp, _f64, _f64, _i32, _i32, C.POINTER(_i32),

@@ -230,6 +230,7 @@ extern "C" void emc_destroy(EmcCtx *ctx)
     if (c->d_sor_partials) cudaFree(c->d_sor_partials);
     if (c->d_err_hist) cudaFree(c->d_err_hist);
     mg_release(c);
+    if (c->d_dep_scratch) cudaFree(c->d_dep_scratch);
     delete ctx;
 }
 
@@ -732,6 +733,14 @@ extern "C" int emc_deposit(EmcCtx *ctx, const double *x, const double *y, const 
     if (n == 0) return EMC_OK;
     cudaError_t e = launch_deposit(c, x, y, z, n, mesh, scheme, (cudaStream_t)stream);
     return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "deposit launch");
+}
+
+extern "C" int emc_set_deposit_mode(EmcCtx *ctx, int32_t mode)
+{
+    CTX_OR_FAIL(ctx);
+    if (mode < 0 || mode > 2) return fail(c, EMC_ERR_INVALID, "emc_set_deposit_mode: 0 auto, 1 direct, 2 tiled");
+    c->deposit_mode = mode;
+    return EMC_OK;
 }
 
 extern "C" int emc_mesh_to_rho(EmcCtx *ctx, const int64_t *mesh, int32_t scheme, double *rho_pad, void *stream)

@@ -78,6 +78,9 @@ struct Ctx {
     double *d_sor_partials = nullptr;
     int32_t *d_sor_flags = nullptr;
     void *mg = nullptr;           // multigrid buffers (emc_multigrid.cu), created on first use
+    int deposit_mode = 0;         // emc_set_deposit_mode: 0 auto, 1 direct atomics, 2 tiled (large NGP meshes)
+    void *d_dep_scratch = nullptr;   // tiled deposit: cell ids, sorted cell ids, tile histogram
+    size_t dep_scratch_bytes = 0;
     int64_t launches = 0;
     std::string last_error;
 };

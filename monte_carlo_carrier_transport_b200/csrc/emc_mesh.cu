@@ -116,10 +116,175 @@ deposit_cic_kernel(const __grid_constant__ DevConst P, const double *__restrict_
     }
 }
 
-// NGP on a mesh that does not fit one block's shared memory
+// ------------------------------------------------------------------------------------------
+// NGP on a mesh that does not fit one block's shared memory: the tiled variant of the north-star
+// sketch ("sort by cell, per-tile partial meshes in shared memory, 64-bit commit").
+//
+// The mesh is cut into tiles of DEP_TILE_CELLS consecutive cells (16 KB of 32-bit counts).  Three
+// passes, all integer, hence bit-identical to the direct kernel and order independent:
+//   1. cells:   per particle the cell of its FIRST hit -> cell_of[n] (4 B) and a per-tile histogram
+//               (shared-memory partials, one global add per block and tile); the additional cells of
+//               a particle ON a face (poisson_.py:31 inclusive test; ~1e-9 of random positions) go
+//               straight to the mesh;
+//   2. scatter: after an exclusive scan of the histogram every block reserves, per tile, a range of
+//               the tile's segment (one global atomic per block and tile) and writes its cell ids there:
+//               a counting sort of the 4-byte cell ids by tile -- the positions are not moved;
+//   3. tiles:   one block per tile portion accumulates its cell ids into a shared-memory partial mesh
+//               and commits every touched cell with ONE 64-bit add.
+// Traffic 24 + 4 + 4 + 4 + 4 = 40 B per particle against 24 B + one L2 atomic per particle for the
+// direct kernel.  Measured (profiles/r2_deposit_ab.txt): see launch_deposit.
+// ------------------------------------------------------------------------------------------
+constexpr int DEP_TILE_CELLS = 4096;
+constexpr int DEP_MAX_TILES = 4096;          // shared-memory histogram of the first two passes (16 KB)
+
+__global__ void __launch_bounds__(256)
+deposit_tiled_cells_kernel(const __grid_constant__ DevConst P, const double *__restrict__ x, const double *__restrict__ y,
+                           const double *__restrict__ z, int64_t n, unsigned long long *mesh, int32_t *cell_of,
+                           unsigned int *tile_count, int n_tiles)
+{
+    extern __shared__ unsigned int hist[];
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) hist[t] = 0u;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int hx[3], hy[3], hz[3];
+        const int nx = axis_hits(x[i], P.seg[0], P.dl[0], P.inv_dl[0], hx);
+        const int ny = axis_hits(y[i], P.seg[1], P.dl[1], P.inv_dl[1], hy);
+        const int nz = axis_hits(z[i], P.seg[2], P.dl[2], P.inv_dl[2], hz);
+        int32_t first = -1;
+        for (int a = 0; a < nx; ++a)
+            for (int b = 0; b < ny; ++b)
+                for (int c = 0; c < nz; ++c) {
+                    const int64_t cell = ((int64_t)hx[a] * P.seg[1] + hy[b]) * P.seg[2] + hz[c];
+                    if (first < 0) first = (int32_t)cell;
+                    else atomicAdd(mesh + cell, 1ull);            // a face / edge / corner hit: rare
+                }
+        cell_of[i] = first;                                       // -1: outside the mesh (counts nowhere)
+        if (first >= 0) atomicAdd(&hist[first / DEP_TILE_CELLS], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x)
+        if (hist[t]) atomicAdd(&tile_count[t], hist[t]);
+}
+
+// exclusive scan of the tile histogram (one block); cursor[t] = start[t] for the scatter pass
+__global__ void deposit_tiled_scan_kernel(const unsigned int *tile_count, unsigned int *tile_start, unsigned int *cursor,
+                                          int n_tiles)
+{
+    __shared__ unsigned int part[1024];
+    const int per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const int lo = threadIdx.x * per, hi = min(n_tiles, lo + per);
+    unsigned int s = 0;
+    for (int t = lo; t < hi; ++t) s += tile_count[t];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int t = 0; t < (int)blockDim.x; ++t) { const unsigned int v = part[t]; part[t] = run; run += v; }
+    }
+    __syncthreads();
+    unsigned int run = part[threadIdx.x];
+    for (int t = lo; t < hi; ++t) { tile_start[t] = run; cursor[t] = run; run += tile_count[t]; }
+    if (hi == n_tiles && lo < hi) tile_start[n_tiles] = run;
+    if (n_tiles == 0 && threadIdx.x == 0) tile_start[0] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+deposit_tiled_scatter_kernel(const int32_t *__restrict__ cell_of, int64_t n, unsigned int *cursor, int32_t *sorted,
+                             int n_tiles, int64_t chunk)
+{
+    extern __shared__ unsigned int sh[];
+    unsigned int *hist = sh, *base = sh + n_tiles;
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(n, lo + chunk);
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) hist[t] = 0u;
+    __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int32_t c = cell_of[i];
+        if (c >= 0) atomicAdd(&hist[c / DEP_TILE_CELLS], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+        base[t] = hist[t] ? atomicAdd(&cursor[t], hist[t]) : 0u;   // this block's range of tile t
+        hist[t] = 0u;
+    }
+    __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int32_t c = cell_of[i];
+        if (c >= 0) {
+            const int t = c / DEP_TILE_CELLS;
+            sorted[base[t] + atomicAdd(&hist[t], 1u)] = c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+deposit_tiled_tiles_kernel(const int32_t *__restrict__ sorted, const unsigned int *__restrict__ tile_start,
+                           unsigned long long *mesh, int n_tiles, int parts, int64_t cells)
+{
+    __shared__ unsigned int cnt[DEP_TILE_CELLS];
+    const int tile = blockIdx.x / parts, part = blockIdx.x % parts;
+    for (int t = threadIdx.x; t < DEP_TILE_CELLS; t += blockDim.x) cnt[t] = 0u;
+    __syncthreads();
+    const unsigned int a = tile_start[tile], b = tile_start[tile + 1];
+    const unsigned int len = b - a, per = (len + parts - 1) / parts;
+    const unsigned int lo = a + part * per, hi = min(b, lo + per);
+    const int32_t c0 = tile * DEP_TILE_CELLS;
+    for (unsigned int e = lo + threadIdx.x; e < hi; e += blockDim.x) atomicAdd(&cnt[sorted[e] - c0], 1u);
+    __syncthreads();
+    for (int t = threadIdx.x; t < DEP_TILE_CELLS; t += blockDim.x) {
+        const unsigned int v = cnt[t];
+        if (v && (int64_t)c0 + t < cells) atomicAdd(mesh + c0 + t, (unsigned long long)v);
+    }
+}
+
+static cudaError_t launch_deposit_tiled(Ctx *ctx, const double *x, const double *y, const double *z, int64_t n,
+                                        unsigned long long *m, int64_t cells, cudaStream_t st)
+{
+    const int n_tiles = (int)((cells + DEP_TILE_CELLS - 1) / DEP_TILE_CELLS);
+    cudaError_t e;
+    // scratch: cell_of[n], sorted[n] (int32), tile_count / tile_start / cursor
+    const size_t need = sizeof(int32_t) * 2 * (size_t)n + sizeof(unsigned int) * (3 * (size_t)n_tiles + 4);
+    if (ctx->dep_scratch_bytes < need) {
+        if (ctx->d_dep_scratch) cudaFree(ctx->d_dep_scratch);
+        ctx->d_dep_scratch = nullptr;
+        ctx->dep_scratch_bytes = 0;
+        if ((e = cudaMalloc(&ctx->d_dep_scratch, need)) != cudaSuccess) return e;
+        ctx->dep_scratch_bytes = need;
+    }
+    int32_t *cell_of = reinterpret_cast<int32_t *>(ctx->d_dep_scratch);
+    int32_t *sorted = cell_of + n;
+    unsigned int *tile_count = reinterpret_cast<unsigned int *>(sorted + n);
+    unsigned int *tile_start = tile_count + n_tiles, *cursor = tile_start + n_tiles + 1;
+    if ((e = cudaMemsetAsync(tile_count, 0, sizeof(unsigned int) * (size_t)n_tiles, st)) != cudaSuccess) return e;
+    int grid = (int)((n + 255) / 256 < (int64_t)ctx->sm_count * 8 ? (n + 255) / 256 : (int64_t)ctx->sm_count * 8);
+    if (grid < 1) grid = 1;
+    ctx->launches += 4;
+    deposit_tiled_cells_kernel<<<grid, 256, sizeof(unsigned int) * (size_t)n_tiles, st>>>(ctx->dc, x, y, z, n, m, cell_of,
+                                                                                        tile_count, n_tiles);
+    deposit_tiled_scan_kernel<<<1, 1024, 0, st>>>(tile_count, tile_start, cursor, n_tiles);
+    const int64_t chunk = (n + grid - 1) / grid;
+    deposit_tiled_scatter_kernel<<<grid, 256, sizeof(unsigned int) * 2 * (size_t)n_tiles, st>>>(cell_of, n, cursor, sorted,
+                                                                                            n_tiles, chunk);
+    // enough blocks per tile to fill the machine
+    int parts = (ctx->sm_count * 4 + n_tiles - 1) / n_tiles;
+    if (parts < 1) parts = 1;
+    deposit_tiled_tiles_kernel<<<n_tiles * parts, 256, 0, st>>>(sorted, tile_start, m, n_tiles, parts, cells);
+    return cudaGetLastError();
+}
+
+// NGP on a mesh that does not fit one block's shared memory.  A/B on B200, 1024 x 1 x 1024 mesh
+// (profiles/r2_deposit_ab.txt): the direct kernel -- one 64-bit L2 reduction per particle -- against the
+// tiled pipeline above; emc_set_deposit_mode picks (0 = auto: the measured winner, 1 = direct, 2 = tiled).
 static cudaError_t launch_deposit_large(Ctx *ctx, const double *x, const double *y, const double *z, int64_t n,
                                         unsigned long long *m, int64_t cells, int grid, cudaStream_t st)
 {
+    const int n_tiles = (int)((cells + DEP_TILE_CELLS - 1) / DEP_TILE_CELLS);
+    const bool tiled_ok = n_tiles <= DEP_MAX_TILES && n < ((int64_t)1 << 31);
+    const bool tiled = ctx->deposit_mode == 2 && tiled_ok;
+    if (tiled) {
+        ctx->launches--;
+        return launch_deposit_tiled(ctx, x, y, z, n, m, cells, st);
+    }
     deposit_ngp_kernel<false><<<grid, 256, 0, st>>>(ctx->dc, x, y, z, n, m, (int)cells);
     return cudaGetLastError();
 }

@@ -230,6 +230,11 @@ class Context:
         self.check(self.lib.emc_set_obs_phase(self.h, int(bool(before_step))))
         self.obs_before = bool(before_step)
 
+    def set_deposit_mode(self, mode: int) -> None:
+        """NGP kernel for meshes beyond one block's shared memory: 0 auto, 1 direct atomics, 2 tiled
+        counting sort + shared-memory partial meshes (``emc_set_deposit_mode``); identical results."""
+        self.check(self.lib.emc_set_deposit_mode(self.h, int(mode)))
+
     def set_exact_libm(self, on: bool) -> None:
         """``True``: compose acos / asin / atan exactly like scatter_.py:1061-1062 and the samplers
         (:811-872) instead of their algebraic equivalents (``emc_set_exact_libm``)."""

@@ -585,11 +585,14 @@ def test_deposit_shared_memory_windows(torch_mod, seg):
         coords[:, 3:] = pos
         ens = engine.Ensemble(c, n).load(coords, np.zeros(n, np.int32), np.ones(n))
         for scheme, ofn in ((abi.DEPOSIT_NGP, orc.deposit_ngp), (abi.DEPOSIT_CIC, orc.deposit_cic)):
-            mesh = engine.Mesh(c, scheme)
-            for rep in range(2):                                      # ADDS to the mesh: twice = doubled
-                mesh.deposit(ens)
             want = ofn(pos[:, 0], pos[:, 1], pos[:, 2], np.array(seg), dl)
-            assert np.array_equal(mesh.counts.cpu().numpy(), 2 * want), scheme
+            for mode in (1, 2):                                       # direct atomics / tiled counting sort
+                c.set_deposit_mode(mode)
+                mesh = engine.Mesh(c, scheme)
+                for rep in range(2):                                  # ADDS to the mesh: twice = doubled
+                    mesh.deposit(ens)
+                assert np.array_equal(mesh.counts.cpu().numpy(), 2 * want), (scheme, mode)
+        c.set_deposit_mode(0)
     finally:
         c.close()
 
