@@ -319,7 +319,7 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
     cold_ms = c0.elapsed_time(c1)
     prime_sweeps = m.last_solve()[0]
     r_cold1 = m.residual()[0]
-    m.field_packed()
+    cs.update_field()
     for _ in range(warmup):
         cs.step()
     torch.cuda.synchronize()
@@ -344,7 +344,7 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
         e[4].record()
         m.solve_async(tol=cs.tol, max_sweeps=cs.max_sweeps, order=order)
         e[5].record()
-        m.field_packed()
+        cs.update_field()
         e[6].record()
         cs.n_steps += 1
     ens.observables()             # the last step's observables (stand-alone reduction)

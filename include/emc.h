@@ -78,8 +78,11 @@ enum { EMC_SOR_LEXICOGRAPHIC = 0, /* poisson_.py:74 order, executed as hyperplan
 enum { EMC_FIELD_CONSTANT = 0,   /* dev.elec_field, main_.py:367,373,388 */
        EMC_FIELD_GROUPS = 1,     /* particle i uses field_groups[(pid_offset+i)/group_size] (velocity-field sweeps) */
        EMC_FIELD_MESH = 2,       /* nearest-cell gather from the Poisson field (poisson_.py:88-96), V/m */
-       EMC_FIELD_MESH_PACKED = 3 }; /* same field, one 32-byte record per cell written by emc_field_packed:
+       EMC_FIELD_MESH_PACKED = 3,   /* same field, one 32-byte record per cell written by emc_field_packed:
                                     `ex` points to it, ey = ez = NULL */
+       EMC_FIELD_MESH_XZ = 4 };  /* ny = 1 meshes: one 16-byte (ex, ez) record per INTERIOR cell, unpadded (nx, nz),
+                                    written by emc_field_xz (ey is identically -0 there, poisson_.py:95 between two
+                                    halo zeros): `ex` points to it, ey = ez = NULL.  Identical trajectories. */
 
 /* Physical / numerical parameters: a snapshot of init_.Parameters, init_.GaAs and
  * init_.Device (init_.py:58-157). */
@@ -378,6 +381,9 @@ int emc_field(EmcCtx *ctx, const double *u_pad, double *ex, double *ey, double *
  * gather of EMC_FIELD_MESH applies): two 128-bit loads per flight segment instead of three
  * scattered 64-bit ones.  e4: device, 4 * (nx+2)(ny+2)(nz+2) doubles, 32-byte aligned. */
 int emc_field_packed(EmcCtx *ctx, const double *u_pad, double *e4, void *stream);
+/* ny = 1 meshes: the field as (ex, ez) in V/cm per interior cell, e2: device, 2 * nx * nz doubles, 16-byte
+ * aligned (EMC_FIELD_MESH_XZ).  Half the gathered bytes of emc_field_packed and no halo records. */
+int emc_field_xz(EmcCtx *ctx, const double *u_pad, double *e2, void *stream);
 /* interior records only (the halo records of e4 are already zero: any buffer a previous
  * emc_field_packed filled) */
 int emc_field_packed_interior(EmcCtx *ctx, const double *u_pad, double *e4, void *stream);

@@ -16,7 +16,7 @@ EMC_MAX_LAYERS = 4
 ABI_VERSION = 1
 
 # enums of include/emc.h
-FIELD_CONSTANT, FIELD_GROUPS, FIELD_MESH, FIELD_MESH_PACKED = 0, 1, 2, 3
+FIELD_CONSTANT, FIELD_GROUPS, FIELD_MESH, FIELD_MESH_PACKED, FIELD_MESH_XZ = 0, 1, 2, 3, 4
 DEPOSIT_NGP, DEPOSIT_CIC = 0, 1
 SOR_LEXICOGRAPHIC, SOR_RED_BLACK, SOR_MULTIGRID = 0, 1, 2
 ERR_INVALID, ERR_CUDA, ERR_NO_TABLES, ERR_DIVERGED, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
@@ -111,6 +111,7 @@ SIGNATURES = {
     "emc_mesh_allreduce_p2p": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp]),
     "emc_field_packed": (C.c_int, [_vp, _dp, _dp, _vp]),
     "emc_field_packed_interior": (C.c_int, [_vp, _dp, _dp, _vp]),
+    "emc_field_xz": (C.c_int, [_vp, _dp, _dp, _vp]),
     "emc_poisson_last": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_f64), _vp]),
     "emc_field": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _vp]),
 }

@@ -521,7 +521,9 @@ static int flight_common(Ctx *c, FlightArgs &A, bool replay, int32_t field_mode,
         return fail(c, EMC_ERR_INVALID, "EMC_FIELD_GROUPS needs emc_set_field_groups");
     if (field_mode == EMC_FIELD_MESH_PACKED && (!ex || ((uintptr_t)ex & 31) != 0))
         return fail(c, EMC_ERR_INVALID, "EMC_FIELD_MESH_PACKED needs a 32-byte aligned packed field in ex");
-    if (field_mode < 0 || field_mode > EMC_FIELD_MESH_PACKED) return fail(c, EMC_ERR_INVALID, "unknown field_mode");
+    if (field_mode == EMC_FIELD_MESH_XZ && (!ex || ((uintptr_t)ex & 15) != 0 || c->dc.seg[1] != 1))
+        return fail(c, EMC_ERR_INVALID, "EMC_FIELD_MESH_XZ needs ny = 1 and a 16-byte aligned (ex, ez) record array in ex");
+    if (field_mode < 0 || field_mode > EMC_FIELD_MESH_XZ) return fail(c, EMC_ERR_INVALID, "unknown field_mode");
     if (A.n >= ((int64_t)1 << 32) - 64)
         return fail(c, EMC_ERR_UNSUPPORTED, "at most 2^32 - 65 particles per call: slice the ensemble (pid_offset keeps the random streams global)");
     if (c->dc.n_layers > 1 && A.mesh)
@@ -816,6 +818,15 @@ extern "C" int emc_field_packed(EmcCtx *ctx, const double *u_pad, double *e4, vo
     if (!u_pad || !e4 || ((uintptr_t)e4 & 31) != 0) return fail(c, EMC_ERR_INVALID, "emc_field_packed: null or unaligned");
     cudaError_t e = launch_field_packed(c, u_pad, e4, (cudaStream_t)stream);
     return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "field_packed launch");
+}
+
+extern "C" int emc_field_xz(EmcCtx *ctx, const double *u_pad, double *e2, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!u_pad || !e2 || ((uintptr_t)e2 & 15) != 0) return fail(c, EMC_ERR_INVALID, "emc_field_xz: null or unaligned");
+    if (c->dc.seg[1] != 1) return fail(c, EMC_ERR_UNSUPPORTED, "emc_field_xz: only for meshes with ny = 1");
+    cudaError_t e = launch_field_xz(c, u_pad, e2, (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "field_xz launch");
 }
 
 extern "C" int emc_poisson_last(EmcCtx *ctx, int32_t *sweeps_out, double *err_out, void *stream)

@@ -356,6 +356,19 @@ __device__ __forceinline__ int64_t mesh_cell(const DevConst &P, const Particle &
     return ((int64_t)ci * (P.seg[1] + 2) + cj) * (P.seg[2] + 2) + ck;
 }
 
+// EMC_FIELD_MESH_XZ (ny = 1 meshes): index of the particle's cell in the UNPADDED (nx, nz) record array
+__device__ __forceinline__ int64_t mesh_cell_xz(const DevConst &P, const Particle &p)
+{
+    const int ci = axis_cell(p.x, P.seg[0], P.dl[0], P.inv_dl[0]);
+    const int ck = axis_cell(p.z, P.seg[2], P.dl[2], P.inv_dl[2]);
+    return (int64_t)ci * P.seg[2] + ck;
+}
+template <int FIELD>
+__device__ __forceinline__ int64_t mesh_cell_of(const DevConst &P, const Particle &p)
+{
+    return FIELD == EMC_FIELD_MESH_XZ ? mesh_cell_xz(P, p) : mesh_cell(P, p);
+}
+
 // The field a flight segment sees depends only on where the segment STARTS, and a scatter event
 // does not move the particle: so the event passes know the cell as soon as a particle is popped
 // and pull its field record towards L1 ~500 instructions before the segment needs it.
@@ -368,7 +381,9 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 template <int FIELD>
 __device__ __forceinline__ void field_prefetch(const FlightArgs &A, int64_t c)
 {
-    if (FIELD == EMC_FIELD_MESH_PACKED) {
+    if (FIELD == EMC_FIELD_MESH_XZ) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ex + 2 * c));
+    } else if (FIELD == EMC_FIELD_MESH_PACKED) {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ex + 4 * c));
     } else if (FIELD == EMC_FIELD_MESH) {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ex + c));
@@ -379,11 +394,16 @@ __device__ __forceinline__ void field_prefetch(const FlightArgs &A, int64_t c)
 
 // each lane stages ITS OWN record and reads it back itself: the per-thread cp.async group
 // semantics are all the ordering needed
+template <int FIELD>
 __device__ __forceinline__ void field_stage(const FlightArgs &A, int64_t c, FieldStage &FS, int lane)
 {
-    const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
-    cp_async16(&FS.rs_a[lane], rec);
-    cp_async16(&FS.rs_b[lane], rec + 1);
+    if (FIELD == EMC_FIELD_MESH_XZ) {             // one 16-byte (ex, ez) record
+        cp_async16(&FS.rs_a[lane], reinterpret_cast<const double2 *>(A.ex) + c);
+    } else {
+        const double2 *rec = reinterpret_cast<const double2 *>(A.ex) + 2 * c;
+        cp_async16(&FS.rs_a[lane], rec);
+        cp_async16(&FS.rs_b[lane], rec + 1);
+    }
     asm volatile("cp.async.commit_group;");
 }
 
@@ -400,7 +420,10 @@ __device__ __forceinline__ void field_at(const DevConst &P, const FlightArgs &A,
         else { efx = __ldg(P.field_groups + 3 * p.grp); efy = __ldg(P.field_groups + 3 * p.grp + 1); }
     } else {
         // nearest-cell gather from the padded (nx+2,ny+2,nz+2) field of emc_field, V/m -> V/cm
-        if (FIELD == EMC_FIELD_MESH_PACKED) {     // one 32-B record per cell, already V/cm
+        if (FIELD == EMC_FIELD_MESH_XZ) {         // one 16-B (ex, ez) record per interior cell, V/cm; ey is -0 on ny = 1
+            const double2 a = staged ? FS.rs_a[lane] : __ldg(reinterpret_cast<const double2 *>(A.ex) + c);
+            efx = a.x; efy = 0.0; efz = a.y;
+        } else if (FIELD == EMC_FIELD_MESH_PACKED) {     // one 32-B record per cell, already V/cm
             double2 a, b;
             if (staged) {                         // landed: the caller waited for the cp.async group
                 a = FS.rs_a[lane]; b = FS.rs_b[lane];
@@ -535,7 +558,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     __shared__ MechMeta Ms[ML ? EMC_MAX_LAYERS : 1];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     WarpQueues *queues = reinterpret_cast<WarpQueues *>(dyn_smem);
-    constexpr bool AHEAD_OK = EMC_FIELD_AHEAD && FIELD == EMC_FIELD_MESH_PACKED;
+    constexpr bool AHEAD_OK = EMC_FIELD_AHEAD && (FIELD == EMC_FIELD_MESH_PACKED || FIELD == EMC_FIELD_MESH_XZ);
     const bool AHEAD = AHEAD_OK && A.field_ahead;                 // warp-uniform (kernel argument)
     const size_t fs_bytes = AHEAD ? sizeof(FieldStage) : 0;
     FieldStage *fstages = reinterpret_cast<FieldStage *>(dyn_smem + sizeof(WarpQueues) * (FLIGHT_THREADS / 32));
@@ -643,7 +666,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         int mech = 0;
         double e_np = 0.0, r_az = 0.0;
         bool act, pend = false, fly = false, park = false, tail = false;
-        constexpr bool MESHF = (FIELD == EMC_FIELD_MESH || FIELD == EMC_FIELD_MESH_PACKED);
+        constexpr bool MESHF = (FIELD == EMC_FIELD_MESH || FIELD == EMC_FIELD_MESH_PACKED || FIELD == EMC_FIELD_MESH_XZ);
         constexpr bool SPEC = EMC_SPEC_SELECT && !REPLAY && !EXACT;
         double lg = 0.0;                                          // SPEC: log(flight uniform) of a finished event
         int64_t cell = 0;                                         // mesh cell of the coming flight segment
@@ -690,8 +713,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     p.grp = g >= P.n_groups ? P.n_groups - 1 : g;
                 }
                 if (MESHF && !(AHEAD && field_staged)) {     // else: staged by the previous refill
-                    cell = mesh_cell(P, p);
-                    if (AHEAD) field_stage(A, cell, FS, lane);
+                    cell = mesh_cell_of<FIELD>(P, p);
+                    if (AHEAD) field_stage<FIELD>(A, cell, FS, lane);
                     else field_prefetch<FIELD>(A, cell);
                 }
                 if (ML && p.val >= 0) {                           // :366 / :372
@@ -751,7 +774,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             __syncwarp();
             if (act) {
                 i = w0 + p.off;
-                if (MESHF) { cell = mesh_cell(P, p); field_prefetch<FIELD>(A, cell); }
+                if (MESHF) { cell = mesh_cell_of<FIELD>(P, p); field_prefetch<FIELD>(A, cell); }
                 if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
                 else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
                 int v = p.val, f;
@@ -819,10 +842,12 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             field_at<FIELD, ZON>(P, A, p, cell, efx, efy, efz, FS, lane, AHEAD_OK && AHEAD && phase == PH_REFILL);
             const Mat &MT = P.mat[ML ? layer : 0];
             const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
-            if ((FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) && (ZON || P.zonly))
-                carrier_drift<true>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
+            if (FIELD == EMC_FIELD_MESH_XZ)
+                carrier_drift<2>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
+            else if ((FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) && (ZON || P.zonly))
+                carrier_drift<1>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             else
-                carrier_drift<false>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
+                carrier_drift<0>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
             acc.count_segment();
         }
         if (phase == PH_REFILL && AHEAD) {
@@ -830,7 +855,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             if (ahead) {
                 Particle q;
                 q.x = nx_; q.y = ny_; q.z = nz_;
-                field_stage(A, mesh_cell(P, q), FS, lane);
+                field_stage<FIELD>(A, mesh_cell_of<FIELD>(P, q), FS, lane);
             }
             field_staged = next < wlen;           // `next` already points at that batch
         }
@@ -953,14 +978,15 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     size_t smem = sizeof(WarpQueues) * (FLIGHT_THREADS / 32);
     // refill-ahead field staging only where the field does not live in L1 anyway (EMC_FIELD_AHEAD)
     const int64_t field_cells = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[1] * ctx->dc.seg[2];
-    A.field_ahead = EMC_FIELD_AHEAD && field_mode == EMC_FIELD_MESH_PACKED && field_cells >= 8192 && !ctx->no_field_ahead;
+    A.field_ahead = EMC_FIELD_AHEAD && (field_mode == EMC_FIELD_MESH_PACKED || field_mode == EMC_FIELD_MESH_XZ) &&
+                    field_cells >= 8192 && !ctx->no_field_ahead;
     if (A.field_ahead) smem += sizeof(FieldStage) * (FLIGHT_THREADS / 32);
     {   // bulk-async refill: every state row 16-byte aligned (the copies are 256-B slices at multiples of 32 particles)
         uintptr_t bits = (uintptr_t)A.valley;
         for (int r = 0; r < 7; ++r) bits |= (uintptr_t)(&A.kx)[r];
         // (not for the mesh-field modes: the tiles' 31 KB of shared memory come out of the L1 that the
         // field gathers live on -- measured 0.745 ms with, 0.721 ms without on 1024 x 1 x 1024, profiles/ab_r2e)
-        const bool mesh_field = field_mode == EMC_FIELD_MESH || field_mode == EMC_FIELD_MESH_PACKED;
+        const bool mesh_field = field_mode == EMC_FIELD_MESH || field_mode == EMC_FIELD_MESH_PACKED || field_mode == EMC_FIELD_MESH_XZ;
         A.bulk = EMC_BULK_REFILL && (bits & 15) == 0 && !ctx->no_bulk_refill && !replay && !mesh_field;
         if (A.bulk) smem += sizeof(RefillTile) * (FLIGHT_THREADS / 32);
     }
@@ -986,6 +1012,7 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     case EMC_FIELD_GROUPS:   return launch_flight_t<STREAM, EMC_FIELD_GROUPS>(ctx, A, grid, smem, st);   \
     case EMC_FIELD_MESH:     return launch_flight_t<STREAM, EMC_FIELD_MESH>(ctx, A, grid, smem, st);     \
     case EMC_FIELD_MESH_PACKED: return launch_flight_t<STREAM, EMC_FIELD_MESH_PACKED>(ctx, A, grid, smem, st); \
+    case EMC_FIELD_MESH_XZ:  return launch_flight_t<STREAM, EMC_FIELD_MESH_XZ>(ctx, A, grid, smem, st); \
     default: return cudaErrorInvalidValue;                                                       \
     }
 #ifdef EMC_PROBE_ONLY

@@ -588,6 +588,28 @@ cudaError_t launch_field_packed(Ctx *ctx, const double *u_pad, double *e4, cudaS
     return cudaGetLastError();
 }
 
+// ny = 1 meshes: (ex, ez) per INTERIOR cell, unpadded (nx, nz), V/cm -- 16 bytes per gather instead of 32,
+// a 16 MB array instead of 101 MB allocated / 34 MB touched on 1024 x 1 x 1024 (EMC_FIELD_MESH_XZ)
+__global__ void field_xz_kernel(const __grid_constant__ DevConst P, const double *__restrict__ u, double2 *e2)
+{
+    const int nx = P.seg[0], nz = P.seg[2];
+    const int64_t sy = nz + 2, sx = (int64_t)3 * (nz + 2);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nx * nz) return;
+    const uint32_t t32 = (uint32_t)t, i0 = t32 / (uint32_t)nz;
+    const int k = 1 + (int)(t32 - i0 * (uint32_t)nz), i = 1 + (int)i0;
+    const int64_t c = (int64_t)i * sx + sy + k;
+    e2[t] = make_double2((-0.5 * (u[c + sx] - u[c - sx]) / P.dl[0]) * 1e-2, (-0.5 * (u[c + 1] - u[c - 1]) / P.dl[2]) * 1e-2);
+}
+
+cudaError_t launch_field_xz(Ctx *ctx, const double *u_pad, double *e2, cudaStream_t st)
+{
+    const int64_t total = (int64_t)ctx->dc.seg[0] * ctx->dc.seg[2];
+    ctx->launches++;
+    field_xz_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->dc, u_pad, reinterpret_cast<double2 *>(e2));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_field(Ctx *ctx, const double *u_pad, double *ex, double *ey, double *ez, cudaStream_t st)
 {
     const int64_t total = (int64_t)(ctx->dc.seg[0] + 2) * (ctx->dc.seg[1] + 2) * (ctx->dc.seg[2] + 2);

@@ -401,6 +401,8 @@ class Ensemble:
             ex, ey, ez = mesh.ex.data_ptr(), mesh.ey.data_ptr(), mesh.ez.data_ptr()
         elif field_mode == abi.FIELD_MESH_PACKED:
             ex = mesh.e4.data_ptr()
+        elif field_mode == abi.FIELD_MESH_XZ:
+            ex = mesh.e2.data_ptr()
         c.check(c.lib.emc_flight_scatter(
             c.h, *self._ptrs(), self.n, field_mode, ex, ey, ez, seed, self.pid_offset, step,
             obs_t.data_ptr() if observe else None,
@@ -427,6 +429,8 @@ class Ensemble:
                     ex, ey, ez = mesh.ex.data_ptr(), mesh.ey.data_ptr(), mesh.ez.data_ptr()
                 elif field_mode == abi.FIELD_MESH_PACKED:
                     ex = mesh.e4.data_ptr()
+                elif field_mode == abi.FIELD_MESH_XZ:
+                    ex = mesh.e2.data_ptr()
                 self._obs_cache = None
                 c.check(c.lib.emc_flight_scatter_steps(
                     c.h, *self._ptrs(), self.n, field_mode, ex, ey, ez, seed, self.pid_offset,
@@ -463,6 +467,8 @@ class Ensemble:
             ex, ey, ez = mesh.ex.data_ptr(), mesh.ey.data_ptr(), mesh.ez.data_ptr()
         elif field_mode == abi.FIELD_MESH_PACKED:
             ex = mesh.e4.data_ptr()
+        elif field_mode == abi.FIELD_MESH_XZ:
+            ex = mesh.e2.data_ptr()
         c.check(c.lib.emc_flight_scatter_replay(
             c.h, *self._ptrs(), self.n, field_mode, ex, ey, ez, self.pid_offset,
             uniforms.data_ptr(), uniforms.shape[1], cursor.data_ptr(),
@@ -526,6 +532,8 @@ class Mesh:
         self.ey = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.ez = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.e4 = torch.zeros(pad + (4,), dtype=torch.float64, device=ctx.device)   # (ex, ey, ez, 0) in V/cm
+        # ny = 1: (ex, ez) per interior cell, unpadded (FIELD_MESH_XZ)
+        self.e2 = torch.zeros((nx, nz, 2), dtype=torch.float64, device=ctx.device) if ny == 1 else None
         self._rho_halo_done = self._e4_halo_done = False
         self.set_initial_guess(None)
 
@@ -654,6 +662,11 @@ class Mesh:
         c.check(c.lib.emc_field(c.h, self.u_pad.data_ptr(), self.ex.data_ptr(), self.ey.data_ptr(),
                                 self.ez.data_ptr(), c.stream))
 
+    def field_xz(self):
+        """ny = 1 meshes: the field as one 16-byte (ex, ez) record per interior cell (FIELD_MESH_XZ)."""
+        c = self.ctx
+        c.check(c.lib.emc_field_xz(c.h, self.u_pad.data_ptr(), self.e2.data_ptr(), c.stream))
+
     def field_packed(self):
         """The same field as one 32-byte record per cell (the flight kernel's FIELD_MESH_PACKED)."""
         c = self.ctx
@@ -670,7 +683,7 @@ class CoupledStepper:
 
     def __init__(self, ctx: Context, ens: Ensemble, mesh: Mesh | None = None, seed: int = 12345,
                  tol: float = 1e-6, max_sweeps: int = 10000, order: int = abi.SOR_RED_BLACK,
-                 group=None, fuse_deposit: bool = False, packed_field: bool = True):
+                 group=None, fuse_deposit: bool = False, packed_field: bool = True, xz_field: bool = True):
         # fuse_deposit: the flight kernel can deposit its end-of-step positions itself (saves
         # re-reading 24 B/particle) but the assignment then runs on half-filled warps inside the
         # register-heavy kernel: measured 0.45 ms fused vs 0.19 ms for the separate deposit kernel
@@ -680,6 +693,9 @@ class CoupledStepper:
         # separate arrays; identical values (Mesh.field() still gives the reference's ef_x/y/z)
         self.packed_field = packed_field
         self.field_mode = abi.FIELD_MESH_PACKED if packed_field else abi.FIELD_MESH
+        if packed_field and ctx.seg[1] == 1 and xz_field:
+            # ny = 1: half-size (ex, ez) records without halo (identical trajectories: ey is -0 there)
+            self.field_mode = abi.FIELD_MESH_XZ
         self.ctx, self.ens, self.seed = ctx, ens, seed
         if mesh is None:
             # multi-rank runs on large meshes sum the charge with the NVLink peer-memory kernel
@@ -710,7 +726,13 @@ class CoupledStepper:
         m.allreduce(self.group)
         m.to_rho()
         m.solve_async(tol=self.tol, max_sweeps=max_sweeps or self.max_sweeps, order=self.order)
-        if self.packed_field:
+        self.update_field()
+
+    def update_field(self):
+        m = self.mesh
+        if self.field_mode == abi.FIELD_MESH_XZ:
+            m.field_xz()
+        elif self.packed_field:
             m.field_packed()
         else:
             m.field()

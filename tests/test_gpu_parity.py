@@ -681,7 +681,7 @@ def test_coupled_stepper_vs_oracle(torch_mod):
         coords, v, dtau = hot_ensemble(n, 36, g)
         dl = np.array(c.params.dl[:])
         ens = engine.Ensemble(c, n).load(coords, v, dtau)
-        cs = engine.CoupledStepper(c, ens, seed=11, order=abi.SOR_LEXICOGRAPHIC).prime()
+        cs = engine.CoupledStepper(c, ens, seed=11, order=abi.SOR_LEXICOGRAPHIC, xz_field=False).prime()
         # oracle side
         o = helpers.make_oracle()
         st = helpers.state_from_coords(coords, v, dtau)
@@ -721,6 +721,16 @@ def test_coupled_stepper_vs_oracle(torch_mod):
             cs3.step()
         a, b = ens.coords(), ens3.coords()
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        # ny = 1: the default gathers 16-byte (ex, ez) records of the unpadded interior (EMC_FIELD_MESH_XZ)
+        ens4 = engine.Ensemble(c, n).load(coords, v, dtau)
+        cs4 = engine.CoupledStepper(c, ens4, seed=11, order=abi.SOR_LEXICOGRAPHIC).prime()
+        assert cs4.field_mode == abi.FIELD_MESH_XZ
+        for s in range(3):
+            cs4.step()
+        assert all(np.array_equal(x, y) for x, y in zip(a, ens4.coords()))
+        e2 = cs4.mesh.e2.cpu().numpy()
+        assert np.array_equal(e2[..., 0], fld[0][1:-1, 1, 1:-1] * 1e-2) and np.array_equal(e2[..., 1], fld[2][1:-1, 1, 1:-1] * 1e-2)
+        assert np.array_equal(cs4.mesh.counts.cpu().numpy(), cnt)
         # the fast path (red-black) stays within the solver tolerance of it
         ens2 = engine.Ensemble(c, n).load(coords, v, dtau)
         cs2 = engine.CoupledStepper(c, ens2, seed=11, order=abi.SOR_RED_BLACK).prime()
