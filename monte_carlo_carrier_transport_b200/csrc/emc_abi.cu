@@ -192,6 +192,7 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
         c->no_lean = ln && std::atoi(ln) == 0;
         const char *br = std::getenv("EMC_BULK_REFILL");
         c->no_bulk_refill = br && std::atoi(br) == 0;
+        c->bulk_mesh = br && std::atoi(br) == 2;
         const char *ex = std::getenv("EMC_EXACT_LIBM");
         c->exact_libm = ex && std::atoi(ex) != 0;
     }

@@ -987,7 +987,7 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
         // (not for the mesh-field modes: the tiles' 31 KB of shared memory come out of the L1 that the
         // field gathers live on -- measured 0.745 ms with, 0.721 ms without on 1024 x 1 x 1024, profiles/ab_r2e)
         const bool mesh_field = field_mode == EMC_FIELD_MESH || field_mode == EMC_FIELD_MESH_PACKED || field_mode == EMC_FIELD_MESH_XZ;
-        A.bulk = EMC_BULK_REFILL && (bits & 15) == 0 && !ctx->no_bulk_refill && !replay && !mesh_field;
+        A.bulk = EMC_BULK_REFILL && (bits & 15) == 0 && !ctx->no_bulk_refill && !replay && (!mesh_field || ctx->bulk_mesh);
         if (A.bulk) smem += sizeof(RefillTile) * (FLIGHT_THREADS / 32);
     }
     if (EMC_OBS_SMEM) {

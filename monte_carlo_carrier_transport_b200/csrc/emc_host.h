@@ -53,6 +53,7 @@ struct Ctx {
     int obs_before = 0;           // emc_set_obs_phase
     bool no_field_ahead = false;  // EMC_FIELD_AHEAD=0 in the environment (tuning)
     bool no_bulk_refill = false;  // EMC_BULK_REFILL=0 in the environment (tuning)
+    bool bulk_mesh = false;       // EMC_BULK_REFILL=2: bulk refill tiles in the mesh-field modes too (A/B)
     bool no_lean = false;         // EMC_LEAN=0 in the environment: always the general flight kernel (A/B, tests)
     bool self_last = false;       // every uploaded table: last column = the one self-scattering mechanism, dE 0, same valley
     bool zonly_constant = false;  // dc.efield has Ex = Ey = +0
