@@ -553,6 +553,15 @@ def run_ours(args):
     faults = int(final_obs["n_fault"]) if final_obs is not None else int(raw[-1, 8])
     clk = clocks.stop() if rank == 0 else None
 
+    if args.no_e2e:       # profiling runs (ncu launch lists): the device-resident arm only
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": segments / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                              "steps": steps, "ms_per_step": elapsed_ms / steps, "kernel_ms": kernel_ms,
+                              "gpu_launches": int(launches), "note": "--no-e2e profiling run"}))
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- end-to-end arm: the caller holds HOST arrays (the reference's coords/valley/dtau) ----
     co, val, dtau = None, None, None
     hs = engine.HostStepper(ctx, n, pid_offset=rank * n)
@@ -686,6 +695,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-coupled", action="store_true", help="skip the coupled MC+Poisson sub-benchmark")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident arm only (ncu launch lists)")
     ap.add_argument("--e2e-loop-steps", type=int, default=50,
                     help="timesteps per HostStepper.run call of the e2e arm (the reference's pts = 50, init_.py:61)")
     ap.add_argument("--obs-phase", default="before", choices=["before", "after"],

@@ -476,6 +476,16 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
     if (FIELD == EMC_FIELD_GROUPS) Q.grp[slot] = p.grp;
 }
 
+#ifndef EMC_LANE_IN_REGISTER
+#define EMC_LANE_IN_REGISTER 1
+#endif
+#ifndef EMC_EARLY_GROUP_FIELD
+// 1 (lean kernel, EMC_FIELD_GROUPS): the particle's field value is loaded as soon as its group is known
+// (refill / queue pop) instead of at the head of the flight segment, where its L1/L2 latency was 2.6 %
+// of the stall samples (profiles/r2f).  Measured: no gain (0.991 vs 0.985 ms, profiles/r2o): the other warps
+// already cover that wait; off.
+#define EMC_EARLY_GROUP_FIELD 0
+#endif
 #ifndef EMC_LEAN_KERNEL
 #define EMC_LEAN_KERNEL 1
 #endif
@@ -589,8 +599,19 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     // the warp index through a full-mask shuffle from lane 0: the compiler then KNOWS it is warp-uniform
     // and keeps everything derived from it (slice bounds, queue and tile addresses, the operands of the
     // bulk copies) in uniform registers
-    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+#if EMC_LANE_IN_REGISTER
+    // lane and the lower-lanes mask read ONCE from their special registers and pinned in two general
+    // registers (volatile asm is not rematerialised): the compiler otherwise re-reads SR_TID.X in every
+    // pass of the loop -- an S2R (~20 cycles) at the head of each pass, 1.3 % of the stall samples in r2f
+    int lane;
+    unsigned lt_mask;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+#else
+    const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+#endif
     WarpQueues &WQ = queues[warp];
     FieldStage &FS = fstages[AHEAD ? warp : 0];                   // only dereferenced when AHEAD
     const int64_t total_warps = (int64_t)gridDim.x * (FLIGHT_THREADS / 32);
@@ -669,6 +690,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         constexpr bool MESHF = (FIELD == EMC_FIELD_MESH || FIELD == EMC_FIELD_MESH_PACKED || FIELD == EMC_FIELD_MESH_XZ);
         constexpr bool SPEC = EMC_SPEC_SELECT && !REPLAY && !EXACT;
         double lg = 0.0;                                          // SPEC: log(flight uniform) of a finished event
+        constexpr bool EARLY_GF = EMC_EARLY_GROUP_FIELD && ZON && FIELD == EMC_FIELD_GROUPS;
+        double gfz = 0.0;                                         // EARLY_GF: Ez of the particle's field group
         int64_t cell = 0;                                         // mesh cell of the coming flight segment
         int layer = 0;                                            // ML: where_am_i of the particle's z
         double dt_seg = 0.0;
@@ -711,6 +734,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     uint32_t r = grp_rem + lane;
                     while (r >= gsz) { r -= gsz; ++g; }
                     p.grp = g >= P.n_groups ? P.n_groups - 1 : g;
+                    if (EARLY_GF) gfz = __ldg(P.field_groups + 3 * p.grp + 2);
                 }
                 if (MESHF && !(AHEAD && field_staged)) {     // else: staged by the previous refill
                     cell = mesh_cell_of<FIELD>(P, p);
@@ -766,6 +790,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             const int slot = qlen + lane;
             if (act) {
                 queue_pop<FIELD>(Qp, slot, p, s0);
+                if (EARLY_GF) gfz = __ldg(P.field_groups + 3 * p.grp + 2);
                 if (!sel) {
                     const double2 er = WQ.sc_er[slot];
                     mech = WQ.sc_mech[slot]; e_np = er.x; r_az = er.y;
@@ -839,7 +864,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         if (AHEAD_OK && AHEAD && phase == PH_REFILL) asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (fly) {                                                // :367 / :373 / :388
             double efx, efy, efz;
-            field_at<FIELD, ZON>(P, A, p, cell, efx, efy, efz, FS, lane, AHEAD_OK && AHEAD && phase == PH_REFILL);
+            if (EARLY_GF) { efx = 0.0; efy = 0.0; efz = gfz; }
+            else field_at<FIELD, ZON>(P, A, p, cell, efx, efy, efz, FS, lane, AHEAD_OK && AHEAD && phase == PH_REFILL);
             const Mat &MT = P.mat[ML ? layer : 0];
             const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
             if (FIELD == EMC_FIELD_MESH_XZ)
