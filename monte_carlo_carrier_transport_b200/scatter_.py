@@ -4,15 +4,15 @@ What lives here (host, run once): the 27 scattering-rate formulas, ``scatter_mec
 ``calc_scatter_table`` -- the inputs of the GPU hot path.
 What does NOT live here: the per-event work.  ``calc_energy`` and ``scatter`` keep the
 reference's signatures but execute on the GPU through the C-ABI (``emc_calc_energy``,
-``emc_scatter_batch``); there is no CPU fallback.
+``emc_scatter``); there is no CPU fallback.
 
 The rate formulas are generated from two descriptor tables instead of 27 hand-written
 functions, but every expression keeps the reference's operation ORDER, so the tables
-are bit-identical to ``scatter_.calc_scatter_table`` (tests/test_tables.py pins the
-SHA-256 recorded from the unmodified reference).  Reference map: Bose_Einstein
+are bit-identical to ``scatter_.calc_scatter_table`` (tests/test_oracle_golden.py and
+tests/test_host_mirrors.py pin the SHA-256 recorded from the unmodified reference).  Reference map: Bose_Einstein
 scatter_.py:57-70, density_of_states :73-89, plasmon_freq :91-106, ADP :110-130,
 POP_abs/ems :133-182, IV_* :185-580, IMP :583-624, cc :626-652, total/self :654-792,
-angle samplers :795-889 (device code: csrc/emc_kernels.cu), scatter_mech :892-951,
+angle samplers :795-889 (device code: csrc/emc_device.cuh ``sample_polar``), scatter_mech :892-951,
 calc_scatter_table :954-984, scatter :986-1099.
 """
 from __future__ import annotations
