@@ -688,6 +688,66 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_config_c2(args):
+    """SURVEY 8d C2 at full length: the bulk velocity-field sweep (24 field points 0.1-50 kV/cm, 1e6
+    electrons per point, one 2.4e7-particle ensemble, cyclic z) over 2500 timesteps = 5 ps, time-averaged
+    after the first 2 ps, next to the same curve from the CPU oracle (C port of the reference's loop,
+    the same algorithm and boundary extension) on a bounded ensemble per field point.  One JSON line
+    with both curves and their difference in units of the combined statistical error."""
+    import torch
+    import helpers
+    import oracle as orc
+    from monte_carlo_carrier_transport_b200 import configs
+    steps, discard, every = args.c2_steps, int(0.4 * args.c2_steps), 10
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    curve = configs.c2(scale=1.0, steps=steps, discard=discard, sample_every=every, seed=SEED, device=0)
+    torch.cuda.synchronize()
+    gpu_s = time.perf_counter() - t0
+    # oracle: the same sweep, n_o electrons per field point
+    n_o, nf = args.c2_oracle_per_field, len(curve)
+    g = helpers.golden_params()
+    phys = dict(g["phys"], z_cyclic=1)
+    ek, tabs, mech = helpers.host_tables()
+    o = orc.Oracle(phys, ek, tabs, [list(zip(m[1].tolist(), m[2].tolist(), m[3].tolist())) for m in mech])
+    fields = configs.field_points(nf)
+    o.set_field_groups(fields, n_o)
+    st = o.init_ensemble(nf * n_o, SEED + 7, 0)
+    threads = os.cpu_count() or 1
+    acc = np.zeros((nf, 3))
+    m = 0
+    t1 = time.perf_counter()
+    for c in range(steps):
+        o.timestep(st, orc.philox_stream(SEED + 7, c, 0), threads=threads)
+        if c >= discard and (c - discard) % every == 0:
+            for gi in range(nf):
+                sl = {k: v[gi * n_o:(gi + 1) * n_o] for k, v in st.items()}
+                ob = o.observables(sl)
+                n = max(sum(ob["n_valley"]), 1)
+                mv = ob["sum_vz"] / n
+                acc[gi] += [mv, ob["sum_vz2"] / n - mv * mv, ob["sum_e"] / n]
+            m += 1
+    cpu_s = time.perf_counter() - t1
+    acc /= max(m, 1)
+    # statistical error of the oracle's time average: ensemble variance / (n_o * independent samples);
+    # the velocity autocorrelation time is taken as 0.3 ps = 150 timesteps = 15 samples (conservative)
+    indep = max(1.0, m / 15.0)
+    rows, worst = [], 0.0
+    for gi, r in enumerate(curve):
+        se = float(np.sqrt(max(acc[gi, 1], 0.0) / (n_o * indep)))
+        z = (r["vz"] - acc[gi, 0]) / se if se > 0 else 0.0
+        worst = max(worst, abs(z))
+        rows.append({"field_kv_cm": r["field_kv_cm"], "vz_gpu": r["vz"], "e_gpu": r["e"], "frac_gamma": r["frac_gamma"],
+                     "frac_l": r["frac_l"], "frac_x": r["frac_x"], "vz_oracle": float(acc[gi, 0]), "vz_oracle_se": se,
+                     "e_oracle": float(acc[gi, 2]), "z": float(z)})
+    seg = 1.8 * N_FIELDS * PER_FIELD * steps
+    print(json.dumps({"config": "c2", "metric": "velocity-field curve, bulk GaAs, 24 field points x 1e6 electrons, %d timesteps "
+                      "(%.1f ps), averaged after %.1f ps" % (steps, steps * 2e-3, discard * 2e-3),
+                      "gpu_wall_s": gpu_s, "approx_steps_per_s_incl_sampling": seg / gpu_s,
+                      "oracle": {"particles_per_field": n_o, "wall_s": cpu_s, "cores": threads, "kind": "port"},
+                      "max_abs_z": worst, "agree_within_4_sigma": bool(worst < 4.0), "curve": rows}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -700,8 +760,14 @@ def main():
                     help="timesteps per HostStepper.run call of the e2e arm (the reference's pts = 50, init_.py:61)")
     ap.add_argument("--obs-phase", default="before", choices=["before", "after"],
                     help="per-step observables reduced while loading the next step's state (default) or at retirement")
+    ap.add_argument("--config", default=None, choices=["c2"],
+                    help="c2: the full-length velocity-field sweep of SURVEY 8d C2 with the oracle's curve beside it")
+    ap.add_argument("--c2-steps", type=int, default=2500)
+    ap.add_argument("--c2-oracle-per-field", type=int, default=12000)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config == "c2":
+        run_config_c2(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

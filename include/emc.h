@@ -230,7 +230,9 @@ int emc_init_photoex(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x,
  * obs (device pointer to one EmcObs, may be NULL): if given, the observables of
  * main_.py:394-403 are reduced in the same kernel and written there.
  * mesh (device int64[nx*ny*nz], may be NULL): if given, the end-of-step NGP charge
- * assignment (poisson_.py:30-38) is fused into the kernel (atomically ADDED to mesh). */
+ * assignment (poisson_.py:30-38) is fused into the kernel (atomically ADDED to mesh).
+ * At most 2^32 - 65 particles per call (EMC_ERR_UNSUPPORTED beyond: the kernel indexes the slice with
+ * 32 bits); larger ensembles are sliced by the caller, pid_offset keeps the random streams global. */
 int emc_flight_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x, double *y,
                        double *z, double *dtau, int32_t *valley, int64_t n,
                        int32_t field_mode, const double *ex, const double *ey, const double *ez,
