@@ -243,12 +243,22 @@ int emc_flight_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, double *
  * loop of main_.py:339 without a host round trip per step (a small ensemble -- the reference's
  * 10^4 electrons take 12 us of GPU time per timestep -- is otherwise bound by the caller's own
  * per-call overhead).  obs_rows: device array of n_steps EmcObs (or NULL), row s written by
- * timestep first_step + s according to emc_set_obs_phase. */
+ * timestep first_step + s according to emc_set_obs_phase.
+ * With obs_rows == NULL (no per-step observables wanted: burn-in phases, sweeps that sample every
+ * m-th timestep) and the lean case -- constant or group field with Ex = Ey = +0, one layer, default
+ * libm composition, the reference's table layout -- all n_steps (2 .. 65535) timesteps run in ONE
+ * persistent launch in which a particle stays in its warp's queues from timestep to timestep
+ * (no reload / write-back per timestep); the final state is bit-identical to n_steps single launches.
+ * EMC_FUSED_STEPS=0 in the environment keeps the launch loop. */
 int emc_flight_scatter_steps(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x,
                              double *y, double *z, double *dtau, int32_t *valley, int64_t n,
                              int32_t field_mode, const double *ex, const double *ey,
                              const double *ez, uint64_t seed, uint64_t pid_offset,
                              uint32_t first_step, int32_t n_steps, EmcObs *obs_rows, void *stream);
+
+/* Self-check of the fused launch above: EMC_ERR_CUDA if any warp ever stopped with particles left in
+ * its queues (cannot happen by construction; synchronises the stream). */
+int emc_flight_steps_check(EmcCtx *ctx, void *stream);
 
 /* Replay mode: the same loop, but every np.random.uniform() of the reference is read from a
  * per-particle sequential stream: uniforms is a device (n, stride) row-major array, cursor a

@@ -88,6 +88,7 @@ SIGNATURES = {
                                                         _u64, _u64, _u32, _vp, _lp, _vp]),
     "emc_flight_scatter_steps": (C.c_int, [_vp] + [_dp] * 7 + [_ip, _i64, _i32, _dp, _dp, _dp,
                                                               _u64, _u64, _u32, _i32, _vp, _vp]),
+    "emc_flight_steps_check": (C.c_int, [_vp, _vp]),
     "emc_flight_scatter_replay": (C.c_int, [_vp] + [_dp] * 7 + [_ip, _i64, _i32, _dp, _dp, _dp,
                                                                _u64, _dp, _i64, _ip, _vp, _lp, _vp]),
     "emc_observables": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip, _i64, C.POINTER(EmcObs), _vp]),

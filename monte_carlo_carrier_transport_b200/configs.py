@@ -66,8 +66,14 @@ def c2(scale=1.0, steps=2500, discard=1000, sample_every=10, seed=SEED, device=0
     acc = np.zeros((n_fields, 6))
     n_samples = 0
     ptr = ens._ptrs()
-    for c in range(steps):
-        ens.step(c, seed, field_mode=abi.FIELD_GROUPS, observe=False)
+    c = -1
+    while c + 1 < steps:
+        # timesteps up to the next sample in ONE persistent launch (Ensemble.advance: the particles stay in
+        # the warps' queues from timestep to timestep), then the observables of every field group
+        nxt = discard if c + 1 <= discard else min(steps - 1, c + sample_every)
+        nxt = max(nxt, c + 1)
+        ens.advance(c + 1, nxt - c, seed, field_mode=abi.FIELD_GROUPS)
+        c = nxt
         if c >= discard and (c - discard) % sample_every == 0:
             for g in range(n_fields):                # observables of one field group = one slice
                 o = abi.EmcObs()

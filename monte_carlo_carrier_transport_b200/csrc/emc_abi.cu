@@ -188,6 +188,8 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
         c->max_grid = c->sm_count * per_sm;
         const char *fa = std::getenv("EMC_FIELD_AHEAD");
         c->no_field_ahead = fa && std::atoi(fa) == 0;
+        const char *fs = std::getenv("EMC_FUSED_STEPS");
+        c->no_fused_steps = fs && std::atoi(fs) == 0;
         const char *ln = std::getenv("EMC_LEAN");
         c->no_lean = ln && std::atoi(ln) == 0;
         const char *br = std::getenv("EMC_BULK_REFILL");
@@ -564,6 +566,19 @@ extern "C" int emc_flight_scatter_steps(EmcCtx *ctx, double *kx, double *ky, dou
     if (n_steps < 0) return fail(c, EMC_ERR_INVALID, "emc_flight_scatter_steps: n_steps < 0");
     int r = check_state(c, kx, ky, kz, x, y, z, dtau, valley, n);
     if (r) return r;
+    // no per-step observables wanted and the lean conditions hold: all n_steps timesteps in ONE
+    // persistent launch (flight_steps_kernel), bit-identical to the loop below
+    c->dc.zonly = (field_mode == EMC_FIELD_CONSTANT && c->zonly_constant) || (field_mode == EMC_FIELD_GROUPS && c->zonly_groups);
+    if (!obs_rows && n_steps >= 2 && n_steps <= 65535 && n > 0 && !c->no_fused_steps && c->have_tables &&
+        (field_mode == EMC_FIELD_CONSTANT || (field_mode == EMC_FIELD_GROUPS && c->dc.field_groups)) && c->dc.zonly &&
+        c->dc.n_layers == 1 && !c->exact_libm && !c->dc.literal_scan && c->self_last && n < ((int64_t)1 << 32) - 64) {
+        FlightArgs A;
+        std::memset(&A, 0, sizeof(A));
+        A.kx = kx; A.ky = ky; A.kz = kz; A.x = x; A.y = y; A.z = z; A.dtau = dtau; A.valley = valley; A.n = n;
+        A.seed = seed; A.pid_offset = pid_offset; A.step = first_step;
+        cudaError_t e = launch_flight_steps(c, A, field_mode, n_steps, (cudaStream_t)stream);
+        return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "flight_steps launch");
+    }
     for (int32_t s = 0; s < n_steps; ++s) {
         FlightArgs A;
         std::memset(&A, 0, sizeof(A));
@@ -592,6 +607,17 @@ extern "C" int emc_flight_scatter_replay(EmcCtx *ctx, double *kx, double *ky, do
     A.uniforms = uniforms; A.stride = stride; A.cursor = cursor; A.pid_offset = pid_offset;
     A.obs = obs; A.mesh = mesh;
     return flight_common(c, A, true, field_mode, ex, ey, ez, stream);
+}
+
+extern "C" int emc_flight_steps_check(EmcCtx *ctx, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    int32_t flag = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(&flag, c->d_sor_flags + 3, sizeof(flag), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail_cuda(c, e, "flight_steps_check");
+    return flag ? fail(c, EMC_ERR_CUDA, "flight_steps_kernel: a warp stopped with particles left in its queues") : EMC_OK;
 }
 
 extern "C" int emc_observables(EmcCtx *ctx, const double *kx, const double *ky, const double *kz, const double *z,

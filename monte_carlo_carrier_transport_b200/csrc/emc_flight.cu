@@ -1052,6 +1052,251 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
 }
 
 // ------------------------------------------------------------------------------------------
+// K timesteps in ONE persistent launch: for uncoupled runs that do not need
+// the observables of every timestep -- burn-in phases, the velocity-field sweep that samples every
+// tenth timestep -- a particle stays in its warp's queues from timestep to timestep instead of being
+// written back and reloaded: no refill and no write-back per timestep (25 % of the one-step kernel's
+// stall samples).  A third queue, NX, holds the particles that have finished a timestep; an ADVANCE
+// pass pops 32 of them (all lanes busy), starts their next timestep (main_.py:361-373 on the carried
+// dtau) or, after the last one, writes them back.  Same per-particle arithmetic and the same Philox
+// counters (key = seed, counter = (block, first_step + ts, particle)) as n_steps launches of
+// flight_scatter_kernel: bit-identical final state (tests/test_gpu_parity.py).  Restricted to the
+// lean case: free-running Philox, default libm composition, one layer, constant or group field
+// with Ex = Ey = +0, padded tables with self-scattering last; everything else takes the launch loop.
+// The parked (real-mechanism) particles carry no extra fields: the scatter pass re-derives energy,
+// mechanism and azimuth from the same counters (scatter_event), 0.1 passes per batch.
+// ------------------------------------------------------------------------------------------
+struct StepQueues {
+    WarpQueue ev;      // waiting for the next event of their current timestep
+    WarpQueue sc;      // drew a real mechanism
+    WarpQueue nx;      // finished a timestep: next timestep / write-back after the last one
+};
+
+template <int FIELD>
+__global__ void __launch_bounds__(FLIGHT_THREADS, 1)
+flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg,
+                    const __grid_constant__ FlightArgs A, const int n_steps, int32_t *stuck_flag)
+{
+    static_assert(FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS, "uncoupled field modes only");
+    __shared__ MechMeta Ms;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    StepQueues *queues = reinterpret_cast<StepQueues *>(dyn_smem);
+    {
+        const int nw = sizeof(MechMeta) / 4;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&Mg);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&Ms);
+        for (int t = threadIdx.x; t < nw; t += blockDim.x) dst[t] = src[t];
+    }
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
+    int lane;
+    unsigned lt_mask;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    StepQueues &WQ = queues[warp];
+    const int64_t total_warps = (int64_t)gridDim.x * (FLIGHT_THREADS / 32);
+    const int64_t gw = (int64_t)blockIdx.x * (FLIGHT_THREADS / 32) + warp;
+    const int64_t slice = (((A.n + total_warps - 1) / total_warps) + 31) & ~(int64_t)31;
+    int64_t wstart = gw * slice;
+    if (wstart > A.n) wstart = A.n;
+    const int64_t wend = (wstart + slice < A.n) ? wstart + slice : A.n;
+    uint32_t next = 0;
+    const uint32_t wlen = (uint32_t)(wend - wstart), w0 = (uint32_t)wstart;
+    int qn = 0, qsc = 0, qnx = 0;
+    const double dt = P.dt;
+    int32_t grp_next = 0;
+    uint32_t grp_rem = 0;
+    const uint32_t gsz = (uint32_t)P.group_size;
+    if (FIELD == EMC_FIELD_GROUPS) {
+        const uint64_t g0 = A.pid_offset + (uint64_t)wstart;
+        const uint64_t gq = g0 / (uint64_t)P.group_size;
+        grp_next = (int32_t)(gq < (uint64_t)P.n_groups ? gq : (uint64_t)P.n_groups);
+        grp_rem = (uint32_t)(g0 % (uint64_t)P.group_size);
+    }
+    const Mat &MT = P.mat[0];
+    enum { PH_REFILL = 0, PH_SELECT = 1, PH_SCATTER = 2, PH_ADVANCE = 3 };
+    while (true) {
+        // a pass pops only what every queue it may push into can hold; a particle goes to exactly one
+        const int room_ev = QCAP - qn, room_sc = QCAP - qsc, room_nx = QCAP - qnx;
+        const int n_sc = min(min(32, qsc), min(room_ev, room_nx));
+        const int n_sel = min(min(32, qn), min(room_sc, room_nx));
+        const int n_adv = min(min(32, qnx), room_ev);            // NX gets back at most what was popped
+        const bool can_refill = next < wlen && room_ev >= 32 && room_nx >= 32;
+        int phase;
+        if (n_sc == 32) phase = PH_SCATTER;
+        else if (n_sel == 32) phase = PH_SELECT;
+        else if (n_adv == 32) phase = PH_ADVANCE;
+        else if (can_refill) phase = PH_REFILL;
+        else if (n_sc > 0 && n_sc >= n_sel && n_sc >= n_adv) phase = PH_SCATTER;
+        else if (n_sel > 0 && n_sel >= n_adv) phase = PH_SELECT;
+        else if (n_adv > 0) phase = PH_ADVANCE;
+        else {
+            if ((qn | qsc | qnx) != 0 && lane == 0) atomicExch(stuck_flag, 1);     // cannot happen (see the analysis in DESIGN.md)
+            break;
+        }
+        Particle p;
+        uint32_t s0 = 0;                      // events so far in the timestep (low 16 bits) | timestep index << 16
+        uint32_t i = 0;
+        bool act, pend = false, fly = false, park = false, store = false;
+        double dt_seg = 0.0;
+        if (phase == PH_REFILL || phase == PH_ADVANCE) {
+            if (phase == PH_REFILL) {
+                i = w0 + next + lane;
+                act = next + lane < wlen;
+                if (act) {
+                    p.kx = A.kx[i]; p.ky = A.ky[i]; p.kz = A.kz[i];
+                    p.x = A.x[i]; p.y = A.y[i]; p.z = A.z[i];
+                    p.dte = A.dtau[i];
+                    p.val = A.valley[i];
+                    p.off = next + lane;
+                    p.grp = 0;
+                    if (FIELD == EMC_FIELD_GROUPS) {
+                        int32_t g = grp_next;
+                        uint32_t r = grp_rem + lane;
+                        while (r >= gsz) { r -= gsz; ++g; }
+                        p.grp = g >= P.n_groups ? P.n_groups - 1 : g;
+                    }
+                    if (p.val < 0) act = false;               // frozen on entry: stays as it is in memory
+                }
+                next += 32;
+#if EMC_PREFETCH_BATCHES > 0
+                {
+                    const uint32_t o0 = next + (uint32_t)(EMC_PREFETCH_BATCHES - 1) * 32u;
+                    const int64_t j0 = wstart + o0;
+                    if (o0 < wlen && lane < 15 && (!(lane & 1) || lane == 14 || o0 + 16 < wlen)) {
+                        const char *base = reinterpret_cast<const char *>((&A.kx)[lane >> 1]);
+                        const int64_t off = lane < 14 ? j0 * 8 + (lane & 1) * 128 : j0 * 4;
+                        prefetch_l2(base + off);
+                    }
+                }
+#endif
+                if (FIELD == EMC_FIELD_GROUPS) {
+                    grp_rem += 32;
+                    while (grp_rem >= gsz) { grp_rem -= gsz; ++grp_next; }
+                }
+            } else {
+                act = lane < n_adv;
+                qnx -= n_adv;
+                if (act) queue_pop<FIELD>(WQ.nx, qnx + lane, p, s0);
+                __syncwarp();
+                if (act) {
+                    i = w0 + p.off;
+                    const uint32_t ts = s0 >> 16;
+                    if (ts + 1u >= (uint32_t)n_steps) { store = true; act = false; }   // the last timestep is done: write back
+                    else s0 = (ts + 1u) << 16;
+                }
+            }
+            if (act) {                                        // main_.py:361-373 on the carried dtau
+                const double dte = p.dte;
+                fly = true;
+                if (dte >= dt) { dt_seg = dt; p.dte = dte - dt; }
+                else { dt_seg = dte; pend = true; }
+            }
+        } else {
+            const bool sel = (phase == PH_SELECT);
+            WarpQueue &Qp = sel ? WQ.ev : WQ.sc;
+            const int cnt = sel ? n_sel : n_sc;
+            int &qlen = sel ? qn : qsc;
+            act = lane < cnt;
+            qlen -= cnt;
+            if (act) queue_pop<FIELD>(Qp, qlen + lane, p, s0);
+            __syncwarp();
+            bool tail = false;
+            double lg = 0.0;
+            PhiloxStream rng;
+            if (act) {
+                i = w0 + p.off;
+                rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step + (s0 >> 16), s0 & 0xffffu);
+                int v = p.val, f, mech = 0;
+                double e_np = 0.0, r_az = 0.0;
+                if (sel) {
+                    bool is_self;
+                    f = select_self_spec<PhiloxStream, true>(P, MT, Ms, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
+                    if (f < 0) {
+                        if (is_self) tail = true;
+                        else park = true;                     // the event index in s0 is unchanged: the scatter pass redoes the event
+                    }
+                } else {
+                    f = scatter_event<false>(P, MT, Ms, p.kx, p.ky, p.kz, v, rng);
+                    lg = fast_log(rng.free_flight());
+                    tail = f < 0;
+                }
+                // a faulted particle is written back at once, frozen (dtau keeps dte): only live valleys
+                // (0..2) fit the queues' packed word
+                if (f >= 0) { p.val = -(1 + f); tail = false; park = false; store = true; act = false; }
+                else p.val = v;
+            }
+            if (tail) {
+                const double dte2 = p.dte;                        // main_.py:376
+                const double dt3 = P.neg_inv_gamma * lg;          // :379
+                const double dtp = dt - dte2;                     // :381
+                dt_seg = (dt3 <= dtp) ? dt3 : dtp;                // :382-385
+                fly = true;
+                const double dte = dte2 + dt3;                    // :389
+                if (dte < dt) { p.dte = dte; pend = true; }       // :375
+                else p.dte = dte - dt;                            // :390-391
+                rng.end_event();
+                if (rng.state() > 0xffffu) {                      // the queues keep 16 bits of the event counter
+                    p.val = -(1 + EMC_FAULT_STREAM); fly = false; pend = false; store = true; act = false;
+                } else {
+                    s0 = (s0 & 0xffff0000u) | rng.state();
+                }
+            }
+        }
+        if (fly) {
+            double efz;
+            if (FIELD == EMC_FIELD_CONSTANT) efz = P.efield[2];
+            else efz = __ldg(P.field_groups + 3 * p.grp + 2);
+            const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
+            carrier_drift<1>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, 0.0, 0.0, efz, dt_seg, dtm);
+        }
+        retire_stores_if(A, i, p, p.val, store);
+        const bool done = act && !pend && !park;                  // finished the timestep: next-step queue
+        const unsigned pm = __ballot_sync(FULL, pend);
+        queue_push_if<FIELD>(WQ.ev, qn + __popc(pm & lt_mask), p, s0, pend);
+        qn += __popc(pm);
+        const unsigned dm = __ballot_sync(FULL, done);
+        queue_push_if<FIELD>(WQ.nx, qnx + __popc(dm & lt_mask), p, s0, done);
+        qnx += __popc(dm);
+        if (phase == PH_SELECT) {
+            const unsigned km = __ballot_sync(FULL, park);
+            queue_push_if<FIELD>(WQ.sc, qsc + __popc(km & lt_mask), p, s0, park);
+            qsc += __popc(km);
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_flight_steps(Ctx *ctx, FlightArgs &A, int field_mode, int n_steps, cudaStream_t st)
+{
+    const int64_t blocks_needed = (A.n + FLIGHT_THREADS - 1) / FLIGHT_THREADS;
+    int grid = (int)(blocks_needed < (int64_t)ctx->sm_count ? blocks_needed : ctx->sm_count);
+    if (grid < 1) grid = 1;
+    const size_t smem = sizeof(StepQueues) * (FLIGHT_THREADS / 32);
+    static bool optin[16][2];
+    const int dev = ctx->device & 15;
+    cudaError_t e;
+    ctx->launches++;
+    if (field_mode == EMC_FIELD_CONSTANT) {
+        auto k = flight_steps_kernel<EMC_FIELD_CONSTANT>;
+        if (!optin[dev][0]) {
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            optin[dev][0] = true;
+        }
+        k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A, n_steps, ctx->d_sor_flags + 3);
+    } else {
+        auto k = flight_steps_kernel<EMC_FIELD_GROUPS>;
+        if (!optin[dev][1]) {
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            optin[dev][1] = true;
+        }
+        k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A, n_steps, ctx->d_sor_flags + 3);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // observables only (main_.py:394-403)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FLIGHT_THREADS)

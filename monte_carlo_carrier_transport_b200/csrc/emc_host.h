@@ -54,6 +54,7 @@ struct Ctx {
     bool no_field_ahead = false;  // EMC_FIELD_AHEAD=0 in the environment (tuning)
     bool no_bulk_refill = false;  // EMC_BULK_REFILL=0 in the environment (tuning)
     bool bulk_mesh = false;       // EMC_BULK_REFILL=2: bulk refill tiles in the mesh-field modes too (A/B)
+    bool no_fused_steps = false;  // EMC_FUSED_STEPS=0: emc_flight_scatter_steps always launches once per timestep
     bool no_lean = false;         // EMC_LEAN=0 in the environment: always the general flight kernel (A/B, tests)
     bool self_last = false;       // every uploaded table: last column = the one self-scattering mechanism, dE 0, same valley
     bool zonly_constant = false;  // dc.efield has Ex = Ey = +0
@@ -88,6 +89,7 @@ struct Ctx {
 
 // emc_flight.cu
 cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, cudaStream_t st);
+cudaError_t launch_flight_steps(Ctx *ctx, FlightArgs &A, int field_mode, int n_steps, cudaStream_t st);
 cudaError_t launch_observables(Ctx *ctx, const double *kx, const double *ky, const double *kz, const double *z,
                                const int32_t *valley, int64_t n, EmcObs *out_dev, cudaStream_t st);
 cudaError_t launch_init_ensemble(Ctx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,

@@ -456,6 +456,29 @@ class Ensemble:
         self._obs_cache = dict(rows[-1]) if rows else None      # what last_obs() reports after the loop
         return rows
 
+    def advance(self, first_step: int, n_steps: int, seed: int, field_mode: int = abi.FIELD_CONSTANT,
+                mesh: "Mesh | None" = None, check: bool = False):
+        """``n_steps`` timesteps WITHOUT observables (burn-in phases, sweeps that sample every m-th
+        timestep): ``emc_flight_scatter_steps`` with no observable rows, which runs all of them in one
+        persistent launch -- particles stay in the warps' queues from timestep to timestep -- whenever
+        the lean conditions hold (constant / group field along z, one layer, default libm), else one
+        launch per timestep.  The final state is the same bit for bit either way.  ``check=True``
+        synchronises and verifies the fused kernel's self-check flag."""
+        c = self.ctx
+        ex = ey = ez = None
+        if field_mode == abi.FIELD_MESH:
+            ex, ey, ez = mesh.ex.data_ptr(), mesh.ey.data_ptr(), mesh.ez.data_ptr()
+        elif field_mode == abi.FIELD_MESH_PACKED:
+            ex = mesh.e4.data_ptr()
+        elif field_mode == abi.FIELD_MESH_XZ:
+            ex = mesh.e2.data_ptr()
+        self._obs_cache = None
+        c.check(c.lib.emc_flight_scatter_steps(c.h, *self._ptrs(), self.n, field_mode, ex, ey, ez, seed,
+                                               self.pid_offset, first_step, n_steps, None, c.stream))
+        if check:
+            c.check(c.lib.emc_flight_steps_check(c.h, c.stream))
+        return self
+
     def step_replay(self, uniforms, cursor, field_mode: int = abi.FIELD_CONSTANT, mesh: "Mesh | None" = None,
                     observe: bool = True, deposit: bool = False):
         """Replay mode: uniforms (n, L) float64 device tensor, cursor (n,) int32 device tensor."""

@@ -62,6 +62,21 @@ def main():
                        "segments": int(raw[:, 9].sum()), "events": int(raw[:, 10].sum()),
                        "state_checksum": checksum(torch, ens)}
     ctx.set_obs_phase(False)
+    # the same workload with K timesteps per persistent launch (no per-step observables)
+    for K in (10, 50):
+        ens2 = engine.Ensemble(ctx, n).init(bench.SEED)
+        ens2.advance(0, K, bench.SEED, field_mode=abi.FIELD_GROUPS)          # warm-up
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        ens2.advance(K, K, bench.SEED, field_mode=abi.FIELD_GROUPS)
+        ens2.advance(2 * K, K, bench.SEED, field_mode=abi.FIELD_GROUPS)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / (2 * K)
+        out["configs1_fused_K%d" % K] = {"ms_per_timestep": ms, "frac_of_hbm_6553.9_algorithmic_120B": 120 * n / (ms * 1e-3) / 1e9 / 6553.9,
+                                         "state_checksum": checksum(torch, ens2)}
+        del ens2
     ctx.close()
     del ens
     if args.mesh:

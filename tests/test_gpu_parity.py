@@ -767,6 +767,60 @@ def test_ragged_ensemble_sizes_vs_oracle(ctx, torch_mod, n):
     assert np.array_equal(co[frozen], coords[frozen])                    # frozen on entry: untouched
 
 
+@pytest.mark.parametrize("mode", ["constant", "groups"])
+def test_fused_timesteps_bit_identical_to_single_launches(ctx, torch_mod, mode):
+    """emc_flight_scatter_steps without observable rows = ONE persistent launch that keeps the
+    particles in the warps' queues across timesteps (flight_steps_kernel): the final state equals K
+    single launches bit for bit -- ragged sizes, frozen particles, hot mixed-valley ensembles (all
+    mechanisms), per-group fields -- and the oracle on the same counters."""
+    torch = torch_mod
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    g = helpers.golden_params()["phys"]
+    K, seed = 13, 4711
+    fields = np.array([[0, 0, -300.0], [0, 0, -5000.0], [0, 0, -20000.0], [0, 0, -50000.0]])
+    for n in (1, 33, 4097, 300001):
+        coords, v, dtau = hot_ensemble(n, 60 + n % 5, g)
+        v[::7] = np.where(np.arange(n)[::7] % 3 == 0, -4, v[::7])       # some particles frozen on entry
+        per = max(1, (n + 3) // 4)
+        if mode == "groups":
+            ctx.set_field_groups(fields, per)
+            fm = abi.FIELD_GROUPS
+        else:
+            ctx.set_efield([0, 0, -30000.0])
+            fm = abi.FIELD_CONSTANT
+        a = engine.Ensemble(ctx, n, pid_offset=5).load(coords, v, dtau)
+        b = engine.Ensemble(ctx, n, pid_offset=5).load(coords, v, dtau)
+        for s in range(K):
+            a.step(20 + s, seed, field_mode=fm, observe=False)
+        before = ctx.launch_count()
+        b.advance(20, K, seed, field_mode=fm, check=True)
+        assert ctx.launch_count() - before == 1                     # one persistent launch
+        assert torch.equal(a.state, b.state) and torch.equal(a.valley, b.valley), (mode, n)
+        if n == 4097:                                                  # and both equal the oracle
+            o = helpers.make_oracle(efield=[0, 0, -30000.0])
+            if mode == "groups":
+                o.set_field_groups(fields, per)
+            st = helpers.state_from_coords(coords, v, dtau)
+            for s in range(K):
+                o.timestep(st, orc.philox_stream(seed, 20 + s, 5), threads=4)
+            co, val, dt_ = b.coords()
+            assert np.array_equal(val, st["valley"])
+            ok = val >= 0
+            assert k_err(co[ok, :3], helpers.coords_from_state(st)[ok, :3]) < 1e-6
+    ctx.set_efield(g["efield"])
+    # the general cases keep the launch loop: a tilted field is not "Ex = Ey = +0"
+    ctx.set_efield([100.0, 0, -30000.0])
+    coords, v, dtau = hot_ensemble(1000, 3, g)
+    a = engine.Ensemble(ctx, 1000).load(coords, v, dtau)
+    b = engine.Ensemble(ctx, 1000).load(coords, v, dtau)
+    for s in range(3):
+        a.step(s, seed, observe=False)
+    before = ctx.launch_count()
+    b.advance(0, 3, seed)
+    assert ctx.launch_count() - before == 3 and torch.equal(a.state, b.state)
+    ctx.set_efield(g["efield"])
+
+
 def test_observables_before_step_phase(ctx, torch_mod):
     """emc_set_obs_phase(1): launch c reduces the ensemble as it FOUND it; Ensemble.run_steps shifts
     the rows back, so they must equal step(); last_obs() of the default phase row for row, with the
