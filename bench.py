@@ -612,6 +612,14 @@ def run_ours(args):
     # the whole time loop as ONE call on the host arrays (main_.py:339-403: coords cross PCIe once each
     # way per loop, K timesteps stay in HBM, K observable rows come back): K = the reference's pts = 50
     loop_k, loop_calls = args.e2e_loop_steps, 2
+    # (chunks of 2^22 particles for the loop: 50 launches per chunk amortise better; measured 1.33 vs 1.41 ms
+    # per timestep with 2^21, profiles/r2_e2e_chunks.txt -- the one-timestep-per-call API prefers 2^21)
+    host = (hs.coords_t, hs.valley_t, hs.dtau_t)
+    hs2 = engine.HostStepper(ctx, n, chunk=1 << 22, pid_offset=rank * n)
+    hs2.coords_t.copy_(host[0]); hs2.valley_t.copy_(host[1]); hs2.dtau_t.copy_(host[2])
+    h2d_bytes, d2h_bytes = hs.h2d_bytes, hs.d2h_bytes
+    del hs, host
+    hs = hs2
     hs.run(20_000, loop_k, SEED, field_mode=abi.FIELD_GROUPS)          # warm-up (row buffers)
     barrier()
     l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -623,7 +631,6 @@ def run_ours(args):
     barrier()
     loop_ms = l0.elapsed_time(l1)
 
-    h2d_bytes, d2h_bytes = hs.h2d_bytes, hs.d2h_bytes
     loop_h2d, loop_d2h = hs.run_h2d_bytes(loop_k), hs.run_d2h_bytes(loop_k)
     del hs
     barrier()
