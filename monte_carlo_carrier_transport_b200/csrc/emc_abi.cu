@@ -220,8 +220,10 @@ extern "C" void emc_destroy(EmcCtx *ctx)
     Ctx *c = &ctx->c;
     cudaSetDevice(c->device);
     for (int l = 0; l < EMC_MAX_LAYERS; ++l)
-        for (int v = 0; v < 3; ++v)
+        for (int v = 0; v < 3; ++v) {
             if (c->d_cum_layers[l][v]) cudaFree(c->d_cum_layers[l][v]);
+            if (c->d_thr_layers[l][v]) cudaFree(c->d_thr_layers[l][v]);
+        }
     if (c->d_mech_layers) cudaFree(c->d_mech_layers);
     if (c->d_background_z) cudaFree(c->d_background_z);
     if (c->d_groups) cudaFree(c->d_groups);
@@ -313,6 +315,24 @@ static int upload_tables_layer(Ctx *c, int layer, const double *ek, int32_t n_en
         if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(table)");
         c->dc.mat[layer].cum[v] = dst;
         c->dc.n_mech[v] = n_mech[v];
+        {   // self-scattering thresholds (Mat::thr, select_self_spec<.., THR>): the second-to-last column of
+            // every row and the smallest last column of the valley; one padding entry like the rows
+            std::vector<double> thr((size_t)n_energy + 1, 0.0);
+            double min_last = HUGE_VAL;
+            for (int64_t i = 0; i < n_energy; ++i) {
+                const double *row = cum[v] + i * n_mech[v];
+                thr[(size_t)i] = n_mech[v] > 1 ? row[n_mech[v] - 2] : -HUGE_VAL;
+                if (!(row[n_mech[v] - 1] >= min_last)) min_last = row[n_mech[v] - 1];
+            }
+            double *&dthr = c->d_thr_layers[layer][v];
+            if (dthr) { cudaFree(dthr); dthr = nullptr; }
+            e = cudaMalloc(&dthr, sizeof(double) * thr.size());
+            if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(thresholds)");
+            e = cudaMemcpy(dthr, thr.data(), sizeof(double) * thr.size(), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return fail_cuda(c, e, "cudaMemcpy(thresholds)");
+            c->dc.mat[layer].thr[v] = dthr;
+            c->dc.mat[layer].min_last[v] = min_last;
+        }
         for (int j = 0; j < EMC_MAX_MECH; ++j) {
             c->mech_layers[layer].dE[v][j] = dE[v * EMC_MAX_MECH + j];
             c->mech_layers[layer].trans[v][j] = trans[v * EMC_MAX_MECH + j];

@@ -307,6 +307,49 @@ struct WarpQueues {
     int32_t stage_val[32];
 #endif
 };
+#ifndef EMC_SELF_THRESHOLD
+// 1: the lean kernels decide self-scattering from the 8-byte threshold table (Mat::thr,
+// select_self_spec<.., THR>) and the scatter pass re-runs a parked event from its counters
+#define EMC_SELF_THRESHOLD 1
+#endif
+// the queues of the threshold form: a parked particle carries nothing but itself
+struct WarpQueuesLean {
+    WarpQueue ev;
+    WarpQueue sc;
+};
+// One whole event (threshold form of the lean kernels): the scatter pass of the parked particles
+// (0.1 passes per batch) -- real mechanisms and the cold exits of the select pass (faults, r2 at or
+// above the valley's smallest last column) -- runs scatter_event -- the general, non-speculative
+// event: same arithmetic, same counters, same fault order -- from the particle's event counter.
+// A CALL keeps its registers (the whole table row, sincos, the samplers) and its ~1500 instructions
+// out of the hot loop's allocation and instruction footprint.
+struct EventOut {
+    double kx, ky, kz, lg;      // k' and log(flight uniform) of the free flight that follows
+    int32_t val, f;             // valley after the event; fault code or -1
+};
+#ifndef EMC_COLD_CALL
+// 1: event_cold is a real CALL (smaller loop, fewer registers in the loop's own allocation: the variant
+// for more than 16 warps per SM); 0: inlined.  Measured at 512 threads: call 0.995 ms, inlined 0.959 ms
+// (the ABI marshalling and the convergence barrier around the call cost 2.5 % more instructions).
+#define EMC_COLD_CALL 0
+#endif
+#if EMC_COLD_CALL
+#define EMC_COLD_INLINE __noinline__
+#else
+#define EMC_COLD_INLINE __forceinline__
+#endif
+__device__ EMC_COLD_INLINE EventOut event_cold(const DevConst *P, const Mat *MT, const MechMeta *M, double kx, double ky,
+                                            double kz, int32_t val, uint64_t seed, uint64_t pid, uint32_t step, uint32_t ev)
+{
+    PhiloxStream rng;
+    rng.init(seed, pid, step, ev);
+    EventOut o;
+    int v = val;
+    o.f = scatter_event<false>(*P, *MT, *M, kx, ky, kz, v, rng);
+    o.lg = fast_log(rng.free_flight());
+    o.kx = kx; o.ky = ky; o.kz = kz; o.val = v;
+    return o;
+}
 // EMC_FIELD_MESH_PACKED with field_ahead only (kept out of WarpQueues: shared memory the other modes
 // do not need would shrink their L1 -- the table-row gathers live on its hit rate: 2 KB per warp
 // more cost the configs[1] kernel 3.4 % in r1t)
@@ -565,6 +608,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     constexpr bool REPLAY = Stream::is_replay;
     constexpr bool ZON = LEAN && (FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS);   // zonly known at compile time
     static_assert(!LEAN || (!REPLAY && !EXACT && !DEPOSIT), "LEAN is the Philox / default-libm / no-deposit kernel");
+    constexpr bool THR = LEAN && EMC_SELF_THRESHOLD && !EMC_STAGE_REFILL;
+    using WarpQueues = typename std::conditional<THR, WarpQueuesLean, emc::WarpQueues>::type;
     __shared__ MechMeta Ms[ML ? EMC_MAX_LAYERS : 1];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     WarpQueues *queues = reinterpret_cast<WarpQueues *>(dyn_smem);
@@ -663,20 +708,35 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
 
     // The phases share ONE copy of the event tail, the flight segment, the retirement and the
     // queue pushes (the kernel has to stay inside the 32 KB instruction cache).
-    enum { PH_REFILL = 0, PH_SELECT = 1, PH_SCATTER = 2 };
-    while (true) {
-        // warp-uniform phase choice: a full scatter or select pass if one is possible, else
-        // refill, else drain whatever is left.  A pass pops only what its pushes can hold.
+    enum { PH_REFILL = 0, PH_SELECT = 1, PH_SCATTER = 2, PH_DONE = 3 };
+    // warp-uniform phase choice: a full scatter or select pass if one is possible, else
+    // refill, else drain whatever is left.  A pass pops only what its pushes can hold.
+    int n_sc = 0, n_sel = 0;
+    auto choose_phase = [&]() -> int {
         const int room_ev = QCAP - qn, room_sc = QCAP - qsc;
-        const int n_sc = min(32, min(qsc, room_ev));              // scatter pushes back into ev
-        const int n_sel = min(32, min(qn, room_sc));              // select may push all into sc
-        int phase;
-        if (n_sc == 32) phase = PH_SCATTER;
-        else if (n_sel == 32) phase = PH_SELECT;
-        else if (qn < 32 && next < wlen) phase = PH_REFILL;
-        else if (n_sel > 0 && n_sel >= n_sc) phase = PH_SELECT;
-        else if (n_sc > 0) phase = PH_SCATTER;
-        else break;
+        n_sc = min(32, min(qsc, room_ev));                        // scatter pushes back into ev
+        n_sel = min(32, min(qn, room_sc));                        // select may push all into sc
+        if (n_sc == 32) return PH_SCATTER;
+        if (n_sel == 32) return PH_SELECT;
+        if (qn < 32 && next < wlen) return PH_REFILL;
+        if (n_sel > 0 && n_sel >= n_sc) return PH_SELECT;
+        if (n_sc > 0) return PH_SCATTER;
+        return PH_DONE;
+    };
+#ifndef EMC_ROTATE_LOOP
+// 1: the phase of the NEXT pass is chosen at the end of a pass, so that the back edge can jump straight
+// into that phase's block (one far taken branch per pass instead of two).  Measured: no gain (0.974 vs
+// 0.969 ms, profiles/r2v_ab_*); off.
+#define EMC_ROTATE_LOOP 0
+#endif
+#if EMC_ROTATE_LOOP
+    int phase = choose_phase();
+    while (phase != PH_DONE) {
+#else
+    while (true) {
+        const int phase = choose_phase();
+        if (phase == PH_DONE) break;
+#endif
         Particle p;
         Stream rng;
         uint32_t s0 = 0;
@@ -791,9 +851,11 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             if (act) {
                 queue_pop<FIELD>(Qp, slot, p, s0);
                 if (EARLY_GF) gfz = __ldg(P.field_groups + 3 * p.grp + 2);
-                if (!sel) {
-                    const double2 er = WQ.sc_er[slot];
-                    mech = WQ.sc_mech[slot]; e_np = er.x; r_az = er.y;
+                if constexpr (!THR) {
+                    if (!sel) {
+                        const double2 er = WQ.sc_er[slot];
+                        mech = WQ.sc_mech[slot]; e_np = er.x; r_az = er.y;
+                    }
                 }
             }
             __syncwarp();
@@ -811,7 +873,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     layer = 0;
                 } else if (sel && SPEC) {
                     bool is_self;
-                    f = select_self_spec<Stream, LEAN>(P, MT, M, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
+                    f = select_self_spec<Stream, LEAN, THR>(P, MT, M, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg, A.sched_zero);
+                    // THR: a cold exit (fault, r2 >= min_last) is parked like a real mechanism -- the scatter
+                    // pass runs the whole event literally, whatever it turns out to be
+                    if (THR && f == EMC_SELECT_COLD) { f = -1; is_self = false; }
                     if (f < 0) {
                         if (is_self) tail = true;
                         else { park = true; s0 = rng.state(); }
@@ -829,6 +894,15 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                             s0 = rng.state();
                         }
                     }
+                } else if (THR) {
+                    // scatter pass of the threshold form: the parked event again from its counters, now
+                    // with the whole table row (a real mechanism: polar sampler, rotation :1059-1089)
+                    if constexpr (THR) {
+                        const EventOut o = event_cold(&P, &MT, &M, p.kx, p.ky, p.kz, v, A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
+                        f = o.f; lg = o.lg;
+                        if (f < 0) { p.kx = o.kx; p.ky = o.ky; p.kz = o.kz; v = o.val; }
+                    }
+                    tail = true;
                 } else {
                     // scatter pass: polar sampler, rotation (:1059-1089)
                     const double r_pol = rng.draw_polar(true);
@@ -913,10 +987,11 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             const unsigned km = __ballot_sync(FULL, park);
             const int slot = qsc + __popc(km & lt_mask);
             queue_push_if<FIELD>(WQ.sc, slot, p, s0, park);
-            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.u32 [%0], %1;\n\t"
-                         "@q st.shared.v2.f64 [%2], {%3, %4};\n\t}"
-                         ::"r"(smem_u32(&WQ.sc_mech[0]) + (uint32_t)slot * 4u), "r"(mech),
-                         "r"(smem_u32(&WQ.sc_er[0]) + (uint32_t)slot * 16u), "d"(e_np), "d"(r_az), "r"((uint32_t)park) : "memory");
+            if constexpr (!THR)
+                asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.u32 [%0], %1;\n\t"
+                             "@q st.shared.v2.f64 [%2], {%3, %4};\n\t}"
+                             ::"r"(smem_u32(&WQ.sc_mech[0]) + (uint32_t)slot * 4u), "r"(mech),
+                             "r"(smem_u32(&WQ.sc_er[0]) + (uint32_t)slot * 16u), "d"(e_np), "d"(r_az), "r"((uint32_t)park) : "memory");
             qsc += __popc(km);
         }
 #else
@@ -929,12 +1004,15 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             if (park) {
                 const int slot = qsc + __popc(km & lt_mask);
                 queue_push<FIELD>(WQ.sc, slot, p, s0);
-                WQ.sc_mech[slot] = mech; WQ.sc_er[slot] = make_double2(e_np, r_az);
+                if constexpr (!THR) { WQ.sc_mech[slot] = mech; WQ.sc_er[slot] = make_double2(e_np, r_az); }
             }
             qsc += __popc(km);
         }
 #endif
         __syncwarp();
+#if EMC_ROTATE_LOOP
+        phase = choose_phase();
+#endif
         }
 
     if (DEPOSIT && A.smem_cells > 0) {
@@ -951,6 +1029,8 @@ template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML, bool LEAN 
 static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
     auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT, ML, LEAN>;
+    // the threshold form's queues carry no park fields (launch_flight sized `smem` for the general ones)
+    if (LEAN && EMC_SELF_THRESHOLD && !EMC_STAGE_REFILL) smem -= (sizeof(WarpQueues) - sizeof(WarpQueuesLean)) * (FLIGHT_THREADS / 32);
     // persistent grid: exactly the blocks that are resident at once (one wave), unless the
     // ensemble is too small to give every block a full tile.  The attribute / occupancy queries
     // are cached per kernel variant and device (they cost tens of microseconds per launch).
@@ -1212,14 +1292,19 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
                 double e_np = 0.0, r_az = 0.0;
                 if (sel) {
                     bool is_self;
-                    f = select_self_spec<PhiloxStream, true>(P, MT, Ms, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
+                    f = select_self_spec<PhiloxStream, true, EMC_SELF_THRESHOLD != 0>(P, MT, Ms, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg, A.sched_zero);
+                    // a cold exit (fault, r2 >= min_last) is parked like a real mechanism: the scatter pass
+                    // runs the whole event literally, whatever it turns out to be
+                    if (EMC_SELF_THRESHOLD && f == EMC_SELECT_COLD) { f = -1; is_self = false; }
                     if (f < 0) {
                         if (is_self) tail = true;
                         else park = true;                     // the event index in s0 is unchanged: the scatter pass redoes the event
                     }
                 } else {
-                    f = scatter_event<false>(P, MT, Ms, p.kx, p.ky, p.kz, v, rng);
-                    lg = fast_log(rng.free_flight());
+                    const EventOut o = event_cold(&P, &MT, &Ms, p.kx, p.ky, p.kz, v, A.seed, A.pid_offset + (uint64_t)i,
+                                                  A.step + (s0 >> 16), s0 & 0xffffu);
+                    f = o.f; lg = o.lg;
+                    if (f < 0) { p.kx = o.kx; p.ky = o.ky; p.kz = o.kz; v = o.val; }
                     tail = f < 0;
                 }
                 // a faulted particle is written back at once, frozen (dtau keeps dte): only live valleys

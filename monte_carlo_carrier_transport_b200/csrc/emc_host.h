@@ -40,6 +40,7 @@ struct FlightArgs {
     int32_t obs_before;          // emc_set_obs_phase: reduce the observables of the state as loaded
     int32_t bulk;                // refill batches arrive by bulk async copies (launch_flight decides: aligned rows)
     const MechMeta *mech_layers; // multi-layer: device array of n_layers mechanism-metadata blocks
+    uint32_t sched_zero;         // always 0 (the callers memset the struct): scheduling anchor, see select_self_spec
 };
 
 struct Ctx {
@@ -61,6 +62,7 @@ struct Ctx {
     bool zonly_groups = false;    // every field group has Ex = Ey = +0
     int batch_layer = 0;          // emc_select_layer: material of the single-function batches
     double *d_cum_layers[EMC_MAX_LAYERS][3] = {};
+    double *d_thr_layers[EMC_MAX_LAYERS][3] = {};   // self-scattering thresholds (Mat::thr)
     double *d_background_z = nullptr;   // emc_set_background_profile
     int background_nz = 0;
     int device = 0;

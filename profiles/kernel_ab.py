@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--mesh", action="store_true", help="also time the mesh-field flight (coupled configs)")
+    ap.add_argument("--no-fused", action="store_true", help="skip the K-timesteps-per-launch runs")
     ap.add_argument("--tag", default=os.path.basename(os.environ.get("EMC_LIB", "default")))
     args = ap.parse_args()
     import torch
@@ -63,7 +64,7 @@ def main():
                        "state_checksum": checksum(torch, ens)}
     ctx.set_obs_phase(False)
     # the same workload with K timesteps per persistent launch (no per-step observables)
-    for K in (10, 50):
+    for K in (() if args.no_fused else (10, 50)):
         ens2 = engine.Ensemble(ctx, n).init(bench.SEED)
         ens2.advance(0, K, bench.SEED, field_mode=abi.FIELD_GROUPS)          # warm-up
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
