@@ -75,6 +75,20 @@ static double layer_threshold(const EmcLayer *layers, int n, int l)
     return d;
 }
 
+// single-precision constants of select_self_thr's index guess (needs the energy grid: called again at table upload)
+static void fill_guess(Ctx *c)
+{
+    DevConst &d = c->dc;
+    for (int l = 0; l < d.n_layers; ++l) {
+        Mat &m = d.mat[l];
+        for (int v = 0; v < 3; ++v) {
+            m.g_c1[v] = (float)(d.hbar2 / m.den[v]);
+            m.g_4a[v] = (float)m.four_a[v];
+            m.g_k[v] = d.ek_step > 0 ? (float)(1.0 / (m.two_a[v] * d.ek_step)) : 0.0f;
+        }
+    }
+}
+
 static void fill_devconst(Ctx *c)
 {
     const EmcParams &p = c->params;
@@ -122,6 +136,7 @@ static void fill_devconst(Ctx *c)
     d.r_hbar = 1 / p.hbar;
     d.r_hbar2 = 1 / d.hbar2;
     d.z_cyclic = p.z_cyclic != 0;
+    fill_guess(c);
 }
 
 // the single layer EmcParams describes (init_.py:127: layers = [layer0])
@@ -353,6 +368,7 @@ static int upload_tables_layer(Ctx *c, int layer, const double *ek, int32_t n_en
     c->dc.ek_step = step;
     c->dc.inv_ek_step = 1 / step;
     c->dc.e_max = ek[n_energy - 1];
+    fill_guess(c);
     c->layer_tables[layer] = true;
     {   // the lean flight kernel's assumption (select_self_spec<LEAN>): in every valley of every layer the
         // last column is the ONLY self-scattering mechanism, changes neither energy nor valley

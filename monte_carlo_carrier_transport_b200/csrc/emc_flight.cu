@@ -28,6 +28,7 @@ struct ObsAcc {
     __device__ __forceinline__ void count_valley(int val) { c[0] += (val == 0); c[1] += (val == 1); c[2] += (val == 2); }
     __device__ __forceinline__ void count_fault() { c[3]++; }
     __device__ __forceinline__ void count_segment() { c[4]++; }
+    __device__ __forceinline__ void derive_segments() { c[4] = c[0] + c[1] + c[2] + c[5]; }
     __device__ __forceinline__ void count_event() { c[5]++; }
     __device__ __forceinline__ long long counter(int k) const { return (long long)c[k]; }
 };
@@ -55,6 +56,7 @@ struct ObsAccShared {
     }
     __device__ __forceinline__ void count_fault() { v2f += 1u << 16; }
     __device__ __forceinline__ void count_segment() { seg++; }
+    __device__ __forceinline__ void derive_segments() { seg = (v01 & 0xffffu) + (v01 >> 16) + (v2f & 0xffffu) + ev; }
     __device__ __forceinline__ void count_event() { ev++; }
     __device__ __forceinline__ long long counter(int k) const
     {
@@ -241,6 +243,12 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 // the ragged last batch of a slice and unaligned callers take the per-lane loads below.
 #define EMC_BULK_REFILL 1
 #endif
+#ifndef EMC_REFILL_TILES
+// tiles per warp: 1 = the batch after the current one is in flight; 2 = two batches ahead (the mbarrier wait is
+// 3.6 % of the stall samples in profiles/r2x).  Measured: 2 tiles 0.949 ms, 1 tile 0.945 ms (profiles/r2z_ab_*):
+// the wait is the try_wait's own latency, not late data; the second tile only costs L1.
+#define EMC_REFILL_TILES 1
+#endif
 struct alignas(16) RefillTile {              // bulk-copy destinations are 16-byte aligned: the size is a multiple of 16
     double row[7][32];                       // kx ky kz x y z dtau of the next batch
     int32_t val[32];
@@ -310,7 +318,9 @@ struct WarpQueues {
 #ifndef EMC_SELF_THRESHOLD
 // 1: the lean kernels decide self-scattering from the 8-byte threshold table (Mat::thr,
 // select_self_spec<.., THR>) and the scatter pass re-runs a parked event from its counters
-#define EMC_SELF_THRESHOLD 1
+// 2: ... from the thresholds of the three rows around a single-precision GUESS of the index
+// (select_self_thr): no exact index and no load at the end of a dependency chain in the select pass
+#define EMC_SELF_THRESHOLD 2
 #endif
 // the queues of the threshold form: a parked particle carries nothing but itself
 struct WarpQueuesLean {
@@ -532,6 +542,26 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
 #ifndef EMC_LEAN_KERNEL
 #define EMC_LEAN_KERNEL 1
 #endif
+#ifndef EMC_REFILL_FLIES
+#define EMC_REFILL_FLIES 1
+#endif
+#ifndef EMC_SCATTER_UNLIKELY
+// 1: the scatter pass (0.1 passes per batch, but half of the loop's instructions) is marked unlikely, so that the
+// code generator places it after the loop's hot blocks (refill, select, shared tail stay contiguous)
+#define EMC_SCATTER_UNLIKELY 1
+#endif
+#if EMC_SCATTER_UNLIKELY
+#define EMC_LIKELY_SELECT(x) __builtin_expect(!!(x), 1)
+#else
+#define EMC_LIKELY_SELECT(x) (x)
+#endif
+#ifndef EMC_PUSH_FIRST
+#define EMC_PUSH_FIRST 1
+#endif
+#ifndef EMC_PARK_UNCOND
+// 1: the (predicated) push into the scatter queue is issued in every pass instead of behind a branch on the phase
+#define EMC_PARK_UNCOND 0
+#endif
 #ifndef EMC_PREDICATED_TAIL
 // 1: the write-back of a finished particle and the queue pushes are predicated stores instead of
 // branches around them.  The loop tail ran at 130 stall samples per instruction against 43 in the
@@ -619,7 +649,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     FieldStage *fstages = reinterpret_cast<FieldStage *>(dyn_smem + sizeof(WarpQueues) * (FLIGHT_THREADS / 32));
     constexpr size_t OBS_BYTES = EMC_OBS_SMEM ? sizeof(double) * 5 * FLIGHT_THREADS : 0;
     const bool BULK = EMC_BULK_REFILL && A.bulk;                  // warp-uniform (kernel argument)
-    const size_t rt_bytes = BULK ? sizeof(RefillTile) : 0;
+    const size_t rt_bytes = BULK ? sizeof(RefillTile) * EMC_REFILL_TILES : 0;
     RefillTile *rtiles = reinterpret_cast<RefillTile *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes) * (FLIGHT_THREADS / 32));
     double *obs_columns = reinterpret_cast<double *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes + rt_bytes) * (FLIGHT_THREADS / 32));
     unsigned int *smesh = reinterpret_cast<unsigned int *>(dyn_smem + (sizeof(WarpQueues) + fs_bytes + rt_bytes) * (FLIGHT_THREADS / 32) + OBS_BYTES);
@@ -670,17 +700,23 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     uint32_t next = 0;
     const uint32_t wlen = (uint32_t)(wend - wstart);
     const uint32_t w0 = (uint32_t)wstart;
-    RefillTile &RT = rtiles[BULK ? warp : 0];                     // only dereferenced when BULK
-    uint32_t rt_parity = 0;                                       // phase of the tile's mbarrier the next wait expects
-    bool rt_pending = false;                                      // a full batch at `next` is in flight / has landed
+    RefillTile *RTW = rtiles + (BULK ? warp * EMC_REFILL_TILES : 0);      // only dereferenced when BULK
+    // the full batches of the slice are issued in order, EMC_REFILL_TILES ahead, into the tiles in turn:
+    // batch b uses tile b % TILES and the mbarrier phase (b / TILES) & 1
+    uint32_t rt_count = 0;                                        // bulk batches consumed so far
     if (BULK) {
         if (elect_one()) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&RT.bar)) : "memory");
+#pragma unroll
+            for (int t = 0; t < EMC_REFILL_TILES; ++t)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&RTW[t].bar)) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        rt_pending = wlen >= 32u;
-        if (rt_pending && elect_one()) refill_issue(RT, A, w0);
+        if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < EMC_REFILL_TILES; ++t)
+                if (wlen >= 32u * (t + 1)) refill_issue(RTW[t], A, w0 + 32u * t);
+        }
     }
 #if EMC_STAGE_REFILL
     stage_batch(WQ, A, wstart + next + lane, wend, lane);
@@ -757,6 +793,30 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         double dt_seg = 0.0;
         double nx_ = 0.0, ny_ = 0.0, nz_ = 0.0;                   // AHEAD: position of the lane's particle in the next batch
         bool ahead = false;
+        // one flight segment of the lane's particle (main_.py:367 / :373 / :388)
+        auto flight_segment = [&](bool staged) {
+            double efx, efy, efz;
+            if (EARLY_GF) { efx = 0.0; efy = 0.0; efz = gfz; }
+            else field_at<FIELD, ZON>(P, A, p, cell, efx, efy, efz, FS, lane, staged);
+            const Mat &MT = P.mat[ML ? layer : 0];
+            const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
+            if (FIELD == EMC_FIELD_MESH_XZ)
+                carrier_drift<2>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
+            else if ((FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) && (ZON || P.zonly))
+                carrier_drift<1>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
+            else
+                carrier_drift<0>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
+            // LEAN: every live particle of the ensemble as loaded flies one first segment and every event is
+            // followed by one more (a Philox stream never overflows): n_segments = n_valley[0..2] of the
+            // before-step observables + n_events, added up after the loop -- one loop-carried register less
+            if (!LEAN) acc.count_segment();
+        };
+        // REFILL_FLIES (lean kernel, constant / group fields): the refill pass has its own copy of the flight
+        // segment, in ONE basic block with the observables of the loaded state -- the two dependency chains
+        // (|k|^2 -> E -> E_np -> sums, 30 serial fp64 operations; free-flight time -> drift -> boundary test) are
+        // independent, but as long as the flight lived in the shared tail they ran one after the other, each at one
+        // instruction per 8 cycles (profiles/r2x: the refill block 75, the tail 176 stall samples per instruction).
+        constexpr bool REFILL_FLIES = EMC_REFILL_FLIES && LEAN && !MESHF;
         if (phase == PH_REFILL) {
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
             i = w0 + next + lane;
@@ -768,17 +828,18 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
 #if EMC_STAGE_REFILL
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
-            if (BULK && rt_pending) {
-                // the whole batch sits in the tile (issued one refill ago): act is true for every lane
-                refill_wait(RT, rt_parity);
-                rt_parity ^= 1u;
+            if (BULK && next + 32u <= wlen) {
+                // a full batch: it sits in its tile (issued EMC_REFILL_TILES refills ago); act is true for every lane
+                RefillTile &RT = RTW[EMC_REFILL_TILES == 1 ? 0 : rt_count % EMC_REFILL_TILES];
+                refill_wait(RT, (rt_count / EMC_REFILL_TILES) & 1u);
+                ++rt_count;
                 p.kx = RT.row[0][lane]; p.ky = RT.row[1][lane]; p.kz = RT.row[2][lane];
                 p.x = RT.row[3][lane]; p.y = RT.row[4][lane]; p.z = RT.row[5][lane];
                 p.dte = RT.row[6][lane];
                 p.val = RT.val[lane];
                 __syncwarp();                                     // every lane has read its slot: the tile may be refilled
-                rt_pending = next + 64u <= wlen;                  // the following batch is a full one, too
-                if (rt_pending && elect_one()) refill_issue(RT, A, w0 + next + 32u);
+                // the batch EMC_REFILL_TILES further on, if it is a full one, too
+                if (next + 32u * (EMC_REFILL_TILES + 1) <= wlen && elect_one()) refill_issue(RT, A, w0 + next + 32u * EMC_REFILL_TILES);
             } else if (act) {
                 p.kx = A.kx[i]; p.ky = A.ky[i]; p.kz = A.kz[i];
                 p.x = A.x[i]; p.y = A.y[i]; p.z = A.z[i];
@@ -808,12 +869,26 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 // obs_before: the observables of the ensemble AS LOADED (= the result of the previous
                 // timestep) are reduced here, where all 32 lanes are busy, instead of at retirement
                 // (17 of 32 lanes on average); a time loop reads the same rows one launch later
+                if (REFILL_FLIES) {
+                    // (the sums are accumulated whether or not this launch reports them: a branch on A.obs would
+                    // split the block; the lean kernel never reduces at retirement)
+                    if (p.val >= 0) {
+                        const double dte = p.dte;                 // :361
+                        if (dte >= dt) { dt_seg = dt; p.dte = dte - dt; }      // :363-367, :390-391
+                        else { dt_seg = dte; pend = true; }       // :370-373
+                        obs_particle(P, P.mat[ML ? layer : 0], acc, p.kx, p.ky, p.kz, p.z, p.val);
+                        flight_segment(false);
+                    } else {
+                        acc.count_fault();
+                    }
+                } else {
                 if (A.obs && A.obs_before) obs_particle(P, P.mat[ML ? layer : 0], acc, p.kx, p.ky, p.kz, p.z, p.val);
                 if (p.val >= 0) {                                 // else frozen after a fault
                     const double dte = p.dte;                     // :361
                     fly = true;
                     if (dte >= dt) { dt_seg = dt; p.dte = dte - dt; }      // :363-367, :390-391
                     else { dt_seg = dte; pend = true; }           // :370-373
+                }
                 }
             }
             next += 32;
@@ -871,9 +946,14 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 if (ML && layer < 0) {
                     f = EMC_FAULT_OUTSIDE;
                     layer = 0;
+                } else if (EMC_LIKELY_SELECT(sel) && SPEC && THR && EMC_SELF_THRESHOLD == 2) {
+                    // finished here (a certain, clean self-scattering event) or parked for the literal path
+                    f = -1;
+                    if (select_self_thr<Stream>(P, MT, p.kx, p.ky, p.kz, v, rng, lg)) tail = true;
+                    else { park = true; s0 = rng.state(); }
                 } else if (sel && SPEC) {
                     bool is_self;
-                    f = select_self_spec<Stream, LEAN, THR>(P, MT, M, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg, A.sched_zero);
+                    f = select_self_spec<Stream, LEAN, THR>(P, MT, M, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
                     // THR: a cold exit (fault, r2 >= min_last) is parked like a real mechanism -- the scatter
                     // pass runs the whole event literally, whatever it turns out to be
                     if (THR && f == EMC_SELECT_COLD) { f = -1; is_self = false; }
@@ -936,20 +1016,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             }
         }
         if (AHEAD_OK && AHEAD && phase == PH_REFILL) asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (fly) {                                                // :367 / :373 / :388
-            double efx, efy, efz;
-            if (EARLY_GF) { efx = 0.0; efy = 0.0; efz = gfz; }
-            else field_at<FIELD, ZON>(P, A, p, cell, efx, efy, efz, FS, lane, AHEAD_OK && AHEAD && phase == PH_REFILL);
-            const Mat &MT = P.mat[ML ? layer : 0];
-            const double dtm = div_const(dt_seg, MT.mass[p.val], MT.r_mass[p.val]);
-            if (FIELD == EMC_FIELD_MESH_XZ)
-                carrier_drift<2>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
-            else if ((FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) && (ZON || P.zonly))
-                carrier_drift<1>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
-            else
-                carrier_drift<0>(P, p.kx, p.ky, p.kz, p.x, p.y, p.z, efx, efy, efz, dt_seg, dtm);
-            acc.count_segment();
-        }
+        if (fly) flight_segment(AHEAD_OK && AHEAD && phase == PH_REFILL);   // :367 / :373 / :388
         if (phase == PH_REFILL && AHEAD) {
             // the rs slots of this batch have been read (own lane, program order): gather the next one
             if (ahead) {
@@ -960,6 +1027,27 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             field_staged = next < wlen;           // `next` already points at that batch
         }
 #if EMC_PREDICATED_TAIL
+        // queue pushes FIRST, write-back last (EMC_PUSH_FIRST): the ballot that followed the eight scattered
+        // global stores waited ~50 cycles for them to leave the load/store queue (its destination register
+        // was still an address operand of one of them, profiles/r2x), and the loop's back edge another ~75 for
+        // the shared-memory stores; in this order the global stores drain behind the branch
+        auto push_queues = [&]() {
+            const unsigned pm = __ballot_sync(FULL, pend);
+            queue_push_if<FIELD>(WQ.ev, qn + __popc(pm & lt_mask), p, s0, pend);
+            qn += __popc(pm);
+            if (EMC_PARK_UNCOND || phase == PH_SELECT) {
+                const unsigned km = __ballot_sync(FULL, park);
+                const int slot = qsc + __popc(km & lt_mask);
+                queue_push_if<FIELD>(WQ.sc, slot, p, s0, park);
+                if constexpr (!THR)
+                    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.u32 [%0], %1;\n\t"
+                                 "@q st.shared.v2.f64 [%2], {%3, %4};\n\t}"
+                                 ::"r"(smem_u32(&WQ.sc_mech[0]) + (uint32_t)slot * 4u), "r"(mech),
+                                 "r"(smem_u32(&WQ.sc_er[0]) + (uint32_t)slot * 16u), "d"(e_np), "d"(r_az), "r"((uint32_t)park) : "memory");
+                qsc += __popc(km);
+            }
+        };
+        if (EMC_PUSH_FIRST) push_queues();
         {
             const bool done = act && !pend && !park;
             int val = p.val, lay = 0;
@@ -980,20 +1068,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                         atomicAdd(reinterpret_cast<unsigned long long *>(A.mesh) + c, 1ull); });
             }
         }
-        const unsigned pm = __ballot_sync(FULL, pend);
-        queue_push_if<FIELD>(WQ.ev, qn + __popc(pm & lt_mask), p, s0, pend);
-        qn += __popc(pm);
-        if (phase == PH_SELECT) {
-            const unsigned km = __ballot_sync(FULL, park);
-            const int slot = qsc + __popc(km & lt_mask);
-            queue_push_if<FIELD>(WQ.sc, slot, p, s0, park);
-            if constexpr (!THR)
-                asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.u32 [%0], %1;\n\t"
-                             "@q st.shared.v2.f64 [%2], {%3, %4};\n\t}"
-                             ::"r"(smem_u32(&WQ.sc_mech[0]) + (uint32_t)slot * 4u), "r"(mech),
-                             "r"(smem_u32(&WQ.sc_er[0]) + (uint32_t)slot * 16u), "d"(e_np), "d"(r_az), "r"((uint32_t)park) : "memory");
-            qsc += __popc(km);
-        }
+        if (!EMC_PUSH_FIRST) push_queues();
 #else
         if (act && !pend && !park) retire<REPLAY, DEPOSIT, ML>(P, A, i, p, s0, acc, smesh);
         const unsigned pm = __ballot_sync(FULL, pend);
@@ -1022,6 +1097,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             if (v) atomicAdd(reinterpret_cast<unsigned long long *>(A.mesh) + t, (unsigned long long)v);
         }
     }
+    if (LEAN) acc.derive_segments();
     if (A.obs) obs_block_reduce_and_finish(acc, A.partials, A.ticket, A.obs);
 }
 
@@ -1094,7 +1170,7 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
         // field gathers live on -- measured 0.745 ms with, 0.721 ms without on 1024 x 1 x 1024, profiles/ab_r2e)
         const bool mesh_field = field_mode == EMC_FIELD_MESH || field_mode == EMC_FIELD_MESH_PACKED || field_mode == EMC_FIELD_MESH_XZ;
         A.bulk = EMC_BULK_REFILL && (bits & 15) == 0 && !ctx->no_bulk_refill && !replay && (!mesh_field || ctx->bulk_mesh);
-        if (A.bulk) smem += sizeof(RefillTile) * (FLIGHT_THREADS / 32);
+        if (A.bulk) smem += sizeof(RefillTile) * EMC_REFILL_TILES * (FLIGHT_THREADS / 32);
     }
     if (EMC_OBS_SMEM) {
         smem += sizeof(double) * 5 * FLIGHT_THREADS;
@@ -1290,9 +1366,13 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
                 rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step + (s0 >> 16), s0 & 0xffffu);
                 int v = p.val, f, mech = 0;
                 double e_np = 0.0, r_az = 0.0;
-                if (sel) {
+                if (sel && EMC_SELF_THRESHOLD == 2) {
+                    f = -1;
+                    if (select_self_thr<PhiloxStream>(P, MT, p.kx, p.ky, p.kz, v, rng, lg)) tail = true;
+                    else park = true;                         // the event index in s0 is unchanged: the scatter pass redoes the event
+                } else if (sel) {
                     bool is_self;
-                    f = select_self_spec<PhiloxStream, true, EMC_SELF_THRESHOLD != 0>(P, MT, Ms, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg, A.sched_zero);
+                    f = select_self_spec<PhiloxStream, true, EMC_SELF_THRESHOLD != 0>(P, MT, Ms, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
                     // a cold exit (fault, r2 >= min_last) is parked like a real mechanism: the scatter pass
                     // runs the whole event literally, whatever it turns out to be
                     if (EMC_SELF_THRESHOLD && f == EMC_SELECT_COLD) { f = -1; is_self = false; }

@@ -40,7 +40,6 @@ struct FlightArgs {
     int32_t obs_before;          // emc_set_obs_phase: reduce the observables of the state as loaded
     int32_t bulk;                // refill batches arrive by bulk async copies (launch_flight decides: aligned rows)
     const MechMeta *mech_layers; // multi-layer: device array of n_layers mechanism-metadata blocks
-    uint32_t sched_zero;         // always 0 (the callers memset the struct): scheduling anchor, see select_self_spec
 };
 
 struct Ctx {
