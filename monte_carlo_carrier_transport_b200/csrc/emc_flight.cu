@@ -543,6 +543,8 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
 #define EMC_LEAN_KERNEL 1
 #endif
 #ifndef EMC_REFILL_FLIES
+// (2: in the mesh-field modes, too -- measured: no gain there, 0.631 vs 0.629 ms on 1024 x 1 x 1024, profiles/r2ae_ab_*:
+// the refill of those modes waits for its field record, not for arithmetic)
 #define EMC_REFILL_FLIES 1
 #endif
 #ifndef EMC_SCATTER_UNLIKELY
@@ -816,7 +818,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         // (|k|^2 -> E -> E_np -> sums, 30 serial fp64 operations; free-flight time -> drift -> boundary test) are
         // independent, but as long as the flight lived in the shared tail they ran one after the other, each at one
         // instruction per 8 cycles (profiles/r2x: the refill block 75, the tail 176 stall samples per instruction).
-        constexpr bool REFILL_FLIES = EMC_REFILL_FLIES && LEAN && !MESHF;
+        constexpr bool REFILL_FLIES = EMC_REFILL_FLIES && LEAN && (EMC_REFILL_FLIES > 1 || !MESHF);
         if (phase == PH_REFILL) {
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
             i = w0 + next + lane;
@@ -877,7 +879,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                         if (dte >= dt) { dt_seg = dt; p.dte = dte - dt; }      // :363-367, :390-391
                         else { dt_seg = dte; pend = true; }       // :370-373
                         obs_particle(P, P.mat[ML ? layer : 0], acc, p.kx, p.ky, p.kz, p.z, p.val);
-                        flight_segment(false);
+                        if (AHEAD_OK && AHEAD) asm volatile("cp.async.wait_group 0;" ::: "memory");   // the staged field record
+                        flight_segment(AHEAD_OK && AHEAD);
                     } else {
                         acc.count_fault();
                     }
@@ -949,6 +952,9 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 } else if (EMC_LIKELY_SELECT(sel) && SPEC && THR && EMC_SELF_THRESHOLD == 2) {
                     // finished here (a certain, clean self-scattering event) or parked for the literal path
                     f = -1;
+                    // (Tried: the next free flight and its flight segment inside this block as well, speculatively on
+                    // the self-scattering k' and committed with selects -- 0.938 vs 0.918 ms, profiles/r2ac_ab_*: the
+                    // segment depends on k', so it only lengthens the block's longest chain.)
                     if (select_self_thr<Stream>(P, MT, p.kx, p.ky, p.kz, v, rng, lg)) tail = true;
                     else { park = true; s0 = rng.state(); }
                 } else if (sel && SPEC) {
