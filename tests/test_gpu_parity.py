@@ -917,3 +917,67 @@ def test_interior_only_mesh_updates(torch_mod):
         assert torch.equal(m.rho_pad, ref_rho) and torch.equal(m.e4, ref_e4), rep
     assert float(m.rho_pad[0].abs().max()) == 0.0 and float(m.e4[:, 0].abs().max()) == 0.0
     c.close()
+
+
+def test_threshold_select_edge_cases_vs_oracle(torch_mod):
+    """The lean kernels decide self-scattering from three 8-byte thresholds around a single-precision
+    GUESS of the table index (select_self_thr) and leave everything else to the literal event of the
+    scatter pass.  Edge cases of that split, against the oracle AND against the general kernel:
+    rows whose last column is below 1 (r2 at or above it is the reference's "no mechanism" case), energies
+    at both ends of the grid and beyond it, k = 0, NaN, k along z (arcsin domain), kx = 0 (exact-zero
+    component of k')."""
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    g = helpers.golden_params()["phys"]
+    ek, tabs, mech = helpers.host_tables()
+    tabs = [t.copy() for t in tabs]
+    for t in tabs:
+        t[::3] *= 0.9995                               # every third row: the cumulative rates end at 0.9995
+        t[1::7, :-1] *= 0.5                            # and neighbouring thresholds that differ by a factor of two
+    mech_l = [list(zip(m[1].tolist(), m[2].tolist(), m[3].tolist())) for m in mech]
+    n, steps, seed, off = 200000, 4, 4711, 77
+    coords, v, dtau = hot_ensemble(n, 97, g)
+    kth = np.sqrt(2 * g["mass"][0] * g["q"] * 0.03) / g["hbar"]
+    coords[0:200, :3] *= 1e-4                          # energies far below the first grid point
+    coords[200:400, :3] *= 30.0                        # far above the last one (> 2 eV)
+    coords[400:420, :3] = 0.0                          # zero energy (scatter_.py:47)
+    coords[420:440, 0] = np.nan                        # NaN energy (scatter_.py:45)
+    coords[440:460, :2] = 0.0                          # k along z: sin(p0) = 0 (arcsin domain)
+    coords[440:460, 2] = kth
+    coords[460:480, 0] = 0.0                           # kx = 0: k'_x is an exact zero (scatter_.py:1079)
+    dtau[:480] = 1e-17                                 # these all meet an event in the first timestep
+    o = orc.Oracle(dict(g), ek, tabs, mech_l)
+    st = helpers.state_from_coords(coords, v, dtau)
+    p = engine.params_from_dict(g)
+    lean = engine.Context(p, device=0, tables=(ek, tabs, mech))
+    assert lean.describe()["lean"] == "1"
+    os.environ["EMC_LEAN"] = "0"
+    try:
+        general = engine.Context(p, device=0, tables=(ek, tabs, mech))
+    finally:
+        del os.environ["EMC_LEAN"]
+    assert general.describe()["lean"] == "0"
+    a = engine.Ensemble(lean, n, pid_offset=off).load(coords, v, dtau)
+    b = engine.Ensemble(general, n, pid_offset=off).load(coords, v, dtau)
+    rows_a = a.run_steps(0, steps, seed)               # before-step observables: the lean instantiation
+    rows_b = b.run_steps(0, steps, seed)
+    c = engine.Ensemble(lean, n, pid_offset=off).load(coords, v, dtau)
+    c.advance(0, steps, seed)                          # K timesteps per launch: the same select pass
+    want = []
+    for s in range(steps):
+        want.append(o.timestep(st, orc.philox_stream(seed, s, off), threads=8))
+    for s in range(steps):
+        for key in ("n_valley", "n_fault", "n_segments", "n_events"):
+            assert rows_a[s][key] == rows_b[s][key] == want[s][key], (s, key)
+    ca, cb, cc = a.coords(), b.coords(), c.coords()
+    for x, y, z in zip(ca, cb, cc):
+        assert np.array_equal(x, y, equal_nan=True) and np.array_equal(x, z, equal_nan=True)
+    assert np.array_equal(ca[1], st["valley"])         # every valley and every fault code
+    faults = {name: int((ca[1] == -(1 + f)).sum()) for f, name in enumerate(abi.FAULT_NAMES)}
+    # (k = 0 picks up a tiny kz from the field on its first flight and ends as a k-along-z domain fault)
+    assert faults["no_mechanism"] > 0 and faults["nan"] >= 20 and faults["domain"] >= 20 and faults["zero_k"] > 0, faults
+    ok = ca[1] >= 0
+    ref = helpers.coords_from_state(st)
+    kerr = np.max(np.abs(ca[0][ok, :3] - ref[ok, :3]), axis=1) / np.linalg.norm(ref[ok, :3], axis=1)
+    assert np.quantile(kerr, 0.999) < TRAJ_RTOL and kerr.max() < OUTLIER_MAX
+    lean.close()
+    general.close()
