@@ -205,6 +205,8 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
         c->no_field_ahead = fa && std::atoi(fa) == 0;
         const char *fs = std::getenv("EMC_FUSED_STEPS");
         c->no_fused_steps = fs && std::atoi(fs) == 0;
+        const char *tm = std::getenv("EMC_REFILL_TENSOR_MAP");
+        c->no_tensor_map = tm && std::atoi(tm) == 0;
         const char *ln = std::getenv("EMC_LEAN");
         c->no_lean = ln && std::atoi(ln) == 0;
         const char *br = std::getenv("EMC_BULK_REFILL");

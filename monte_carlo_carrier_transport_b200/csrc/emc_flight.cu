@@ -243,16 +243,27 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 // the ragged last batch of a slice and unaligned callers take the per-lane loads below.
 #define EMC_BULK_REFILL 1
 #endif
+#ifndef EMC_REFILL_TEST_WAIT
+#define EMC_REFILL_TEST_WAIT 0
+#endif
 #ifndef EMC_REFILL_TILES
 // tiles per warp: 1 = the batch after the current one is in flight; 2 = two batches ahead (the mbarrier wait is
 // 3.6 % of the stall samples in profiles/r2x).  Measured: 2 tiles 0.949 ms, 1 tile 0.945 ms (profiles/r2z_ab_*):
 // the wait is the try_wait's own latency, not late data; the second tile only costs L1.
 #define EMC_REFILL_TILES 1
 #endif
-struct alignas(16) RefillTile {              // bulk-copy destinations are 16-byte aligned: the size is a multiple of 16
+#ifndef EMC_REFILL_TENSOR_MAP
+// 1: when the seven state rows are the rows of ONE 2-D array (equal, 16-byte aligned pitch -- engine.Ensemble's
+// (7, N) tensor), the seven 256-byte row slices of a batch arrive by ONE tensor copy (cp.async.bulk.tensor.2d,
+// SASS UTMALDG, box 32 x 7 of a CUtensorMap that launch_flight encodes) instead of seven bulk copies with their
+// uniform-datapath address arithmetic: 49 -> ~15 single-lane instructions per refill (profiles/r2ag)
+#define EMC_REFILL_TENSOR_MAP 1
+#endif
+struct alignas(128) RefillTile {             // tensor-copy destinations are 128-byte aligned
     double row[7][32];                       // kx ky kz x y z dtau of the next batch
     int32_t val[32];
     unsigned long long bar;                  // mbarrier: one arrival (the issuing lane) + 1920 bytes
+    uint32_t loaded;                         // written by every lane once its loads of the tile have completed (see the refill pass)
 };
 static_assert(sizeof(RefillTile) % 16 == 0, "RefillTile must keep the next tile 16-byte aligned");
 constexpr uint32_t REFILL_TILE_BYTES = 7 * 256 + 128;
@@ -276,10 +287,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 // one lane: arm the tile's mbarrier with the byte count and issue the eight row copies of the batch at `j`
-__device__ __forceinline__ void refill_issue(RefillTile &T, const FlightArgs &A, uint32_t j)
+__device__ __forceinline__ void refill_issue(RefillTile &T, const FlightArgs &A, uint32_t j, const CUtensorMap *tmap)
 {
     const uint32_t bar = smem_u32(&T.bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(REFILL_TILE_BYTES) : "memory");
+    if (EMC_REFILL_TENSOR_MAP && A.bulk == 2) {               // warp-uniform (kernel argument)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(smem_u32(&T.row[0][0])), "l"(tmap), "r"((int32_t)j), "r"(0), "r"(bar) : "memory");
+        bulk_g2s(smem_u32(&T.val[0]), A.valley + j, 128u, bar);
+        return;
+    }
     const uint32_t t0 = smem_u32(&T.row[0][0]);
 #pragma unroll
     for (int r = 0; r < 7; ++r) bulk_g2s(t0 + r * 256, (&A.kx)[r] + j, 256u, bar);
@@ -289,10 +306,17 @@ __device__ __forceinline__ void refill_issue(RefillTile &T, const FlightArgs &A,
 __device__ __forceinline__ void refill_wait(RefillTile &T, uint32_t parity)
 {
     const uint32_t bar = smem_u32(&T.bar);
+#if EMC_REFILL_TEST_WAIT
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+#else
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "WAIT_%=:\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 
 constexpr int QCAP = 64;                    // a phase runs only if its pushes fit: <= 32 + 32
@@ -322,10 +346,35 @@ struct WarpQueues {
 // (select_self_thr): no exact index and no load at the end of a dependency chain in the select pass
 #define EMC_SELF_THRESHOLD 2
 #endif
-// the queues of the threshold form: a parked particle carries nothing but itself
+// the queues of the threshold form: a parked particle carries nothing but itself (the scatter pass runs the
+// event again from its counters) ...
 struct WarpQueuesLean {
     WarpQueue ev;
     WarpQueue sc;
+};
+#ifndef EMC_PARK_FIELDS
+// 1: ... or, in the one-step kernel, E_np, r2 and the azimuth uniform of the select pass (ParkFields), so that the
+// scatter pass neither evaluates Philox block A nor the energy chain a second time (~150 of its ~1170
+// instructions; the scatter pass was 13.6 % of the stall samples in profiles/r2ag)
+#define EMC_PARK_FIELDS 1
+#endif
+struct WarpQueuesPark {
+    WarpQueue ev;
+    WarpQueue sc;
+    double2 sc_er[QCAP];                     // E_np (NaN: energy fault), azimuth uniform
+    double sc_r2[QCAP];
+};
+template <bool LEAN> struct FlightQueues {
+    typedef WarpQueues type;
+};
+template <> struct FlightQueues<true> {
+#if EMC_SELF_THRESHOLD == 2 && EMC_PARK_FIELDS && !EMC_STAGE_REFILL
+    typedef WarpQueuesPark type;
+#elif EMC_SELF_THRESHOLD && !EMC_STAGE_REFILL
+    typedef WarpQueuesLean type;
+#else
+    typedef WarpQueues type;
+#endif
 };
 // One whole event (threshold form of the lean kernels): the scatter pass of the parked particles
 // (0.1 passes per batch) -- real mechanisms and the cold exits of the select pass (faults, r2 at or
@@ -635,15 +684,16 @@ __device__ __forceinline__ void queue_pop(const WarpQueue &Q, int slot, Particle
 template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML, bool LEAN = false>
 __global__ void EMC_FLIGHT_BOUNDS
 flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg,
-                      const __grid_constant__ FlightArgs A)
+                      const __grid_constant__ FlightArgs A, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr bool REPLAY = Stream::is_replay;
     constexpr bool ZON = LEAN && (FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS);   // zonly known at compile time
     static_assert(!LEAN || (!REPLAY && !EXACT && !DEPOSIT), "LEAN is the Philox / default-libm / no-deposit kernel");
     constexpr bool THR = LEAN && EMC_SELF_THRESHOLD && !EMC_STAGE_REFILL;
-    using WarpQueues = typename std::conditional<THR, WarpQueuesLean, emc::WarpQueues>::type;
+    using WarpQueues = typename FlightQueues<LEAN>::type;
+    constexpr bool PARKF = THR && EMC_SELF_THRESHOLD == 2 && EMC_PARK_FIELDS;
     __shared__ MechMeta Ms[ML ? EMC_MAX_LAYERS : 1];
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     WarpQueues *queues = reinterpret_cast<WarpQueues *>(dyn_smem);
     constexpr bool AHEAD_OK = EMC_FIELD_AHEAD && (FIELD == EMC_FIELD_MESH_PACKED || FIELD == EMC_FIELD_MESH_XZ);
     const bool AHEAD = AHEAD_OK && A.field_ahead;                 // warp-uniform (kernel argument)
@@ -717,7 +767,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < EMC_REFILL_TILES; ++t)
-                if (wlen >= 32u * (t + 1)) refill_issue(RTW[t], A, w0 + 32u * t);
+                if (wlen >= 32u * (t + 1)) refill_issue(RTW[t], A, w0 + 32u * t, &tmap);
         }
     }
 #if EMC_STAGE_REFILL
@@ -784,6 +834,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         uint32_t i = 0;
         int mech = 0;
         double e_np = 0.0, r_az = 0.0;
+        ParkFields pf = {0.0, 0.0, 0.0};                          // PARKF: what a parked particle carries to its scatter pass
         bool act, pend = false, fly = false, park = false, tail = false;
         constexpr bool MESHF = (FIELD == EMC_FIELD_MESH || FIELD == EMC_FIELD_MESH_PACKED || FIELD == EMC_FIELD_MESH_XZ);
         constexpr bool SPEC = EMC_SPEC_SELECT && !REPLAY && !EXACT;
@@ -839,9 +890,23 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 p.x = RT.row[3][lane]; p.y = RT.row[4][lane]; p.z = RT.row[5][lane];
                 p.dte = RT.row[6][lane];
                 p.val = RT.val[lane];
-                __syncwarp();                                     // every lane has read its slot: the tile may be refilled
-                // the batch EMC_REFILL_TILES further on, if it is a full one, too
-                if (next + 32u * (EMC_REFILL_TILES + 1) <= wlen && elect_one()) refill_issue(RT, A, w0 + next + 32u * EMC_REFILL_TILES);
+                // The batch EMC_REFILL_TILES further on, if it is a full one, too, goes into this tile -- once every
+                // lane's loads have COMPLETED.  A shared-memory load that has been issued has not yet read the tile, and a
+                // warp barrier orders instructions, not the copy engine: without the store below, one copy in ~10^9
+                // particle-timesteps landed before a lane's load had executed and gave that lane a row of the NEXT batch
+                // (run-to-run differences of a few trajectories, found with profiles/kernel_ab.py's checksum once a
+                // larger scatter queue had moved the tiles).  The store's operand is a fold of all eight loaded
+                // registers, so it cannot issue before they have arrived; the copy is issued behind it and the barrier.
+                // (Issuing at the end of the refill block or of the pass instead is safe, too, but the shorter lead costs
+                // 4 % and 7 %: 0.958 / 0.984 vs 0.92 ms, profiles/r2am_*.)
+                {
+                    const uint32_t fold = (uint32_t)__double2loint(p.kx) ^ (uint32_t)__double2loint(p.ky) ^ (uint32_t)__double2loint(p.kz) ^
+                                          (uint32_t)__double2loint(p.x) ^ (uint32_t)__double2loint(p.y) ^ (uint32_t)__double2loint(p.z) ^
+                                          (uint32_t)__double2loint(p.dte) ^ (uint32_t)p.val;
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(&RT.loaded)), "r"(fold) : "memory");
+                }
+                __syncwarp();
+                if (next + 32u * (EMC_REFILL_TILES + 1) <= wlen && elect_one()) refill_issue(RT, A, w0 + next + 32u * EMC_REFILL_TILES, &tmap);
             } else if (act) {
                 p.kx = A.kx[i]; p.ky = A.ky[i]; p.kz = A.kz[i];
                 p.x = A.x[i]; p.y = A.y[i]; p.z = A.z[i];
@@ -935,6 +1000,12 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                         mech = WQ.sc_mech[slot]; e_np = er.x; r_az = er.y;
                     }
                 }
+                if constexpr (PARKF) {
+                    if (!sel) {
+                        const double2 er = WQ.sc_er[slot];
+                        pf.e_np = er.x; pf.r_az = er.y; pf.r2 = WQ.sc_r2[slot];
+                    }
+                }
             }
             __syncwarp();
             if (act) {
@@ -955,7 +1026,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     // (Tried: the next free flight and its flight segment inside this block as well, speculatively on
                     // the self-scattering k' and committed with selects -- 0.938 vs 0.918 ms, profiles/r2ac_ab_*: the
                     // segment depends on k', so it only lengthens the block's longest chain.)
-                    if (select_self_thr<Stream>(P, MT, p.kx, p.ky, p.kz, v, rng, lg)) tail = true;
+                    if (select_self_thr<Stream, PARKF>(P, MT, p.kx, p.ky, p.kz, v, rng, lg, pf)) tail = true;
                     else { park = true; s0 = rng.state(); }
                 } else if (sel && SPEC) {
                     bool is_self;
@@ -983,7 +1054,11 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 } else if (THR) {
                     // scatter pass of the threshold form: the parked event again from its counters, now
                     // with the whole table row (a real mechanism: polar sampler, rotation :1059-1089)
-                    if constexpr (THR) {
+                    if constexpr (PARKF) {
+                        // ... or, with the select pass's E_np, r2 and azimuth uniform, the rest of it (scatter_parked)
+                        f = scatter_parked<Stream>(P, MT, M, p.kx, p.ky, p.kz, v, rng, pf);
+                        lg = fast_log(rng.free_flight());
+                    } else if constexpr (THR) {
                         const EventOut o = event_cold(&P, &MT, &M, p.kx, p.ky, p.kz, v, A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
                         f = o.f; lg = o.lg;
                         if (f < 0) { p.kx = o.kx; p.ky = o.ky; p.kz = o.kz; v = o.val; }
@@ -1050,6 +1125,11 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                                  "@q st.shared.v2.f64 [%2], {%3, %4};\n\t}"
                                  ::"r"(smem_u32(&WQ.sc_mech[0]) + (uint32_t)slot * 4u), "r"(mech),
                                  "r"(smem_u32(&WQ.sc_er[0]) + (uint32_t)slot * 16u), "d"(e_np), "d"(r_az), "r"((uint32_t)park) : "memory");
+                if constexpr (PARKF)
+                    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.f64 [%0], %1;\n\t"
+                                 "@q st.shared.v2.f64 [%2], {%3, %4};\n\t}"
+                                 ::"r"(smem_u32(&WQ.sc_r2[0]) + (uint32_t)slot * 8u), "d"(pf.r2),
+                                 "r"(smem_u32(&WQ.sc_er[0]) + (uint32_t)slot * 16u), "d"(pf.e_np), "d"(pf.r_az), "r"((uint32_t)park) : "memory");
                 qsc += __popc(km);
             }
         };
@@ -1086,6 +1166,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 const int slot = qsc + __popc(km & lt_mask);
                 queue_push<FIELD>(WQ.sc, slot, p, s0);
                 if constexpr (!THR) { WQ.sc_mech[slot] = mech; WQ.sc_er[slot] = make_double2(e_np, r_az); }
+                if constexpr (PARKF) { WQ.sc_r2[slot] = pf.r2; WQ.sc_er[slot] = make_double2(pf.e_np, pf.r_az); }
             }
             qsc += __popc(km);
         }
@@ -1111,8 +1192,8 @@ template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML, bool LEAN 
 static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
     auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT, ML, LEAN>;
-    // the threshold form's queues carry no park fields (launch_flight sized `smem` for the general ones)
-    if (LEAN && EMC_SELF_THRESHOLD && !EMC_STAGE_REFILL) smem -= (sizeof(WarpQueues) - sizeof(WarpQueuesLean)) * (FLIGHT_THREADS / 32);
+    // launch_flight sized `smem` for the general queues; the lean kernels' are smaller or larger
+    smem = smem - sizeof(WarpQueues) * (FLIGHT_THREADS / 32) + sizeof(typename FlightQueues<LEAN>::type) * (FLIGHT_THREADS / 32);
     // persistent grid: exactly the blocks that are resident at once (one wave), unless the
     // ensemble is too small to give every block a full tile.  The attribute / occupancy queries
     // are cached per kernel variant and device (they cost tens of microseconds per launch).
@@ -1130,7 +1211,7 @@ static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid
     const int per_sm = cached_per_sm[dev];
     const int resident = ctx->sm_count * per_sm * ctx->waves;
     if (grid > resident) grid = resident;
-    k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A);
+    k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A, ctx->state_tmap);
     return cudaGetLastError();
 }
 
@@ -1156,6 +1237,46 @@ static cudaError_t launch_flight_t(const Ctx *ctx, const FlightArgs &A, int grid
                   : launch_flight_k<Stream, FIELD, false, false, false>(ctx, A, grid, smem, st);
 }
 
+// The CUtensorMap of the state rows as one (7, n) fp64 array with a box of 32 particles x 7 rows, when the
+// caller's seven pointers ARE such an array (equal pitch, a multiple of 16 bytes; 16-byte aligned base).  Encoded
+// by the driver (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint: no link-time dependency on libcuda) and
+// cached while base, length and pitch stay the same.  false = use the per-row bulk copies.
+static bool state_tensor_map(Ctx *ctx, const FlightArgs &A)
+{
+    const char *base = reinterpret_cast<const char *>(A.kx);
+    const ptrdiff_t pitch = reinterpret_cast<const char *>(A.ky) - base;
+    if (pitch <= 0 || (pitch & 15) || ((uintptr_t)base & 15) || A.n < 32 || A.n > 0x7fffffff || pitch < A.n * 8) return false;
+    for (int r = 1; r < 7; ++r)
+        if (reinterpret_cast<const char *>((&A.kx)[r]) - base != pitch * r) return false;
+    if (ctx->tmap_base == base && ctx->tmap_n == A.n && ctx->tmap_pitch == pitch) return true;
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        looked_up = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+        else
+            (void)cudaGetLastError();
+    }
+    if (!encode) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)A.n, 7};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {32, 7}, estr[2] = {1, 1};
+    ctx->tmap_base = nullptr;
+    if (encode(&ctx->state_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<char *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    ctx->tmap_base = base; ctx->tmap_n = A.n; ctx->tmap_pitch = pitch;
+    return true;
+}
+
 cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, cudaStream_t st)
 {
     if (A.n >= ((int64_t)1 << 32) - 64) return cudaErrorInvalidValue;   // 32-bit particle index inside a launch (checked by the ABI)
@@ -1176,6 +1297,7 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
         // field gathers live on -- measured 0.745 ms with, 0.721 ms without on 1024 x 1 x 1024, profiles/ab_r2e)
         const bool mesh_field = field_mode == EMC_FIELD_MESH || field_mode == EMC_FIELD_MESH_PACKED || field_mode == EMC_FIELD_MESH_XZ;
         A.bulk = EMC_BULK_REFILL && (bits & 15) == 0 && !ctx->no_bulk_refill && !replay && (!mesh_field || ctx->bulk_mesh);
+        if (A.bulk && EMC_REFILL_TENSOR_MAP && !ctx->no_tensor_map && state_tensor_map(ctx, A)) A.bulk = 2;
         if (A.bulk) smem += sizeof(RefillTile) * EMC_REFILL_TILES * (FLIGHT_THREADS / 32);
     }
     if (EMC_OBS_SMEM) {
@@ -1366,7 +1488,7 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
             __syncwarp();
             bool tail = false;
             double lg = 0.0;
-            PhiloxStream rng;
+            PhiloxStreamSteps rng;
             if (act) {
                 i = w0 + p.off;
                 rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step + (s0 >> 16), s0 & 0xffffu);
@@ -1374,11 +1496,12 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
                 double e_np = 0.0, r_az = 0.0;
                 if (sel && EMC_SELF_THRESHOLD == 2) {
                     f = -1;
-                    if (select_self_thr<PhiloxStream>(P, MT, p.kx, p.ky, p.kz, v, rng, lg)) tail = true;
+                    ParkFields unused;
+                    if (select_self_thr<PhiloxStreamSteps>(P, MT, p.kx, p.ky, p.kz, v, rng, lg, unused)) tail = true;
                     else park = true;                         // the event index in s0 is unchanged: the scatter pass redoes the event
                 } else if (sel) {
                     bool is_self;
-                    f = select_self_spec<PhiloxStream, true, EMC_SELF_THRESHOLD != 0>(P, MT, Ms, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
+                    f = select_self_spec<PhiloxStreamSteps, true, EMC_SELF_THRESHOLD != 0>(P, MT, Ms, p.kx, p.ky, p.kz, v, rng, e_np, r_az, mech, is_self, lg);
                     // a cold exit (fault, r2 >= min_last) is parked like a real mechanism: the scatter pass
                     // runs the whole event literally, whatever it turns out to be
                     if (EMC_SELF_THRESHOLD && f == EMC_SELECT_COLD) { f = -1; is_self = false; }

@@ -1,5 +1,6 @@
 // emc_host.h -- host-side context and launcher prototypes shared by the .cu files.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <string>
 #include "emc_device.cuh"
@@ -84,6 +85,12 @@ struct Ctx {
     int deposit_mode = 0;         // emc_set_deposit_mode: 0 auto, 1 direct atomics, 2 tiled (large NGP meshes)
     void *d_dep_scratch = nullptr;   // tiled deposit: cell ids, sorted cell ids, tile histogram
     size_t dep_scratch_bytes = 0;
+    // the state rows as one 2-D tensor for the refill tiles (launch_flight; cached per base / length / pitch)
+    alignas(64) CUtensorMap state_tmap = {};
+    const char *tmap_base = nullptr;
+    int64_t tmap_n = 0;
+    ptrdiff_t tmap_pitch = 0;
+    bool no_tensor_map = false;   // EMC_REFILL_TENSOR_MAP=0 in the environment (A/B, tests)
     int64_t launches = 0;
     std::string last_error;
 };

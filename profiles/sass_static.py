@@ -22,7 +22,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "monte_carlo_carrier_transport_b200", "libemc_b200.so")
 SRC = os.path.join(ROOT, "monte_carlo_carrier_transport_b200", "csrc", "emc_flight.cu")
-KERNEL = "flight_scatter_kernelINS_12PhiloxStreamELi1ELb0ELb0ELb0ELb1E"
+KERNEL = "flight_scatter_kernelINS_13PhiloxStreamTILb1EEELi1ELb0ELb0ELb0ELb1E"
 
 FP64 = ("DFMA", "DMUL", "DADD", "DSETP", "MUFU")
 CONTROL = ("BRA", "BSSY", "BSYNC", "EXIT", "CALL", "RET", "WARPSYNC", "NOP", "BAR", "BREAK", "BMOV")

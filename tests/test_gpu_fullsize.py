@@ -207,3 +207,43 @@ def test_configs2_full_size_diode_layers(torch_mod):
         part.step(s, SEED)
     assert torch.equal(part.state, ens.state[:, a:b]) and torch.equal(part.valley, ens.valley[a:b])
     ctx.close()
+
+
+def test_bulk_refill_tiles_are_race_free_at_full_size(torch_mod):
+    """The lean kernel brings every refill batch into a per-warp shared-memory tile with asynchronous bulk /
+    tensor copies and refills the tile as soon as it has been read.  "Read" has to mean that the loads have
+    COMPLETED: a copy issued behind loads that had merely been issued overtook one of them about once in 10^9
+    particle-timesteps (a lane then flew a row of the next batch).  Regression test at the size where that
+    shows: 40 timesteps of configs[1] (10^9 particle-timesteps), bit for bit against the same run with the
+    plain per-lane loads (EMC_BULK_REFILL=0, no asynchronous agent), twice."""
+    import os
+    torch = torch_mod
+    import bench
+    from monte_carlo_carrier_transport_b200 import abi, engine
+
+    def run(steps):
+        ctx = engine.Context(device=0)
+        ctx.set_field_groups(bench.field_points(), bench.PER_FIELD)
+        ens = engine.Ensemble(ctx, N_C2).init(SEED)
+        rows = ens.run_steps(0, steps, SEED, field_mode=abi.FIELD_GROUPS)       # before-step observables: lean kernel
+        desc = ctx.describe()
+        s = ens.state.view(torch.int64)
+        w = torch.arange(1, 8, device=s.device, dtype=torch.int64)[:, None]
+        fold = (int(s.sum().item()), int((s * w).sum().item()), int(ens.valley.to(torch.int64).sum().item()))
+        counts = [(r["n_segments"], r["n_events"], r["n_fault"]) for r in rows]
+        del ens
+        ctx.close()
+        return fold, counts, desc
+
+    steps = 40
+    os.environ["EMC_BULK_REFILL"] = "0"
+    try:
+        plain = run(steps)
+    finally:
+        del os.environ["EMC_BULK_REFILL"]
+    assert plain[2]["bulk_refill"] == "0" and plain[2]["lean"] == "1"
+    for _ in range(2):
+        bulk = run(steps)
+        assert bulk[2]["bulk_refill"] == "1"
+        assert bulk[1] == plain[1]
+        assert bulk[0] == plain[0]
