@@ -452,10 +452,10 @@ extern "C" int emc_describe(const EmcCtx *ctx, char *buf, int32_t cap)
     const char *sor = std::getenv("EMC_SOR_BLOCKS_PER_SM");
     const int n = std::snprintf(buf, (size_t)cap,
                                 "exact_libm=%d zonly_constant=%d zonly_groups=%d field_ahead=%d bulk_refill=%d lean=%d waves=%d max_grid=%d "
-                                "obs_before=%d n_layers=%d literal_scan=%d sor_blocks_per_sm=%s flight_threads=%d",
+                                "obs_before=%d n_layers=%d literal_scan=%d sor_blocks_per_sm=%s flight_threads=%d refill_tensor_map=%d",
                                 (int)c->exact_libm, (int)c->zonly_constant, (int)c->zonly_groups,
                                 (int)!c->no_field_ahead, (int)!c->no_bulk_refill, (int)(!c->no_lean && c->self_last), c->waves, c->max_grid, c->obs_before, c->dc.n_layers,
-                                c->dc.literal_scan, sor ? sor : "auto", FLIGHT_THREADS);
+                                c->dc.literal_scan, sor ? sor : "auto", FLIGHT_THREADS, (int)(!c->no_tensor_map && c->tmap_base != nullptr));
     return n < cap ? n : cap - 1;
 }
 

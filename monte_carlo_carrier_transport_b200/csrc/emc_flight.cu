@@ -364,18 +364,23 @@ struct WarpQueuesPark {
     double2 sc_er[QCAP];                     // E_np (NaN: energy fault), azimuth uniform
     double sc_r2[QCAP];
 };
-template <bool LEAN> struct FlightQueues {
+// (not in the multi-layer kernel: its six more live registers cost that kernel 20 %, 0.697 vs 0.580 ms for the
+// flight of configs[2], profiles/r2ap_*)
+template <bool LEAN, bool ML> struct FlightQueues {
     typedef WarpQueues type;
 };
-template <> struct FlightQueues<true> {
-#if EMC_SELF_THRESHOLD == 2 && EMC_PARK_FIELDS && !EMC_STAGE_REFILL
-    typedef WarpQueuesPark type;
-#elif EMC_SELF_THRESHOLD && !EMC_STAGE_REFILL
+#if EMC_SELF_THRESHOLD && !EMC_STAGE_REFILL
+template <> struct FlightQueues<true, true> {
     typedef WarpQueuesLean type;
+};
+template <> struct FlightQueues<true, false> {
+#if EMC_SELF_THRESHOLD == 2 && EMC_PARK_FIELDS
+    typedef WarpQueuesPark type;
 #else
-    typedef WarpQueues type;
+    typedef WarpQueuesLean type;
 #endif
 };
+#endif
 // One whole event (threshold form of the lean kernels): the scatter pass of the parked particles
 // (0.1 passes per batch) -- real mechanisms and the cold exits of the select pass (faults, r2 at or
 // above the valley's smallest last column) -- runs scatter_event -- the general, non-speculative
@@ -690,8 +695,8 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     constexpr bool ZON = LEAN && (FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS);   // zonly known at compile time
     static_assert(!LEAN || (!REPLAY && !EXACT && !DEPOSIT), "LEAN is the Philox / default-libm / no-deposit kernel");
     constexpr bool THR = LEAN && EMC_SELF_THRESHOLD && !EMC_STAGE_REFILL;
-    using WarpQueues = typename FlightQueues<LEAN>::type;
-    constexpr bool PARKF = THR && EMC_SELF_THRESHOLD == 2 && EMC_PARK_FIELDS;
+    using WarpQueues = typename FlightQueues<LEAN, ML>::type;
+    constexpr bool PARKF = THR && EMC_SELF_THRESHOLD == 2 && EMC_PARK_FIELDS && !ML;
     __shared__ MechMeta Ms[ML ? EMC_MAX_LAYERS : 1];
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     WarpQueues *queues = reinterpret_cast<WarpQueues *>(dyn_smem);
@@ -1193,7 +1198,7 @@ static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid
 {
     auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT, ML, LEAN>;
     // launch_flight sized `smem` for the general queues; the lean kernels' are smaller or larger
-    smem = smem - sizeof(WarpQueues) * (FLIGHT_THREADS / 32) + sizeof(typename FlightQueues<LEAN>::type) * (FLIGHT_THREADS / 32);
+    smem = smem - sizeof(WarpQueues) * (FLIGHT_THREADS / 32) + sizeof(typename FlightQueues<LEAN, ML>::type) * (FLIGHT_THREADS / 32);
     // persistent grid: exactly the blocks that are resident at once (one wave), unless the
     // ensemble is too small to give every block a full tile.  The attribute / occupancy queries
     // are cached per kernel variant and device (they cost tens of microseconds per launch).

@@ -55,7 +55,7 @@ def launches(path, out):
     tot = sum(a[1] for a in agg.values())
     with open(out, "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
-        f.write("# bench.py --no-e2e: <PhiloxStream, 1, 0, 0, 0, 1> (the LEAN instantiation) = the timed configs[1] step, one\n"
+        f.write("# bench.py --no-e2e: <PhiloxStreamT<1>, 1, 0, 0, 0, 1> (the LEAN instantiation) = the timed configs[1] step, one\n"
                 "# launch per timestep = 100 % of it; <.., 0> = the warm-up steps (observables at retirement -> general kernel);\n"
                 "# observables_kernel = the one stand-alone reduction that closes the timed region; init / fills = set-up\n")
         f.write("# %-70s %6s %12s %8s %10s %10s\n" % ("kernel", "count", "total_ms", "share", "median_ms", "max_ms"))
