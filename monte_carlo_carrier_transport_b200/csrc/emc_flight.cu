@@ -243,9 +243,6 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 // the ragged last batch of a slice and unaligned callers take the per-lane loads below.
 #define EMC_BULK_REFILL 1
 #endif
-#ifndef EMC_REFILL_TEST_WAIT
-#define EMC_REFILL_TEST_WAIT 0
-#endif
 #ifndef EMC_REFILL_TILES
 // tiles per warp: 1 = the batch after the current one is in flight; 2 = two batches ahead (the mbarrier wait is
 // 3.6 % of the stall samples in profiles/r2x).  Measured: 2 tiles 0.949 ms, 1 tile 0.945 ms (profiles/r2z_ab_*):
@@ -306,17 +303,10 @@ __device__ __forceinline__ void refill_issue(RefillTile &T, const FlightArgs &A,
 __device__ __forceinline__ void refill_wait(RefillTile &T, uint32_t parity)
 {
     const uint32_t bar = smem_u32(&T.bar);
-#if EMC_REFILL_TEST_WAIT
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "WAIT_%=:\n\t"
-                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
-#else
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "WAIT_%=:\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
-#endif
 }
 
 constexpr int QCAP = 64;                    // a phase runs only if its pushes fit: <= 32 + 32
@@ -600,16 +590,6 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
 // (2: in the mesh-field modes, too -- measured: no gain there, 0.631 vs 0.629 ms on 1024 x 1 x 1024, profiles/r2ae_ab_*:
 // the refill of those modes waits for its field record, not for arithmetic)
 #define EMC_REFILL_FLIES 1
-#endif
-#ifndef EMC_SCATTER_UNLIKELY
-// 1: the scatter pass (0.1 passes per batch, but half of the loop's instructions) is marked unlikely, so that the
-// code generator places it after the loop's hot blocks (refill, select, shared tail stay contiguous)
-#define EMC_SCATTER_UNLIKELY 1
-#endif
-#if EMC_SCATTER_UNLIKELY
-#define EMC_LIKELY_SELECT(x) __builtin_expect(!!(x), 1)
-#else
-#define EMC_LIKELY_SELECT(x) (x)
 #endif
 #ifndef EMC_PUSH_FIRST
 #define EMC_PUSH_FIRST 1
@@ -1025,7 +1005,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 if (ML && layer < 0) {
                     f = EMC_FAULT_OUTSIDE;
                     layer = 0;
-                } else if (EMC_LIKELY_SELECT(sel) && SPEC && THR && EMC_SELF_THRESHOLD == 2) {
+                } else if (sel && SPEC && THR && EMC_SELF_THRESHOLD == 2) {
                     // finished here (a certain, clean self-scattering event) or parked for the literal path
                     f = -1;
                     // (Tried: the next free flight and its flight segment inside this block as well, speculatively on
