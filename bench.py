@@ -338,9 +338,14 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
         e[1].record()
         m.deposit(ens)
         e[2].record()
-        m.allreduce()
-        e[3].record()
-        m.to_rho()
+        fused_rho = m.p2p is not None and "rho_ptrs" in m.p2p
+        if fused_rho:
+            m.allreduce_to_rho()      # ONE kernel: counts reduce-scatter, rho of this rank's slice, all-gather of both
+            e[3].record()
+        else:
+            m.allreduce()
+            e[3].record()
+            m.to_rho()
         e[4].record()
         m.solve_async(tol=cs.tol, max_sweeps=cs.max_sweeps, order=order)
         e[5].record()
@@ -390,6 +395,8 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
             "cold_start": {"ms": cold_ms, "iterations": prime_sweeps, "true_residual_before": r_cold0,
                            "true_residual_after": r_cold1},
             "charge_allreduce": ("none (1 rank)" if world == 1 else
+                                 "emc_mesh_allreduce_rho_p2p over NVLink symmetric memory (charge all-reduce fused with rho: "
+                                 "the `allreduce` stage holds both, `to_rho` is empty)" if p2p and fused_rho else
                                  "emc_mesh_allreduce_p2p over NVLink symmetric memory" if p2p
                                  else "NCCL all_reduce (%s)" % (p2p_err or "EMC_P2P=0")),
             "mesh": "x".join(str(v) for v in COUPLED_MESH), "particles_per_gpu": n, "global_particles": n * world,

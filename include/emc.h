@@ -342,6 +342,15 @@ int emc_set_deposit_mode(EmcCtx *ctx, int32_t mode);
 #define EMC_MAX_PEERS 16
 int emc_mesh_allreduce_p2p(EmcCtx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs,
                            int32_t world, int32_t rank, int64_t n_cells, void *stream);
+/* The same exchange FUSED with rho (poisson_.py:27,36 per cell, as emc_mesh_to_rho): this rank sums its
+ * slice of the counts, turns the totals of that slice into rho and stores totals AND rho into every rank's
+ * buffers -- the sequential accumulation of poisson_.py:36 is then done once per cell in the whole job instead
+ * of once per cell on every rank.  rho_ptrs: `world` peer-mapped padded (nx+2,ny+2,nz+2) fp64 arrays whose halo
+ * is already zero; interior cells only are written.  Same barriers as emc_mesh_allreduce_p2p; rho is
+ * bit-identical to emc_mesh_to_rho of the totals. */
+int emc_mesh_allreduce_rho_p2p(EmcCtx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs,
+                               double *const *rho_ptrs, int32_t world, int32_t rank, int64_t n_cells,
+                               int32_t scheme, void *stream);
 
 /* rho_pad (device, (nx+2,ny+2,nz+2), zero halo as np.pad at poisson_.py:53).  NGP: background
  * then `count` sequential += increment (poisson_.py:27,36: bit-identical to the reference's

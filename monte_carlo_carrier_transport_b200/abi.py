@@ -110,6 +110,7 @@ SIGNATURES = {
     "emc_poisson_mg": (C.c_int, [_vp, _dp, _dp, _f64, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_f64), _dp, _vp]),
     "emc_poisson_residual": (C.c_int, [_vp, _dp, _dp, C.POINTER(_f64), C.POINTER(_f64), _dp, _vp]),
     "emc_mesh_allreduce_p2p": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp]),
+    "emc_mesh_allreduce_rho_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
     "emc_field_packed": (C.c_int, [_vp, _dp, _dp, _vp]),
     "emc_field_packed_interior": (C.c_int, [_vp, _dp, _dp, _vp]),
     "emc_field_xz": (C.c_int, [_vp, _dp, _dp, _vp]),

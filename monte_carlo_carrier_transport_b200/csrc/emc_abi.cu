@@ -877,6 +877,25 @@ extern "C" int emc_mesh_allreduce_p2p(EmcCtx *ctx, const int64_t *const *in_ptrs
     return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "mesh_allreduce_p2p launch");
 }
 
+extern "C" int emc_mesh_allreduce_rho_p2p(EmcCtx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs,
+                                          double *const *rho_ptrs, int32_t world, int32_t rank, int64_t n_cells,
+                                          int32_t scheme, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!in_ptrs || !out_ptrs || !rho_ptrs || world < 1 || world > EMC_MAX_PEERS || rank < 0 || rank >= world ||
+        (scheme != EMC_DEPOSIT_NGP && scheme != EMC_DEPOSIT_CIC))
+        return fail(c, EMC_ERR_INVALID, "emc_mesh_allreduce_rho_p2p: bad argument");
+    if (n_cells != (int64_t)c->dc.seg[0] * c->dc.seg[1] * c->dc.seg[2])
+        return fail(c, EMC_ERR_INVALID, "emc_mesh_allreduce_rho_p2p: n_cells is not this context's mesh");
+    for (int p = 0; p < world; ++p)
+        if (!in_ptrs[p] || !out_ptrs[p] || !rho_ptrs[p] || ((uintptr_t)in_ptrs[p] & 15) || ((uintptr_t)out_ptrs[p] & 15) ||
+            ((uintptr_t)rho_ptrs[p] & 7))
+            return fail(c, EMC_ERR_INVALID, "emc_mesh_allreduce_rho_p2p: null or unaligned peer pointer");
+    cudaError_t e = launch_mesh_allreduce_rho_p2p(c, in_ptrs, out_ptrs, rho_ptrs, world, rank, n_cells, scheme,
+                                                  (cudaStream_t)stream);
+    return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "mesh_allreduce_rho_p2p launch");
+}
+
 extern "C" int emc_field_packed(EmcCtx *ctx, const double *u_pad, double *e4, void *stream)
 {
     CTX_OR_FAIL(ctx);

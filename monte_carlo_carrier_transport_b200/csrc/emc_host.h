@@ -137,6 +137,9 @@ int run_poisson_sor(Ctx *ctx, double *u_pad, const double *rho_pad, double omega
 
 cudaError_t launch_mesh_allreduce_p2p(Ctx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs, int world,
                                       int rank, int64_t n_cells, cudaStream_t st);
+cudaError_t launch_mesh_allreduce_rho_p2p(Ctx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs,
+                                          double *const *rho_ptrs, int world, int rank, int64_t n_cells, int scheme,
+                                          cudaStream_t st);
 cudaError_t launch_field_packed(Ctx *ctx, const double *u_pad, double *e4, cudaStream_t st, bool interior_only = false);
 cudaError_t launch_field_xz(Ctx *ctx, const double *u_pad, double *e2, cudaStream_t st);
 int poisson_last(Ctx *ctx, int32_t *sweeps_out, double *err_out, cudaStream_t st);

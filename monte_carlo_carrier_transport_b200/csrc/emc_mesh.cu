@@ -522,6 +522,69 @@ cudaError_t launch_mesh_to_rho(Ctx *ctx, const int64_t *mesh, int scheme, double
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// The charge all-reduce FUSED with rho (multi-GPU coupled timestep): reduce-scatter of the integer
+// counts over peer memory, rho of this rank's 1/world slice of the cells from the totals -- the
+// reference's sequential accumulation (add_repeated), which costs more the more particles a cell
+// holds and which every rank used to repeat for the WHOLE mesh (0.095 ms of a 1.0 ms timestep at
+// 8 GPUs) -- and all-gather of both, totals and rho, with peer stores.  One launch between the same
+// two cross-rank barriers as mesh_allreduce_p2p_kernel; same integers, same add_repeated on them:
+// rho is bit-identical to emc_mesh_to_rho of the totals on every rank.
+// ------------------------------------------------------------------------------------------
+struct PeerRho {
+    const long long *in[EMC_MAX_PEERS];
+    long long *out[EMC_MAX_PEERS];
+    double *rho[EMC_MAX_PEERS];              // padded (nx+2, ny+2, nz+2) arrays, halo already zero
+};
+
+// one thread per cell: the accumulation of poisson_.py:36 is a serial chain per cell, so the kernel's time is
+// one such chain plus the peer round trips -- more threads, not more work per thread
+__global__ void __launch_bounds__(128)
+mesh_allreduce_rho_p2p_kernel(const __grid_constant__ DevConst P, const __grid_constant__ PeerRho M, int world,
+                              int64_t first, int64_t count, int scheme, double background,
+                              const double *__restrict__ background_z, double increment)
+{
+    const uint32_t ny = (uint32_t)P.seg[1], nz = (uint32_t)P.seg[2];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const int64_t cell = first + t;
+        long long m = 0;
+        for (int p = 0; p < world; ++p) m += M.in[p][cell];
+        for (int p = 0; p < world; ++p) M.out[p][cell] = m;
+        const uint32_t c32 = (uint32_t)cell, q32 = c32 / nz;
+        const uint32_t k = c32 - q32 * nz, i = q32 / ny, j = q32 - i * ny;
+        const int64_t idx = ((int64_t)(i + 1) * (ny + 2) + (j + 1)) * (nz + 2) + (k + 1);
+        const double bg = background_z ? background_z[k] : background;     // poisson_.py:27
+        const double r = scheme == EMC_DEPOSIT_NGP ? add_repeated(bg, increment, m)   // poisson_.py:36
+                                                   : bg + increment * ((double)m / 4294967296.0);
+        for (int p = 0; p < world; ++p) M.rho[p][idx] = r;
+    }
+}
+
+cudaError_t launch_mesh_allreduce_rho_p2p(Ctx *ctx, const int64_t *const *in_ptrs, int64_t *const *out_ptrs,
+                                          double *const *rho_ptrs, int world, int rank, int64_t n_cells, int scheme,
+                                          cudaStream_t st)
+{
+    PeerRho M;
+    for (int p = 0; p < world; ++p) {
+        M.in[p] = reinterpret_cast<const long long *>(in_ptrs[p]);
+        M.out[p] = reinterpret_cast<long long *>(out_ptrs[p]);
+        M.rho[p] = rho_ptrs[p];
+    }
+    // slices of whole 128-byte lines of the count meshes
+    const int64_t per = (((n_cells + world - 1) / world) + 15) & ~(int64_t)15;
+    const int64_t first = (int64_t)rank * per;
+    const int64_t count = first >= n_cells ? 0 : (first + per > n_cells ? n_cells - first : per);
+    if (count == 0) return cudaSuccess;
+    int grid = (int)((count + 127) / 128);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    ctx->launches++;
+    mesh_allreduce_rho_p2p_kernel<<<grid, 128, 0, st>>>(ctx->dc, M, world, first, count, scheme,
+                                                        ctx->params.rho_background, ctx->d_background_z,
+                                                        ctx->params.rho_increment);
+    return cudaGetLastError();
+}
+
 // E = -central difference on interior cells (poisson_.py:88-96), zero halo
 __global__ void field_kernel(const __grid_constant__ DevConst P, const double *__restrict__ u, double *ex,
                              double *ey, double *ez)

@@ -15,6 +15,7 @@ no CPU fallback: constructing a Context without a CUDA device raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -549,7 +550,10 @@ class Mesh:
             self.counts = torch.zeros(cells, dtype=torch.int64, device=ctx.device)
             self.total = self.counts                       # after allreduce(): summed in place
         pad = ctx.padded_shape
-        self.rho_pad = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
+        if self.p2p is not None and "rho" in self.p2p:
+            self.rho_pad = self.p2p["rho"]                 # symmetric memory: peers store their slice of rho here
+        else:
+            self.rho_pad = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.u_pad = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.ex = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
         self.ey = torch.zeros(pad, dtype=torch.float64, device=ctx.device)
@@ -599,6 +603,14 @@ class Mesh:
                         out_ptrs=(C.c_void_p * world)(*[b + even * 8 for b in base]))
         self.counts = buf[0, :cells]          # this rank's deposits
         self.total = buf[1, :cells]           # sum over the ranks, written by all peers
+        if os.environ.get("EMC_P2P_RHO", "1") != "0":
+            # rho in symmetric memory as well: allreduce_to_rho() lets every rank compute rho for its slice only
+            pad = self.ctx.padded_shape
+            rbuf = symm.empty(pad[0] * pad[1] * pad[2], dtype=torch.float64, device=self.ctx.device)
+            rbuf.zero_()
+            rhdl = symm.rendezvous(rbuf, group)
+            self.p2p.update(rho_hdl=rhdl, rho_buf=rbuf, rho=rbuf.view(pad),
+                            rho_ptrs=(C.c_void_p * world)(*[int(p) for p in rhdl.buffer_ptrs]))
 
     def allreduce(self, group=None):
         """Sum the integer charge mesh over the ranks; the result is ``self.total``.  NVLink peer
@@ -612,6 +624,21 @@ class Mesh:
             return
         from . import parallel
         parallel.allreduce_counts(self.counts, group)
+
+    def allreduce_to_rho(self, group=None):
+        """``allreduce`` + ``to_rho``.  With the mesh AND rho in NVLink symmetric memory both happen in one
+        kernel (``emc_mesh_allreduce_rho_p2p``): every rank accumulates rho for its 1/world slice of the cells
+        only and stores it into all ranks' rho arrays -- bit-identical to ``to_rho`` of the totals."""
+        if self.p2p is not None and "rho_ptrs" in self.p2p:
+            c, p = self.ctx, self.p2p
+            p["hdl"].barrier(channel=0)                      # every rank's deposits are complete (and rho is free)
+            c.check(c.lib.emc_mesh_allreduce_rho_p2p(c.h, p["in_ptrs"], p["out_ptrs"], p["rho_ptrs"], p["world"],
+                                                     p["rank"], p["cells"], self.scheme, c.stream))
+            p["hdl"].barrier(channel=1)                      # every peer has written its slice of my totals and rho
+            self._rho_halo_done = True                       # the halo of the symmetric buffer was zeroed at set-up
+            return
+        self.allreduce(group)
+        self.to_rho()
 
     def to_rho(self):
         """rho_pad from the (all-reduced) charge mesh.  The first call writes the zero halo too, later
@@ -746,8 +773,7 @@ class CoupledStepper:
 
     def _solve(self, max_sweeps: int | None = None):
         m = self.mesh
-        m.allreduce(self.group)
-        m.to_rho()
+        m.allreduce_to_rho(self.group)
         m.solve_async(tol=self.tol, max_sweeps=max_sweeps or self.max_sweeps, order=self.order)
         self.update_field()
 
