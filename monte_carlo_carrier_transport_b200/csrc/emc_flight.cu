@@ -175,6 +175,10 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
 //            closed form (scatter_self); particles that drew a REAL mechanism are parked in the
 //            SCATTER queue with their mechanism, energy and azimuth uniform;
 //   scatter  pop 32 particles from the scatter queue: polar-angle sampler, sincos, rotation.
+// (The LEAN instantiation's select pass decides "self-scattering or not" from three 8-byte thresholds
+// around a single-precision guess of the table index and parks EVERYTHING else -- real mechanisms,
+// ambiguous draws, faults -- with E_np, r2 and the azimuth uniform; its scatter pass computes the exact
+// index, loads the row and runs the literal event: select_self_thr / scatter_parked in emc_device.cuh.)
 // select and scatter share the tail (free-flight draw, flight segment, retirement or push
 // back).  So the divergent branches -- event count, self vs. real mechanism -- are turned into
 // queue traffic instead of idle lanes.  A particle's trajectory depends only on its own state
