@@ -1241,18 +1241,15 @@ static bool state_tensor_map(Ctx *ctx, const FlightArgs &A)
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    static bool looked_up = false;
-    if (!looked_up) {
-        looked_up = true;
+    static const EncodeFn encode = []() -> EncodeFn {         // looked up once (thread-safe static initialisation)
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            encode = reinterpret_cast<EncodeFn>(fn);
-        else
-            (void)cudaGetLastError();
-    }
+            return reinterpret_cast<EncodeFn>(fn);
+        (void)cudaGetLastError();
+        return nullptr;
+    }();
     if (!encode) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)A.n, 7};
     const cuuint64_t strides[1] = {(cuuint64_t)pitch};
