@@ -583,9 +583,10 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
 #ifndef EMC_EARLY_GROUP_FIELD
 // 1 (lean kernel, EMC_FIELD_GROUPS): the particle's field value is loaded as soon as its group is known
 // (refill / queue pop) instead of at the head of the flight segment, where its L1/L2 latency was 2.6 %
-// of the stall samples (profiles/r2f).  Measured: no gain (0.991 vs 0.985 ms, profiles/r2o): the other warps
-// already cover that wait; off.
-#define EMC_EARLY_GROUP_FIELD 0
+// of the stall samples (profiles/r2f).  Measured in r2o: no gain (0.991 vs 0.985 ms); measured again on the
+// final kernel, whose flight no longer hides behind a long tail: -0.7 %, and -1.8 % together with
+// EMC_PARK_UNCOND (0.912 vs 0.929 ms, profiles/r2ar_ab_*): on.
+#define EMC_EARLY_GROUP_FIELD 1
 #endif
 #ifndef EMC_LEAN_KERNEL
 #define EMC_LEAN_KERNEL 1
@@ -600,7 +601,9 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
 #endif
 #ifndef EMC_PARK_UNCOND
 // 1: the (predicated) push into the scatter queue is issued in every pass instead of behind a branch on the phase
-#define EMC_PARK_UNCOND 0
+// (one ballot, two POPCs and five predicated-off stores more in the refill and scatter passes, one BSSY / BRA /
+// BSYNC region less in every pass: -0.7 %, profiles/r2ar_ab_*)
+#define EMC_PARK_UNCOND 1
 #endif
 #ifndef EMC_PREDICATED_TAIL
 // 1: the write-back of a finished particle and the queue pushes are predicated stores instead of
