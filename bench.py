@@ -307,6 +307,14 @@ def coupled_bench(torch, dist, engine, abi, local, rank, world, barrier, steps=2
     m.allreduce()
     m.to_rho()
     r_cold0 = m.residual()[0]
+    # one untimed throw-away solve first (the solver's first call allocates its levels and loads the kernel: 4 ms
+    # of host work in r2z that is not the solve), then the potential is reset to the reference's cold start
+    # (zeros + the z-min surface value, poisson_.py:47-52) and the cold solve is timed
+    if mg:
+        m.solve_mg(tol_residual=1e-8 * r_cold0, max_cycles=1, sync=False)
+    else:
+        m.solve_async(tol=cs.tol, max_sweeps=1, order=order)
+    m.set_initial_guess(None)
     torch.cuda.synchronize()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
@@ -584,6 +592,36 @@ def run_ours(args):
                  "approx_steps_per_s": 1.8 * world * n / (fused_ms * 1e-3),
                  "note": "no per-timestep observables and no per-timestep HBM round trip (120 B per particle per LAUNCH): "
                          "not comparable with the HBM roofline of the one-step kernel; bit-identical final state"}
+    # ---- K timesteps WITH their observable rows per persistent launch (timestep chain): reported NEXT TO the headline ----
+    chained = None
+    if not args.no_e2e:
+        ck = 50
+        ens.run_steps(60_000, ck, SEED, field_mode=abi.FIELD_GROUPS)                # warm-up (buffers)
+        barrier()
+        launches1 = ctx.launch_count()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rows_c = torch.zeros((2 * ck, 11), dtype=torch.int64, device=ctx.device)
+        ctx.set_obs_phase(True)
+        c0.record()
+        for r in range(2):
+            ctx.check(ctx.lib.emc_flight_scatter_steps(ctx.h, *ens._ptrs(), n, abi.FIELD_GROUPS, None, None, None, SEED,
+                                                       rank * n, 60_050 + r * ck, ck, rows_c[r * ck:].data_ptr(), ctx.stream))
+        c1.record()
+        barrier()
+        ctx.set_obs_phase(False)
+        ct = torch.tensor([c0.elapsed_time(c1) / (2 * ck)], dtype=torch.float64, device=ctx.device)
+        if world > 1:
+            dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+        chained_ms = float(ct.cpu()[0])
+        seg_c = int(rows_c[:, 9].sum().item())
+        chained = {"api": "emc_flight_scatter_steps WITH observable rows (engine.Ensemble.run_steps, HostStepper.run): %d timesteps "
+                          "and their %d rows per persistent launch, blocks pop (slice, timestep) items from a device-side FIFO -- "
+                          "no launch ramp / tail / gap per timestep; same 120 B per particle-timestep of HBM traffic" % (ck, ck),
+                   "timesteps_per_launch": ck, "launches": int(ctx.launch_count() - launches1), "ms_per_timestep": chained_ms,
+                   "steps_per_s": world * seg_c / (2 * ck) / (chained_ms * 1e-3),
+                   "hbm_frac": 120.0 * n / (chained_ms * 1e-3) / 1e9 / measured_peak_gbs()[0],
+                   "note": "bit-identical state and rows to one launch per timestep (tests/test_gpu_parity.py); the headline "
+                           "`value` / `roofline` stay on the one-launch-per-timestep kernel"}
     if args.no_e2e:       # profiling runs (ncu launch lists): the device-resident arm only
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": segments / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -622,7 +660,9 @@ def run_ours(args):
     # (chunks of 2^22 particles for the loop: 50 launches per chunk amortise better; measured 1.33 vs 1.41 ms
     # per timestep with 2^21, profiles/r2_e2e_chunks.txt -- the one-timestep-per-call API prefers 2^21)
     host = (hs.coords_t, hs.valley_t, hs.dtau_t)
-    hs2 = engine.HostStepper(ctx, n, chunk=1 << 22, pid_offset=rank * n)
+    # graduated chunks (engine.chunk_schedule: 1, 2, 4, 8, 4.9, 2, 1 Mi particles): the first H2D and the last D2H copy
+    # are the PCIe time no kernel overlaps -- 1.274 -> 1.185 ms per timestep, profiles/r2as_e2e_ramp.txt
+    hs2 = engine.HostStepper(ctx, n, chunk=1 << 23, pid_offset=rank * n, ramp_from=1 << 20)
     hs2.coords_t.copy_(host[0]); hs2.valley_t.copy_(host[1]); hs2.dtau_t.copy_(host[2])
     h2d_bytes, d2h_bytes = hs.h2d_bytes, hs.d2h_bytes
     del hs, host
@@ -639,6 +679,7 @@ def run_ours(args):
     loop_ms = l0.elapsed_time(l1)
 
     loop_h2d, loop_d2h = hs.run_h2d_bytes(loop_k), hs.run_d2h_bytes(loop_k)
+    loop_chunks = [m for _, m in hs.schedule]
     del hs
     barrier()
     pcie = pcie_duplex_gbs(torch, ctx.device)      # all ranks at once: what the HOST sustains with N GPUs copying
@@ -702,7 +743,7 @@ def run_ours(args):
             # API: the caller's pinned (N,6) coords / valley / dtau go in once, 50 timesteps run in HBM,
             # the arrays and 50 observable rows come back.  The one-call-per-timestep API is kept beside it.
             "e2e": {"value": seg_loop / (loop_ms * 1e-3), "unit": UNIT, "steps": loop_k * loop_calls,
-                    "steps_per_call": loop_k, "calls": loop_calls,
+                    "steps_per_call": loop_k, "calls": loop_calls, "chunk_particles": loop_chunks,
                     "ms_per_step": loop_ms / (loop_k * loop_calls),
                     "h2d_bytes_per_step": loop_h2d / loop_k, "d2h_bytes_per_step": loop_d2h / loop_k,
                     "h2d_bytes_per_call": loop_h2d, "d2h_bytes_per_call": loop_d2h,
@@ -717,7 +758,7 @@ def run_ours(args):
                         "bound": "PCIe / host DRAM: 60 B per particle each way per timestep; the kernel is 3 % of it"},
                     "pcie_duplex_gbs_per_direction_per_gpu_all_ranks_copying": pcie_min,
                     "host_binding": binding},
-            "fused_timesteps": fused,
+            "fused_timesteps": fused, "chained_timesteps": chained,
             "gpu_launches": int(launches), "clocks": clk, "knobs": active_knobs(ctx),
             "coupled": coupled, "coupled_multigrid": coupled_mg, "coupled_strong_1e8": coupled_strong, "by_config": by_config,
         }

@@ -205,6 +205,8 @@ extern "C" int emc_create(const EmcParams *params, int device, EmcCtx **out)
         c->no_field_ahead = fa && std::atoi(fa) == 0;
         const char *fs = std::getenv("EMC_FUSED_STEPS");
         c->no_fused_steps = fs && std::atoi(fs) == 0;
+        const char *cs = std::getenv("EMC_CHAIN_STEPS");
+        c->no_chain = cs && std::atoi(cs) == 0;
         const char *tm = std::getenv("EMC_REFILL_TENSOR_MAP");
         c->no_tensor_map = tm && std::atoi(tm) == 0;
         const char *ln = std::getenv("EMC_LEAN");
@@ -246,6 +248,8 @@ extern "C" void emc_destroy(EmcCtx *ctx)
     if (c->d_groups) cudaFree(c->d_groups);
     if (c->partials) cudaFree(c->partials);
     if (c->ticket) cudaFree(c->ticket);
+    if (c->d_chain) cudaFree(c->d_chain);
+    if (c->chain_partials) cudaFree(c->chain_partials);
     if (c->d_obs) cudaFree(c->d_obs);
     if (c->d_sor_scalars) cudaFree(c->d_sor_scalars);
     if (c->d_sor_flags) cudaFree(c->d_sor_flags);
@@ -452,10 +456,10 @@ extern "C" int emc_describe(const EmcCtx *ctx, char *buf, int32_t cap)
     const char *sor = std::getenv("EMC_SOR_BLOCKS_PER_SM");
     const int n = std::snprintf(buf, (size_t)cap,
                                 "exact_libm=%d zonly_constant=%d zonly_groups=%d field_ahead=%d bulk_refill=%d lean=%d waves=%d max_grid=%d "
-                                "obs_before=%d n_layers=%d literal_scan=%d sor_blocks_per_sm=%s flight_threads=%d refill_tensor_map=%d",
+                                "obs_before=%d n_layers=%d literal_scan=%d sor_blocks_per_sm=%s flight_threads=%d refill_tensor_map=%d chain_steps=%d",
                                 (int)c->exact_libm, (int)c->zonly_constant, (int)c->zonly_groups,
                                 (int)!c->no_field_ahead, (int)!c->no_bulk_refill, (int)(!c->no_lean && c->self_last), c->waves, c->max_grid, c->obs_before, c->dc.n_layers,
-                                c->dc.literal_scan, sor ? sor : "auto", FLIGHT_THREADS, (int)(!c->no_tensor_map && c->tmap_base != nullptr));
+                                c->dc.literal_scan, sor ? sor : "auto", FLIGHT_THREADS, (int)(!c->no_tensor_map && c->tmap_base != nullptr), (int)!c->no_chain);
     return n < cap ? n : cap - 1;
 }
 
@@ -617,7 +621,23 @@ extern "C" int emc_flight_scatter_steps(EmcCtx *ctx, double *kx, double *ky, dou
         cudaError_t e = launch_flight_steps(c, A, field_mode, n_steps, (cudaStream_t)stream);
         return e == cudaSuccess ? EMC_OK : fail_cuda(c, e, "flight_steps launch");
     }
-    for (int32_t s = 0; s < n_steps; ++s) {
+    int32_t s = 0;
+    // per-step observable rows in the before-step phase and the lean conditions hold: timestep chains, i.e. up to
+    // CHAIN_MAX_STEPS timesteps with their rows per persistent launch (launch_flight_chain), bit-identical -- state
+    // and rows -- to the loop below
+    while (obs_rows && c->obs_before && c->have_tables && n > 0 && n_steps - s >= 2) {
+        const int32_t k = n_steps - s < CHAIN_MAX_STEPS ? n_steps - s : CHAIN_MAX_STEPS;
+        FlightArgs A;
+        std::memset(&A, 0, sizeof(A));
+        A.kx = kx; A.ky = ky; A.kz = kz; A.x = x; A.y = y; A.z = z; A.dtau = dtau; A.valley = valley; A.n = n;
+        A.seed = seed; A.pid_offset = pid_offset; A.step = first_step + (uint32_t)s;
+        A.obs = obs_rows + s;
+        const cudaError_t e = launch_flight_chain(c, A, field_mode, k, (cudaStream_t)stream);
+        if (e == cudaErrorNotSupported) break;              // nothing enqueued: one launch per timestep
+        if (e != cudaSuccess) return fail_cuda(c, e, "flight chain launch");
+        s += k;
+    }
+    for (; s < n_steps; ++s) {
         FlightArgs A;
         std::memset(&A, 0, sizeof(A));
         A.kx = kx; A.ky = ky; A.kz = kz; A.x = x; A.y = y; A.z = z; A.dtau = dtau; A.valley = valley; A.n = n;

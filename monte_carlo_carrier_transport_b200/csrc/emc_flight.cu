@@ -85,8 +85,11 @@ __device__ __forceinline__ void obs_particle(const DevConst &P, const Mat &MT, A
 // Deterministic two-level reduction: warp shuffles, then shared memory, one partial per block;
 // the last block to finish (ticket) folds the partials in a fixed order, so the result does
 // not depend on block scheduling.
+// (bidx / nblk: the block's slot and the number of slots -- blockIdx.x / gridDim.x, or the slice of a timestep
+// chain's work item and the number of slices; a chain's per-timestep tickets are zeroed by the host, not here)
 template <class Acc>
-__device__ void obs_block_reduce_and_finish(const Acc &acc, ObsPartial *partials, unsigned int *ticket, EmcObs *out)
+__device__ void obs_block_reduce_and_finish(const Acc &acc, ObsPartial *partials, unsigned int *ticket, EmcObs *out,
+                                            const unsigned int bidx, const unsigned int nblk, const bool reset_ticket)
 {
     __shared__ ObsPartial warp_part[32];
     __shared__ bool is_last;
@@ -118,10 +121,10 @@ __device__ void obs_block_reduce_and_finish(const Acc &acc, ObsPartial *partials
             for (int k = 0; k < 5; ++k) t.d[k] += warp_part[w].d[k];
             for (int k = 0; k < 6; ++k) t.c[k] += warp_part[w].c[k];
         }
-        partials[blockIdx.x] = t;
+        partials[bidx] = t;
         __threadfence();
         const unsigned int done = atomicAdd(ticket, 1u);
-        is_last = (done == gridDim.x - 1);
+        is_last = (done == nblk - 1);
     }
     __syncthreads();
     if (!is_last) return;
@@ -131,15 +134,15 @@ __device__ void obs_block_reduce_and_finish(const Acc &acc, ObsPartial *partials
         const int k = threadIdx.x;
         if (k < 5) {
             double s = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[b].d[k]);
+            for (unsigned int b = 0; b < nblk; ++b) s += __ldcg(&partials[b].d[k]);
             (&out->sum_z)[k] = s;
         } else {
             long long s = 0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[b].c[k - 5]);
+            for (unsigned int b = 0; b < nblk; ++b) s += __ldcg(&partials[b].c[k - 5]);
             (&out->n_valley[0])[k - 5] = s;      // n_valley[3], n_fault, n_segments, n_events are contiguous
         }
     }
-    if (threadIdx.x == 0) *ticket = 0u;
+    if (threadIdx.x == 0 && reset_ticket) *ticket = 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -577,6 +580,11 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
     if (FIELD == EMC_FIELD_GROUPS) Q.grp[slot] = p.grp;
 }
 
+#ifndef EMC_INTERLEAVE_BATCHES
+// 1: the lean constant / group-field kernels give a warp every W-th batch of the ensemble instead of a contiguous
+// run (see ILV in flight_scatter_kernel)
+#define EMC_INTERLEAVE_BATCHES 1
+#endif
 #ifndef EMC_LANE_IN_REGISTER
 #define EMC_LANE_IN_REGISTER 1
 #endif
@@ -673,12 +681,19 @@ __device__ __forceinline__ void queue_pop(const WarpQueue &Q, int slot, Particle
 // alternative of those run-time switches compiled OUT.  The kernel is sensitive to the size of its
 // loop (three copies of the flight code cost 50 %, profiles/ab_r2g): 270 instructions and 9 registers
 // fewer are 2.4 % (profiles/ab_r2h).  launch_flight picks it whenever the conditions hold.
-template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML, bool LEAN = false>
+// CHAIN (lean constant / group-field kernels): the block does not run ONE timestep of slice blockIdx.x but pops
+// (slice, timestep) work items from the FIFO of a timestep chain (ChainCtl, emc_host.h) until all
+// A.chain_steps x A.chain_slices of them are done -- K timesteps WITH their observable rows in one persistent
+// launch.  Same slices, same arithmetic, same Philox counters and the same fixed-order fold of the observable
+// partials (by slice) as K launches: bit-identical state and rows.
+template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML, bool LEAN = false, bool CHAIN = false>
 __global__ void EMC_FLIGHT_BOUNDS
 flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant__ MechMeta Mg,
                       const __grid_constant__ FlightArgs A, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr bool REPLAY = Stream::is_replay;
+    static_assert(!CHAIN || (LEAN && !ML && (FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS)),
+                  "timestep chains: lean single-layer constant / group-field kernels only");
     constexpr bool ZON = LEAN && (FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS);   // zonly known at compile time
     static_assert(!LEAN || (!REPLAY && !EXACT && !DEPOSIT), "LEAN is the Philox / default-libm / no-deposit kernel");
     constexpr bool THR = LEAN && EMC_SELF_THRESHOLD && !EMC_STAGE_REFILL;
@@ -711,6 +726,54 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     }
     __syncthreads();
 
+    uint32_t rt_count = 0;                                        // bulk batches consumed so far (mbarrier phase: across work items)
+    [[maybe_unused]] bool chain_first = true;
+    [[maybe_unused]] __shared__ unsigned long long chain_item_s;
+    for (;;) {                                                    // CHAIN: one work item per pass; otherwise a single pass
+    unsigned int bid = blockIdx.x, nblk = gridDim.x;              // the block's slice and the number of slices
+    uint32_t step_now = A.step;
+    EmcObs *obs_out = A.obs;
+    ObsPartial *obs_parts = A.partials;
+    unsigned int *obs_ticket = A.ticket;
+    [[maybe_unused]] uint32_t chain_j = 0;
+    if constexpr (CHAIN) {
+        if (threadIdx.x == 0) {
+            ChainCtl *C = A.chain;
+            const unsigned int total = (unsigned int)A.chain_steps * (unsigned int)A.chain_slices;
+            const unsigned int T = atomicAdd(&C->popped, 1u);
+            unsigned long long item;
+            if (T >= total) {
+                item = ~0ull;                                     // every item has an owner: done
+            } else if (T < (unsigned int)A.chain_slices) {
+                item = (unsigned long long)T;                     // timestep 0 of slice T: the state as the caller left it
+            } else {
+                // item T is pushed by the block that finishes the timestep before it on that slice: a block with a
+                // smaller ticket, i.e. one that is running (all blocks are resident: one wave)
+                const unsigned long long *slot = &C->ready[T % CHAIN_RING];
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(item) : "l"(slot) : "memory");
+                    if ((unsigned int)(item >> 32) == T + 1u) break;
+                    __nanosleep(64);
+                }
+                item &= 0xffffffffull;
+                __threadfence();
+            }
+            chain_item_s = item;
+        }
+        __syncthreads();
+        const unsigned long long item = chain_item_s;
+        if (item == ~0ull) break;
+        // the slice was written by another SM's ordinary stores and is read here by the copy engine (async proxy)
+        asm volatile("fence.proxy.async;" ::: "memory");
+        bid = (unsigned int)__shfl_sync(0xffffffffu, (int)(item & 0xffffu), 0);
+        chain_j = (uint32_t)__shfl_sync(0xffffffffu, (int)((item >> 16) & 0xffffu), 0);
+        nblk = (unsigned int)A.chain_slices;
+        step_now = A.step + chain_j;
+        obs_out = A.obs + chain_j;
+        obs_parts = A.partials + (size_t)chain_j * nblk;
+        obs_ticket = &A.chain->step_done[chain_j];
+    }
+
     FlightObsAcc acc;
     acc.zero(obs_columns + threadIdx.x);
 
@@ -733,33 +796,54 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
 #endif
     WarpQueues &WQ = queues[warp];
     FieldStage &FS = fstages[AHEAD ? warp : 0];                   // only dereferenced when AHEAD
-    const int64_t total_warps = (int64_t)gridDim.x * (FLIGHT_THREADS / 32);
-    const int64_t gw = (int64_t)blockIdx.x * (FLIGHT_THREADS / 32) + warp;
-    const int64_t slice = (((A.n + total_warps - 1) / total_warps) + 31) & ~(int64_t)31;
-    int64_t wstart = gw * slice;
-    if (wstart > A.n) wstart = A.n;
-    const int64_t wend = (wstart + slice < A.n) ? wstart + slice : A.n;
-    // loop state in 32 bits (a warp's slice is shorter than 2^29 particles: the queues pack the
-    // valley above the slice offset): `next` and the slice length relative to wstart
+    const int64_t total_warps = (int64_t)nblk * (FLIGHT_THREADS / 32);
+    const int64_t gw = (int64_t)bid * (FLIGHT_THREADS / 32) + warp;
+    // ILV (lean constant / group-field kernels): a warp's batches are interleaved with the other warps' -- batch
+    // gw, gw + W, gw + 2 W ... of the ensemble (W = all warps of the grid) -- instead of one contiguous run.  With
+    // field groups a contiguous run lies inside ONE group, and the groups differ in work (a 50 kV/cm group has
+    // several times the real scattering of a 0.1 kV/cm one): the blocks of configs[1] finished 3.3 % apart (ncu
+    // r2z: sm__cycles_active min / max).  Interleaved, every warp samples every group.  Batches stay 32 consecutive
+    // particles (the same 256-byte row slices), and at any moment the grid works on one contiguous window of the
+    // ensemble.  A particle's offset in its warp's run (`next` + lane, p.off) -> its index: w0 + (off / 32) * 32 W + off % 32.
+    constexpr bool ILV = EMC_INTERLEAVE_BATCHES && ZON;
+    int64_t wstart, wend;
+    uint32_t wlen_;
+    if (ILV) {
+        const int64_t nb = (A.n + 31) >> 5;                       // batches of the ensemble, the last one may be ragged
+        const int64_t mine = gw < nb ? (nb - gw + total_warps - 1) / total_warps : 0;
+        wstart = mine ? gw * 32 : 0;
+        wlen_ = (uint32_t)(mine * 32);
+        if (mine && gw + (mine - 1) * total_warps == nb - 1) wlen_ -= (uint32_t)(nb * 32 - A.n);
+        wend = 0;                                                 // (only the disabled staging variant reads it)
+    } else {
+        const int64_t slice = (((A.n + total_warps - 1) / total_warps) + 31) & ~(int64_t)31;
+        wstart = gw * slice;
+        if (wstart > A.n) wstart = A.n;
+        wend = (wstart + slice < A.n) ? wstart + slice : A.n;
+        wlen_ = (uint32_t)(wend - wstart);
+    }
+    const uint32_t Wp = ILV ? (uint32_t)total_warps : 1u;         // stride of the warp's batches, in batches
+    // loop state in 32 bits (a warp's run is shorter than 2^29 particles: the queues pack the
+    // valley above the offset): `next` and the length of the run relative to wstart
     uint32_t next = 0;
-    const uint32_t wlen = (uint32_t)(wend - wstart);
+    const uint32_t wlen = wlen_;
     const uint32_t w0 = (uint32_t)wstart;
     RefillTile *RTW = rtiles + (BULK ? warp * EMC_REFILL_TILES : 0);      // only dereferenced when BULK
     // the full batches of the slice are issued in order, EMC_REFILL_TILES ahead, into the tiles in turn:
     // batch b uses tile b % TILES and the mbarrier phase (b / TILES) & 1
-    uint32_t rt_count = 0;                                        // bulk batches consumed so far
     if (BULK) {
-        if (elect_one()) {
+        if ((!CHAIN || chain_first) && elect_one()) {
 #pragma unroll
             for (int t = 0; t < EMC_REFILL_TILES; ++t)
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&RTW[t].bar)) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
+        chain_first = false;
         __syncwarp();
         if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < EMC_REFILL_TILES; ++t)
-                if (wlen >= 32u * (t + 1)) refill_issue(RTW[t], A, w0 + 32u * t, &tmap);
+                if (wlen >= 32u * (t + 1)) refill_issue(RTW[t], A, w0 + 32u * t * Wp, &tmap);
         }
     }
 #if EMC_STAGE_REFILL
@@ -779,11 +863,18 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     int32_t grp_next = 0;
     uint32_t grp_rem = 0;
     const uint32_t gsz = (uint32_t)P.group_size;
+    [[maybe_unused]] uint32_t grp_dq = 0, grp_dr = 32;            // one batch further on: groups / remainder to add
     if (FIELD == EMC_FIELD_GROUPS) {
         const uint64_t g0 = A.pid_offset + (uint64_t)wstart;
         const uint64_t gq = g0 / (uint64_t)P.group_size;
         grp_next = (int32_t)(gq < (uint64_t)P.n_groups ? gq : (uint64_t)P.n_groups);
         grp_rem = (uint32_t)(g0 % (uint64_t)P.group_size);
+        if (ILV) {                                                // the warp's next batch is 32 W particles further on
+            const uint64_t delta = 32ull * (uint64_t)total_warps;
+            const uint64_t dq = delta / (uint64_t)P.group_size;
+            grp_dq = (uint32_t)(dq < 0x7fffffffull ? dq : 0x7fffffffull);
+            grp_dr = (uint32_t)(delta % (uint64_t)P.group_size);
+        }
     }
 
     // The phases share ONE copy of the event tail, the flight segment, the retirement and the
@@ -864,7 +955,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         constexpr bool REFILL_FLIES = EMC_REFILL_FLIES && LEAN && (EMC_REFILL_FLIES > 1 || !MESHF);
         if (phase == PH_REFILL) {
             // ---- refill phase: main_.py:361-373 for the next 32 particles -----------------------
-            i = w0 + next + lane;
+            i = w0 + next * Wp + lane;
             act = next + lane < wlen;
             if (AHEAD && next + lane + 32 < wlen) {
                 ahead = true;
@@ -898,12 +989,21 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(&RT.loaded)), "r"(fold) : "memory");
                 }
                 __syncwarp();
-                if (next + 32u * (EMC_REFILL_TILES + 1) <= wlen && elect_one()) refill_issue(RT, A, w0 + next + 32u * EMC_REFILL_TILES, &tmap);
+                if (next + 32u * (EMC_REFILL_TILES + 1) <= wlen && elect_one()) refill_issue(RT, A, w0 + (next + 32u * EMC_REFILL_TILES) * Wp, &tmap);
             } else if (act) {
+                if constexpr (CHAIN) {
+                    // the slice was written by another SM a moment ago: read it where that SM's stores went (L2), whatever
+                    // this SM's L1 still holds of an earlier timestep of the same slice
+                    p.kx = __ldcg(A.kx + i); p.ky = __ldcg(A.ky + i); p.kz = __ldcg(A.kz + i);
+                    p.x = __ldcg(A.x + i); p.y = __ldcg(A.y + i); p.z = __ldcg(A.z + i);
+                    p.dte = __ldcg(A.dtau + i);
+                    p.val = __ldcg(A.valley + i);
+                } else {
                 p.kx = A.kx[i]; p.ky = A.ky[i]; p.kz = A.kz[i];
                 p.x = A.x[i]; p.y = A.y[i]; p.z = A.z[i];
                 p.dte = A.dtau[i];
                 p.val = A.valley[i];
+                }
             }
             if (act) {
                 p.off = next + lane;
@@ -962,7 +1062,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 // row l>>1, lane 14 the valley line (the row pointers are consecutive kernel
                 // parameters, indexed from the constant bank)
                 const uint32_t o0 = next + (uint32_t)(EMC_PREFETCH_BATCHES - 1) * 32u;
-                const int64_t j0 = wstart + o0;
+                const int64_t j0 = wstart + (int64_t)o0 * Wp;
                 if (!BULK && o0 < wlen && lane < 15 && (!(lane & 1) || lane == 14 || o0 + 16 < wlen)) {
                     const char *base = reinterpret_cast<const char *>((&A.kx)[lane >> 1]);
                     const int64_t off = lane < 14 ? j0 * 8 + (lane & 1) * 128 : j0 * 4;
@@ -971,8 +1071,15 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             }
 #endif
             if (FIELD == EMC_FIELD_GROUPS) {
-                grp_rem += 32;
-                while (grp_rem >= gsz) { grp_rem -= gsz; ++grp_next; }
+                if (ILV) {
+                    // (saturating: past the last group every lane clamps to it anyway)
+                    grp_next = (int32_t)min((uint32_t)grp_next + grp_dq, 0x7fffffffu);
+                    grp_rem += grp_dr;                            // < 2 gsz <= 2^32
+                    if (grp_rem >= gsz) { grp_rem -= gsz; if (grp_next < 0x7fffffff) ++grp_next; }
+                } else {
+                    grp_rem += 32;
+                    while (grp_rem >= gsz) { grp_rem -= gsz; ++grp_next; }
+                }
             }
         } else {
             // ---- an event, main_.py:375-389 / scatter_.py:986-1099, in one or two passes ---------
@@ -1001,10 +1108,10 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             }
             __syncwarp();
             if (act) {
-                i = w0 + p.off;
+                i = ILV ? w0 + (p.off & ~31u) * Wp + (p.off & 31u) : w0 + p.off;
                 if (MESHF) { cell = mesh_cell_of<FIELD>(P, p); field_prefetch<FIELD>(A, cell); }
                 if constexpr (REPLAY) rng.init(A.uniforms, A.stride, i, (int32_t)s0);
-                else rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
+                else rng.init(A.seed, A.pid_offset + (uint64_t)i, step_now, s0);
                 int v = p.val, f;
                 if (ML) layer = where_am_i(P, p.z);               // :377 (and :387: a scatter does not move)
                 const Mat &MT = P.mat[ML ? (layer < 0 ? 0 : layer) : 0];
@@ -1051,7 +1158,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                         f = scatter_parked<Stream>(P, MT, M, p.kx, p.ky, p.kz, v, rng, pf);
                         lg = fast_log(rng.free_flight());
                     } else if constexpr (THR) {
-                        const EventOut o = event_cold(&P, &MT, &M, p.kx, p.ky, p.kz, v, A.seed, A.pid_offset + (uint64_t)i, A.step, s0);
+                        const EventOut o = event_cold(&P, &MT, &M, p.kx, p.ky, p.kz, v, A.seed, A.pid_offset + (uint64_t)i, step_now, s0);
                         f = o.f; lg = o.lg;
                         if (f < 0) { p.kx = o.kx; p.ky = o.ky; p.kz = o.kz; v = o.val; }
                     }
@@ -1177,13 +1284,28 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
         }
     }
     if (LEAN) acc.derive_segments();
-    if (A.obs) obs_block_reduce_and_finish(acc, A.partials, A.ticket, A.obs);
+    if (obs_out) obs_block_reduce_and_finish(acc, obs_parts, obs_ticket, obs_out, bid, nblk, !CHAIN);
+    if constexpr (!CHAIN) {
+        break;
+    } else {
+        // The slice is written back: hand its next timestep to whichever block asks next.  Every thread's state
+        // stores precede the barriers of the reduction above, thread 0's fence makes them visible at GPU scope
+        // before the item (release), and the popping thread acquires it.
+        if (threadIdx.x == 0 && chain_j + 1u < (uint32_t)A.chain_steps) {
+            ChainCtl *C = A.chain;
+            __threadfence();
+            const unsigned int Pn = (unsigned int)A.chain_slices + atomicAdd(&C->pushed, 1u);
+            const unsigned long long v = ((unsigned long long)(Pn + 1u) << 32) | ((unsigned long long)(chain_j + 1u) << 16) | bid;
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&C->ready[Pn % CHAIN_RING]), "l"(v) : "memory");
+        }
+    }
+    }   // work items
 }
 
-template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML, bool LEAN = false>
+template <class Stream, int FIELD, bool EXACT, bool DEPOSIT, bool ML, bool LEAN = false, bool CHAIN = false>
 static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid, size_t smem, cudaStream_t st)
 {
-    auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT, ML, LEAN>;
+    auto k = flight_scatter_kernel<Stream, FIELD, EXACT, DEPOSIT, ML, LEAN, CHAIN>;
     // launch_flight sized `smem` for the general queues; the lean kernels' are smaller or larger
     smem = smem - sizeof(WarpQueues) * (FLIGHT_THREADS / 32) + sizeof(typename FlightQueues<LEAN, ML>::type) * (FLIGHT_THREADS / 32);
     // persistent grid: exactly the blocks that are resident at once (one wave), unless the
@@ -1203,6 +1325,15 @@ static cudaError_t launch_flight_k(const Ctx *ctx, const FlightArgs &A, int grid
     const int per_sm = cached_per_sm[dev];
     const int resident = ctx->sm_count * per_sm * ctx->waves;
     if (grid > resident) grid = resident;
+    if constexpr (CHAIN) {
+        // the slices of a chain are the blocks of the one-timestep launch; all of them resident (a block waits for items
+        // that running blocks produce)
+        if (ctx->waves != 1 || grid > ctx->sm_count * per_sm) return cudaErrorNotSupported;
+        FlightArgs B = A;
+        B.chain_slices = grid;
+        k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, B, ctx->state_tmap);
+        return cudaGetLastError();
+    }
     k<<<grid, FLIGHT_THREADS, smem, st>>>(ctx->dc, ctx->mech, A, ctx->state_tmap);
     return cudaGetLastError();
 }
@@ -1213,6 +1344,10 @@ static cudaError_t launch_flight_t(const Ctx *ctx, const FlightArgs &A, int grid
     if constexpr (!Stream::is_replay) {
         // the lean instantiation (see flight_scatter_kernel) whenever its compile-time assumptions hold
         const bool zon_ok = (FIELD != EMC_FIELD_CONSTANT && FIELD != EMC_FIELD_GROUPS) || ctx->dc.zonly;
+        if constexpr (FIELD == EMC_FIELD_CONSTANT || FIELD == EMC_FIELD_GROUPS) {
+            if (A.chain)      // launch_flight_chain has checked the lean conditions
+                return launch_flight_k<Stream, FIELD, false, false, false, true, true>(ctx, A, grid, smem, st);
+        }
         if (EMC_LEAN_KERNEL && !ctx->no_lean && !ctx->exact_libm && !A.mesh && !(A.obs && !A.obs_before) &&
             !ctx->dc.literal_scan && ctx->self_last && zon_ok)
             return ctx->dc.n_layers > 1 ? launch_flight_k<Stream, FIELD, false, false, true, true>(ctx, A, grid, smem, st)
@@ -1301,8 +1436,10 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
         // privatise the counts in shared memory only while two blocks per SM still fit beside the queues
         if (cells * 4 <= 16 * 1024) { A.smem_cells = (int)cells; smem += (size_t)cells * 4; }
     }
-    A.partials = ctx->partials;
-    A.ticket = ctx->ticket;
+    if (!A.chain) {
+        A.partials = ctx->partials;
+        A.ticket = ctx->ticket;
+    }
     A.mech_layers = ctx->d_mech_layers;
     ctx->launches++;
 #define EMC_DISPATCH(STREAM)                                                                     \
@@ -1322,6 +1459,45 @@ cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, 
     if (replay) { EMC_DISPATCH(ReplayStream) } else { EMC_DISPATCH(PhiloxStream) }
 #endif
 #undef EMC_DISPATCH
+}
+
+// ------------------------------------------------------------------------------------------
+// Timestep chain: n_steps timesteps WITH their observable rows in one persistent launch of the lean one-timestep
+// kernel (CHAIN instantiation, ChainCtl in emc_host.h).  What it removes is the time an SM idles per launch: the
+// launch ramp, the spread of the blocks' finishing times (ncu r2z: the average SM is busy 97.3 % of a 0.92-ms
+// launch, i.e. 25 us idle; ~30 us of a 0.18-ms launch over a 2^22-particle chunk of the host-array loop), the
+// gap between launches.  The state makes the same HBM round trip per timestep as with n_steps launches.
+// cudaErrorNotSupported: the conditions do not hold (nothing has been enqueued); the caller loops over launches.
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_flight_chain(Ctx *ctx, FlightArgs &A, int field_mode, int n_steps, cudaStream_t st)
+{
+    const bool zonly = (field_mode == EMC_FIELD_CONSTANT && ctx->zonly_constant) || (field_mode == EMC_FIELD_GROUPS && ctx->zonly_groups);
+    if (!EMC_LEAN_KERNEL || ctx->no_chain || ctx->no_lean || ctx->exact_libm || ctx->dc.literal_scan || !ctx->self_last ||
+        !zonly || ctx->dc.n_layers != 1 || ctx->waves != 1 || !ctx->obs_before || !A.obs || A.mesh ||
+        (field_mode != EMC_FIELD_CONSTANT && field_mode != EMC_FIELD_GROUPS) ||
+        (field_mode == EMC_FIELD_GROUPS && !ctx->dc.field_groups) || n_steps < 2 || n_steps > CHAIN_MAX_STEPS ||
+        A.n < 1 || A.n >= ((int64_t)1 << 32) - 64 || ctx->max_grid > 65535)
+        return cudaErrorNotSupported;
+    cudaError_t e;
+    if (!ctx->d_chain && (e = cudaMalloc(&ctx->d_chain, sizeof(ChainCtl))) != cudaSuccess) return e;
+    const size_t need = (size_t)n_steps * (size_t)ctx->max_grid;
+    if (ctx->chain_partials_cap < need) {
+        // (cudaFree synchronises the device: an earlier chain may still be using the old buffer; growth is rare)
+        if (ctx->chain_partials && (e = cudaFree(ctx->chain_partials)) != cudaSuccess) return e;
+        ctx->chain_partials = nullptr;
+        ctx->chain_partials_cap = 0;
+        if ((e = cudaMalloc(&ctx->chain_partials, sizeof(ObsPartial) * need)) != cudaSuccess) return e;
+        ctx->chain_partials_cap = need;
+    }
+    if ((e = cudaMemsetAsync(ctx->d_chain, 0, sizeof(ChainCtl), st)) != cudaSuccess) return e;
+    A.chain = ctx->d_chain;
+    A.chain_steps = n_steps;
+    A.chain_slices = 0;                   // launch_flight_k: the grid it launches
+    A.partials = ctx->chain_partials;
+    A.ticket = nullptr;
+    A.obs_before = 1;
+    ctx->dc.zonly = zonly;
+    return launch_flight(ctx, A, false, field_mode, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1614,7 +1790,7 @@ observables_kernel(const __grid_constant__ DevConst P, const double *kx, const d
             obs_particle(P, P.mat[layer], acc, a[u], b[u], c[u], zz[u], val);
         }
     }
-    obs_block_reduce_and_finish(acc, partials, ticket, out);
+    obs_block_reduce_and_finish(acc, partials, ticket, out, blockIdx.x, gridDim.x, true);
 }
 
 cudaError_t launch_observables(Ctx *ctx, const double *kx, const double *ky, const double *kz, const double *z,

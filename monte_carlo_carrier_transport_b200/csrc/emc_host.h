@@ -18,6 +18,22 @@ struct ObsPartial {
     long long c[6];
 };
 
+// Control block of a timestep chain (flight_scatter_kernel<..., CHAIN = true>, launch_flight_chain): K timesteps
+// WITH their observable rows in one persistent launch.  The work items are (slice, timestep) pairs in a FIFO in
+// device memory: a block pops one, runs the one-timestep body on that slice, and pushes (slice, timestep + 1) when
+// it has written the slice back -- no grid-wide barrier between timesteps (slices are independent: a timestep
+// only needs ITS slice of the previous one), so a slow SM never holds the others up and there is no launch gap.
+// ready[i]: (i + 1) << 32 | timestep << 16 | slice, written with release semantics; the first `slices` items
+// (timestep 0 of every slice) are implicit.  Zeroed by a memset before every chain launch.
+constexpr int CHAIN_RING = 4096;          // >> the number of items in flight (<= slices <= max_grid)
+constexpr int CHAIN_MAX_STEPS = 1024;     // timesteps per chain launch (longer loops are split)
+struct ChainCtl {
+    unsigned int popped, pushed;
+    unsigned int pad[30];
+    unsigned long long ready[CHAIN_RING];
+    unsigned int step_done[CHAIN_MAX_STEPS];      // observable partials of a timestep written so far
+};
+
 // kernel arguments of the timestep kernel (device pointers are the caller's)
 struct FlightArgs {
     double *kx, *ky, *kz, *x, *y, *z, *dtau;
@@ -41,6 +57,9 @@ struct FlightArgs {
     int32_t obs_before;          // emc_set_obs_phase: reduce the observables of the state as loaded
     int32_t bulk;                // refill batches arrive by bulk async copies (launch_flight decides: aligned rows)
     const MechMeta *mech_layers; // multi-layer: device array of n_layers mechanism-metadata blocks
+    // timestep chain (CHAIN kernels): obs = the first of chain_steps rows, partials = [chain_steps][chain_slices]
+    ChainCtl *chain;
+    int32_t chain_steps, chain_slices;
 };
 
 struct Ctx {
@@ -91,6 +110,11 @@ struct Ctx {
     int64_t tmap_n = 0;
     ptrdiff_t tmap_pitch = 0;
     bool no_tensor_map = false;   // EMC_REFILL_TENSOR_MAP=0 in the environment (A/B, tests)
+    // timestep chain: control block and per-timestep observable partials (grown on demand)
+    ChainCtl *d_chain = nullptr;
+    ObsPartial *chain_partials = nullptr;
+    size_t chain_partials_cap = 0;    // in ObsPartial units
+    bool no_chain = false;        // EMC_CHAIN_STEPS=0 in the environment: one launch per timestep (A/B, tests)
     int64_t launches = 0;
     std::string last_error;
 };
@@ -98,6 +122,9 @@ struct Ctx {
 // emc_flight.cu
 cudaError_t launch_flight(Ctx *ctx, FlightArgs &A, bool replay, int field_mode, cudaStream_t st);
 cudaError_t launch_flight_steps(Ctx *ctx, FlightArgs &A, int field_mode, int n_steps, cudaStream_t st);
+// n_steps timesteps with their observable rows (A.obs[0 .. n_steps)) in one persistent launch; cudaErrorNotSupported
+// = the chain conditions do not hold for this call (the caller launches once per timestep instead)
+cudaError_t launch_flight_chain(Ctx *ctx, FlightArgs &A, int field_mode, int n_steps, cudaStream_t st);
 cudaError_t launch_observables(Ctx *ctx, const double *kx, const double *ky, const double *kz, const double *z,
                                const int32_t *valley, int64_t n, EmcObs *out_dev, cudaStream_t st);
 cudaError_t launch_init_ensemble(Ctx *ctx, double *kx, double *ky, double *kz, double *x, double *y, double *z,

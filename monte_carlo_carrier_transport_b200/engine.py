@@ -820,6 +820,39 @@ class CoupledStepper:
         return self.mesh.last_solve()
 
 
+def chunk_schedule(n: int, chunk: int, ramp_from: int | None = None) -> list:
+    """[(first particle, count)] of ``HostStepper.run``'s chunks.  Without ``ramp_from``: equal chunks.
+    With it: ramp_from, 2 ramp_from, 4 ramp_from ... up to ``chunk``, chunks of ``chunk``, and the same
+    ramp down again (the remainder goes before the ramp down), e.g. 2.4e7 particles, chunk 2^23,
+    ramp_from 2^20: 1, 2, 4, 8, 4.9, 2, 1 Mi particles."""
+    n, chunk = int(n), max(int(chunk), 1)
+    if n <= 0:
+        return []
+    sizes = []
+    if ramp_from is None or ramp_from <= 0 or ramp_from >= chunk:
+        sizes = [chunk] * (n // chunk) + ([n % chunk] if n % chunk else [])
+    else:
+        up, c = [], int(ramp_from)
+        while c < chunk:
+            up.append(c)
+            c *= 2
+        down = up[::-1][1:] if len(up) > 1 else up[::-1]       # the top step of the ramp only once
+        while up and sum(up) + sum(down) > n:                  # small ensembles: shorten both ramps from the top
+            if len(up) >= len(down) + 1 or not down:
+                up.pop()
+            else:
+                down.pop(0)
+        rest = n - sum(up) - sum(down)
+        mid = [chunk] * (rest // chunk) + ([rest % chunk] if rest % chunk else [])
+        sizes = up + mid + down
+    out, lo = [], 0
+    for m in sizes:
+        out.append((lo, m))
+        lo += m
+    assert lo == n and all(0 < m <= chunk for _, m in out)
+    return out
+
+
 class HostStepper:
     """The timestep for callers that keep the reference's HOST arrays (main_.py:51-53,337):
     coords (N,6) float64, valley (N,) int32, dtau (N,) float64, all in pinned memory.
@@ -829,10 +862,18 @@ class HostStepper:
     chunks and the three stages (H2D, kernels, D2H) of consecutive chunks overlap on three
     CUDA streams, so the call runs at PCIe speed in both directions at once."""
 
-    def __init__(self, ctx: Context, n: int, chunk: int = 1 << 21, pid_offset: int = 0):
+    def __init__(self, ctx: Context, n: int, chunk: int = 1 << 21, pid_offset: int = 0, ramp_from: int | None = None):
+        """``chunk``: particles per chunk (and per device buffer).  ``ramp_from``: ``run`` then cuts the
+        ensemble into GRADUATED chunks (``chunk_schedule``): the first and the last copy of a loop are the
+        part of the PCIe traffic that no kernel overlaps, so the loop starts and ends with chunks of
+        ``ramp_from`` particles and doubles up to ``chunk`` in between, where long launches amortise the
+        fixed cost of a launch (~20 us of a 0.18-ms launch at 2^22 particles).  Results do not depend on
+        the chunking (Philox counters are global particle ids)."""
         torch = _torch()
         self.ctx, self.n, self.pid_offset = ctx, int(n), int(pid_offset)
         self.chunk = int(min(chunk, max(self.n, 1)))
+        self.ramp_from = None if ramp_from is None else int(ramp_from)
+        self.schedule = chunk_schedule(self.n, self.chunk, self.ramp_from)
         # pinned host arrays the caller reads / writes (numpy views)
         self.coords_t = torch.zeros((self.n, 6), dtype=torch.float64).pin_memory()
         self.valley_t = torch.zeros(self.n, dtype=torch.int32).pin_memory()
@@ -852,7 +893,7 @@ class HostStepper:
                 done=torch.cuda.Event(), free=torch.cuda.Event()))
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev), torch.cuda.Stream(dev),
                                              torch.cuda.Stream(dev))
-        self.n_chunks = (self.n + self.chunk - 1) // self.chunk
+        self.n_chunks = max((self.n + self.chunk - 1) // self.chunk, len(self.schedule))
         self.obs_pinned = torch.zeros((self.n_chunks, 11), dtype=torch.int64).pin_memory()
 
     @property
@@ -888,9 +929,7 @@ class HostStepper:
         was = c.obs_before
         c.set_obs_phase(True)
         try:
-            for ci in range(self.n_chunks):
-                lo = ci * self.chunk
-                m = min(self.chunk, self.n - lo)
+            for ci, (lo, m) in enumerate(self.schedule):
                 bi = ci % len(self.bufs)
                 b = self.bufs[bi]
                 with torch.cuda.stream(self.s_in):
@@ -926,7 +965,7 @@ class HostStepper:
             c.set_obs_phase(was)
         self.s_out.synchronize()
         cur.wait_stream(self.s_out)
-        raw = rows_pinned.numpy()[:, :n_steps + 1]
+        raw = rows_pinned.numpy()[:len(self.schedule), :n_steps + 1]
         d = raw[:, :, :5].copy().view(np.float64).sum(axis=0)         # (n_steps + 1, 5): sums over the chunks
         k = raw[:, :, 5:].sum(axis=0)
         out = []
@@ -943,7 +982,7 @@ class HostStepper:
         return self.h2d_bytes
 
     def run_d2h_bytes(self, n_steps: int) -> int:
-        return self.n * (48 + 4 + 8) + self.n_chunks * 88 * (int(n_steps) + 1)
+        return self.n * (48 + 4 + 8) + len(self.schedule) * 88 * (int(n_steps) + 1)
 
     def step(self, step: int, seed: int, field_mode: int = abi.FIELD_CONSTANT) -> dict:
         """One timestep on the pinned host arrays, in place; returns the observables."""
@@ -955,7 +994,7 @@ class HostStepper:
         cur = torch.cuda.current_stream(c.device)
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(cur)
-        for ci in range(self.n_chunks):
+        for ci in range((self.n + self.chunk - 1) // self.chunk):
             lo = ci * self.chunk
             m = min(self.chunk, self.n - lo)
             b = self.bufs[ci % len(self.bufs)]
@@ -987,7 +1026,7 @@ class HostStepper:
                 b["free"].record(self.s_out)
         self.s_out.synchronize()
         cur.wait_stream(self.s_out)
-        raw = self.obs_pinned.numpy()
+        raw = self.obs_pinned.numpy()[:(self.n + self.chunk - 1) // self.chunk]
         d = raw[:, :5].copy().view(np.float64).sum(axis=0)
         k = raw[:, 5:].sum(axis=0)
         return dict(sum_z=float(d[0]), sum_vz=float(d[1]), sum_e=float(d[2]), sum_vz2=float(d[3]),

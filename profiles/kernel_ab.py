@@ -78,6 +78,27 @@ def main():
         out["configs1_fused_K%d" % K] = {"ms_per_timestep": ms, "frac_of_hbm_6553.9_algorithmic_120B": 120 * n / (ms * 1e-3) / 1e9 / 6553.9,
                                          "state_checksum": checksum(torch, ens2)}
         del ens2
+    # ... and with K timesteps AND their observable rows per persistent launch (timestep chain)
+    for K in (() if args.no_fused else (50,)):
+        ens3 = engine.Ensemble(ctx, n).init(bench.SEED)
+        rows = torch.zeros((3 * K, 11), dtype=torch.int64, device=ctx.device)
+        ctx.set_obs_phase(True)
+        call = lambda r: ctx.check(ctx.lib.emc_flight_scatter_steps(ctx.h, *ens3._ptrs(), n, abi.FIELD_GROUPS, None, None, None,
+                                                                      bench.SEED, 0, r * K, K, rows[r * K:].data_ptr(), ctx.stream))
+        call(0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        call(1)
+        call(2)
+        b.record()
+        torch.cuda.synchronize()
+        ctx.set_obs_phase(False)
+        ms = a.elapsed_time(b) / (2 * K)
+        out["configs1_chained_K%d" % K] = {"ms_per_timestep": ms, "frac_of_hbm_6553.9": 120 * n / (ms * 1e-3) / 1e9 / 6553.9,
+                                           "rows_checksum": "%016x" % (int(rows.sum().item()) & 0xFFFFFFFFFFFFFFFF),
+                                           "state_checksum": checksum(torch, ens3)}
+        del ens3
     ctx.close()
     del ens
     if args.mesh:

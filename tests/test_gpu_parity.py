@@ -434,8 +434,10 @@ def test_host_stepper_whole_loop_matches_device_path(ctx, torch_mod):
     for s in range(K):
         ens.step(100 + s, 98)
         want.append(ens.last_obs())
-    for chunk in (7000, 1 << 21):
-        hs = engine.HostStepper(ctx, n, chunk=chunk, pid_offset=11)
+    # (equal chunks, one chunk, and the graduated schedule: 1024, 2048, ... 16384, ..., 2048, 1024 particles)
+    for chunk, ramp in ((7000, None), (1 << 21, None), (16384, 1024)):
+        hs = engine.HostStepper(ctx, n, chunk=chunk, pid_offset=11, ramp_from=ramp)
+        assert sum(m for _, m in hs.schedule) == n and (ramp is None or hs.schedule[0][1] == hs.schedule[-1][1] == ramp)
         hs.coords[:], hs.valley[:], hs.dtau[:] = coords, v, dtau
         rows = hs.run(100, K, 98)
         co, val, dt_ = ens.coords()
@@ -446,7 +448,7 @@ def test_host_stepper_whole_loop_matches_device_path(ctx, torch_mod):
                 assert got[key] == ref[key], key
             for key in ("sum_z", "sum_vz", "sum_e", "sum_vz2", "sum_e2"):
                 assert abs(got[key] - ref[key]) <= 1e-11 * abs(ref[key]), key
-        assert hs.run_d2h_bytes(K) == n * 60 + hs.n_chunks * 88 * (K + 1)
+        assert hs.run_d2h_bytes(K) == n * 60 + len(hs.schedule) * 88 * (K + 1)
     assert not ctx.obs_before                                   # the phase switch is restored
 
 
@@ -765,6 +767,61 @@ def test_ragged_ensemble_sizes_vs_oracle(ctx, torch_mod, n):
         assert k_err(co[ok, :3], ref[ok, :3]) < 1e-6
     frozen = ~ok & (v < 0)
     assert np.array_equal(co[frozen], coords[frozen])                    # frozen on entry: untouched
+
+
+@pytest.mark.parametrize("mode", ["constant", "groups"])
+def test_timestep_chain_bit_identical_to_one_launch_per_timestep(ctx, torch_mod, mode):
+    """emc_flight_scatter_steps WITH observable rows in the before-step phase = timestep chains: K timesteps and
+    their K rows in ONE persistent launch, the blocks popping (slice, timestep) items from a device-side FIFO
+    (flight_scatter_kernel<..., CHAIN>).  State AND rows equal K single launches bit for bit (same slices, same
+    counters, same fixed-order fold by slice) -- ragged sizes, frozen particles, one slice and all 148, per-group
+    fields -- and repeating the chain gives the same bits (the FIFO order is not part of the result)."""
+    torch = torch_mod
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    g = helpers.golden_params()["phys"]
+    K, seed = 9, 1234
+    fields = np.array([[0, 0, -300.0], [0, 0, -5000.0], [0, 0, -20000.0], [0, 0, -50000.0]])
+    assert ctx.describe().get("chain_steps") == "1"
+    for n in (1, 33, 4097, 300001, 2_000_003):
+        coords, v, dtau = hot_ensemble(n, 70 + n % 5, g)
+        v[::7] = np.where(np.arange(n)[::7] % 3 == 0, -4, v[::7])       # some particles frozen on entry
+        per = max(1, (n + 3) // 4)
+        if mode == "groups":
+            ctx.set_field_groups(fields, per)
+            fm = abi.FIELD_GROUPS
+        else:
+            ctx.set_efield([0, 0, -30000.0])
+            fm = abi.FIELD_CONSTANT
+        a = engine.Ensemble(ctx, n, pid_offset=5).load(coords, v, dtau)
+        rows_a = torch.zeros((K, 11), dtype=torch.int64, device=ctx.device)
+        ctx.set_obs_phase(True)
+        try:
+            for s in range(K):
+                a.step(20 + s, seed, field_mode=fm, obs_out=rows_a[s])
+            runs = []
+            for rep in range(2):
+                b = engine.Ensemble(ctx, n, pid_offset=5).load(coords, v, dtau)
+                rows_b = torch.zeros((K, 11), dtype=torch.int64, device=ctx.device)
+                before = ctx.launch_count()
+                ctx.check(ctx.lib.emc_flight_scatter_steps(ctx.h, *b._ptrs(), n, fm, None, None, None, seed, 5, 20, K,
+                                                           rows_b.data_ptr(), ctx.stream))
+                assert ctx.launch_count() - before == 1                 # one persistent launch
+                runs.append((b, rows_b))
+        finally:
+            ctx.set_obs_phase(False)
+        for b, rows_b in runs:
+            assert torch.equal(a.state, b.state) and torch.equal(a.valley, b.valley), (mode, n)
+            assert torch.equal(rows_a, rows_b), (mode, n)
+        assert int(rows_a[:, 9].sum()) > 0 or n == 1
+    ctx.set_efield(g["efield"])
+    # what a chain does not cover keeps the launch loop: a tilted field is not "Ex = Ey = +0"
+    n = 4097
+    coords, v, dtau = hot_ensemble(n, 77, g)
+    ctx.set_efield([100.0, 0, -30000.0])
+    b = engine.Ensemble(ctx, n).load(coords, v, dtau)
+    rows = b.run_steps(0, 3, seed)
+    ctx.set_efield(g["efield"])
+    assert len(rows) == 3
 
 
 @pytest.mark.parametrize("mode", ["constant", "groups"])

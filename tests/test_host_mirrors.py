@@ -122,3 +122,21 @@ def test_value_for_value_against_the_reference_modules():
         for k in ma[v]:
             assert ma[v][k]["dE"] == mb[v][k]["dE"] and ma[v][k]["trans"] == mb[v][k]["trans"]
             assert ma[v][k]["polar"].__name__ == mb[v][k]["polar"].__name__
+
+
+def test_host_stepper_chunk_schedule():
+    """engine.chunk_schedule: every particle in exactly one chunk, none larger than the device buffer; the
+    graduated form starts and ends with the small chunk (the copies no kernel overlaps) and doubles in between."""
+    from monte_carlo_carrier_transport_b200.engine import chunk_schedule
+    for n, chunk, ramp in ((24_000_000, 1 << 23, 1 << 20), (24_000_000, 1 << 22, None), (10, 7, None), (10, 7, 2),
+                           (5_000_000, 1 << 23, 1 << 20), (1 << 20, 1 << 23, 1 << 20), (100, 1 << 23, 1 << 20),
+                           (3 << 20, 1 << 22, 1 << 20), (50001, 16384, 1024), (1, 1, 1), (0, 8, 2)):
+        sched = chunk_schedule(n, chunk, ramp)
+        lo = 0
+        for first, m in sched:
+            assert first == lo and 0 < m <= chunk
+            lo += m
+        assert lo == n
+    sizes = [m for _, m in chunk_schedule(24_000_000, 1 << 23, 1 << 20)]
+    assert sizes == [1 << 20, 1 << 21, 1 << 22, 1 << 23, 24_000_000 - (1 << 23) - (10 << 20), 1 << 21, 1 << 20]
+    assert [m for _, m in chunk_schedule(24_000_000, 1 << 22, None)] == [1 << 22] * 5 + [24_000_000 - 5 * (1 << 22)]
