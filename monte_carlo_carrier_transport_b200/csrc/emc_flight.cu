@@ -585,6 +585,9 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
 // run (see ILV in flight_scatter_kernel)
 #define EMC_INTERLEAVE_BATCHES 1
 #endif
+#ifndef EMC_INTERLEAVE_STEPS_KERNEL
+#define EMC_INTERLEAVE_STEPS_KERNEL 0
+#endif
 #ifndef EMC_LANE_IN_REGISTER
 #define EMC_LANE_IN_REGISTER 1
 #endif
@@ -1546,22 +1549,46 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
     StepQueues &WQ = queues[warp];
     const int64_t total_warps = (int64_t)gridDim.x * (FLIGHT_THREADS / 32);
     const int64_t gw = (int64_t)blockIdx.x * (FLIGHT_THREADS / 32) + warp;
-    const int64_t slice = (((A.n + total_warps - 1) / total_warps) + 31) & ~(int64_t)31;
-    int64_t wstart = gw * slice;
-    if (wstart > A.n) wstart = A.n;
-    const int64_t wend = (wstart + slice < A.n) ? wstart + slice : A.n;
+    // interleaved batches, as in flight_scatter_kernel (ILV): batch gw, gw + W, gw + 2 W ... of the ensemble, so that
+    // every warp samples every field group.  Measured SLOWER here (0.848 vs 0.832 ms per timestep at K = 10,
+    // profiles/r2av_ab_*: over K timesteps the groups' differences average out less than the strided plain loads
+    // and write-backs cost); off.
+    constexpr bool ILV = EMC_INTERLEAVE_STEPS_KERNEL != 0;
+    int64_t wstart;
+    uint32_t wlen_;
+    if (ILV) {
+        const int64_t nb = (A.n + 31) >> 5;
+        const int64_t mine = gw < nb ? (nb - gw + total_warps - 1) / total_warps : 0;
+        wstart = mine ? gw * 32 : 0;
+        wlen_ = (uint32_t)(mine * 32);
+        if (mine && gw + (mine - 1) * total_warps == nb - 1) wlen_ -= (uint32_t)(nb * 32 - A.n);
+    } else {
+        const int64_t slice = (((A.n + total_warps - 1) / total_warps) + 31) & ~(int64_t)31;
+        wstart = gw * slice;
+        if (wstart > A.n) wstart = A.n;
+        const int64_t wend = (wstart + slice < A.n) ? wstart + slice : A.n;
+        wlen_ = (uint32_t)(wend - wstart);
+    }
+    const uint32_t Wp = ILV ? (uint32_t)total_warps : 1u;
     uint32_t next = 0;
-    const uint32_t wlen = (uint32_t)(wend - wstart), w0 = (uint32_t)wstart;
+    const uint32_t wlen = wlen_, w0 = (uint32_t)wstart;
     int qn = 0, qsc = 0, qnx = 0;
     const double dt = P.dt;
     int32_t grp_next = 0;
     uint32_t grp_rem = 0;
+    [[maybe_unused]] uint32_t grp_dq = 0, grp_dr = 32;
     const uint32_t gsz = (uint32_t)P.group_size;
     if (FIELD == EMC_FIELD_GROUPS) {
         const uint64_t g0 = A.pid_offset + (uint64_t)wstart;
         const uint64_t gq = g0 / (uint64_t)P.group_size;
         grp_next = (int32_t)(gq < (uint64_t)P.n_groups ? gq : (uint64_t)P.n_groups);
         grp_rem = (uint32_t)(g0 % (uint64_t)P.group_size);
+        if (ILV) {
+            const uint64_t delta = 32ull * (uint64_t)total_warps;
+            const uint64_t dq = delta / (uint64_t)P.group_size;
+            grp_dq = (uint32_t)(dq < 0x7fffffffull ? dq : 0x7fffffffull);
+            grp_dr = (uint32_t)(delta % (uint64_t)P.group_size);
+        }
     }
     const Mat &MT = P.mat[0];
     enum { PH_REFILL = 0, PH_SELECT = 1, PH_SCATTER = 2, PH_ADVANCE = 3 };
@@ -1591,7 +1618,7 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
         double dt_seg = 0.0;
         if (phase == PH_REFILL || phase == PH_ADVANCE) {
             if (phase == PH_REFILL) {
-                i = w0 + next + lane;
+                i = w0 + next * Wp + lane;
                 act = next + lane < wlen;
                 if (act) {
                     p.kx = A.kx[i]; p.ky = A.ky[i]; p.kz = A.kz[i];
@@ -1612,7 +1639,7 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
 #if EMC_PREFETCH_BATCHES > 0
                 {
                     const uint32_t o0 = next + (uint32_t)(EMC_PREFETCH_BATCHES - 1) * 32u;
-                    const int64_t j0 = wstart + o0;
+                    const int64_t j0 = wstart + (int64_t)o0 * Wp;
                     if (o0 < wlen && lane < 15 && (!(lane & 1) || lane == 14 || o0 + 16 < wlen)) {
                         const char *base = reinterpret_cast<const char *>((&A.kx)[lane >> 1]);
                         const int64_t off = lane < 14 ? j0 * 8 + (lane & 1) * 128 : j0 * 4;
@@ -1621,8 +1648,14 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
                 }
 #endif
                 if (FIELD == EMC_FIELD_GROUPS) {
-                    grp_rem += 32;
-                    while (grp_rem >= gsz) { grp_rem -= gsz; ++grp_next; }
+                    if (ILV) {
+                        grp_next = (int32_t)min((uint32_t)grp_next + grp_dq, 0x7fffffffu);
+                        grp_rem += grp_dr;
+                        if (grp_rem >= gsz) { grp_rem -= gsz; if (grp_next < 0x7fffffff) ++grp_next; }
+                    } else {
+                        grp_rem += 32;
+                        while (grp_rem >= gsz) { grp_rem -= gsz; ++grp_next; }
+                    }
                 }
             } else {
                 act = lane < n_adv;
@@ -1630,7 +1663,7 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
                 if (act) queue_pop<FIELD>(WQ.nx, qnx + lane, p, s0);
                 __syncwarp();
                 if (act) {
-                    i = w0 + p.off;
+                    i = ILV ? w0 + (p.off & ~31u) * Wp + (p.off & 31u) : w0 + p.off;
                     const uint32_t ts = s0 >> 16;
                     if (ts + 1u >= (uint32_t)n_steps) { store = true; act = false; }   // the last timestep is done: write back
                     else s0 = (ts + 1u) << 16;
@@ -1655,7 +1688,7 @@ flight_steps_kernel(const __grid_constant__ DevConst P, const __grid_constant__ 
             double lg = 0.0;
             PhiloxStreamSteps rng;
             if (act) {
-                i = w0 + p.off;
+                i = ILV ? w0 + (p.off & ~31u) * Wp + (p.off & 31u) : w0 + p.off;
                 rng.init(A.seed, A.pid_offset + (uint64_t)i, A.step + (s0 >> 16), s0 & 0xffffu);
                 int v = p.val, f, mech = 0;
                 double e_np = 0.0, r_az = 0.0;

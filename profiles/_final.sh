@@ -2,6 +2,4 @@ set -x
 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/r2z_pytest_gpu.log
 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/r2z_bench_reference.json 2> gpurun_out/r2z_bench_reference.err
 python bench.py --steps 20 --warmup 5 > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2z_launches.csv python bench.py --steps 5 --warmup 3 --no-e2e --no-coupled > gpurun_out/r2z_ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:flight_scatter -s 4 -c 1 -o gpurun_out/flight_r2z -f python profiles/kernel_ab.py --no-fused --steps 2 --warmup 3 > gpurun_out/r2z_ncu_full.log 2>&1
-tail -c 300 gpurun_out/r2z_bench.json
+tail -c 300 gpurun_out/r2z_bench.json; cat gpurun_out/r2z_pytest_gpu.log; tail -3 gpurun_out/r2z_bench.err

@@ -35,6 +35,9 @@ KEYS = [
     "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
     "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
     "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+    # balance of the persistent grid: how long the least / average / most loaded SM is busy within the launch
+    "sm__cycles_elapsed.max", "sm__cycles_active.min", "sm__cycles_active.avg", "sm__cycles_active.max",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
 ]
 
 
