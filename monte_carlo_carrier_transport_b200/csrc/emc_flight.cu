@@ -582,7 +582,9 @@ __device__ __forceinline__ void queue_push(WarpQueue &Q, int slot, const Particl
 
 #ifndef EMC_INTERLEAVE_BATCHES
 // 1: the lean constant / group-field kernels give a warp every W-th batch of the ensemble instead of a contiguous
-// run (see ILV in flight_scatter_kernel)
+// run (see ILV in flight_scatter_kernel): 0.911 -> 0.889 ms on configs[1], profiles/r2au_ab_*.
+// 2: the lean mesh-field kernels, too -- measured 0.7 % slower (0.647 vs 0.6425 ms on 1024 x 1 x 1024,
+// profiles/r2aw_ab_*): their plain loads behind an L2 prefetch like the contiguous run better.
 #define EMC_INTERLEAVE_BATCHES 1
 #endif
 #ifndef EMC_INTERLEAVE_STEPS_KERNEL
@@ -808,7 +810,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
     // r2z: sm__cycles_active min / max).  Interleaved, every warp samples every group.  Batches stay 32 consecutive
     // particles (the same 256-byte row slices), and at any moment the grid works on one contiguous window of the
     // ensemble.  A particle's offset in its warp's run (`next` + lane, p.off) -> its index: w0 + (off / 32) * 32 W + off % 32.
-    constexpr bool ILV = EMC_INTERLEAVE_BATCHES && ZON;
+    constexpr bool ILV = EMC_INTERLEAVE_BATCHES && (ZON || (EMC_INTERLEAVE_BATCHES > 1 && LEAN));   // 2: the lean mesh-field kernels, too (A/B)
     int64_t wstart, wend;
     uint32_t wlen_;
     if (ILV) {
@@ -962,7 +964,7 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             act = next + lane < wlen;
             if (AHEAD && next + lane + 32 < wlen) {
                 ahead = true;
-                nx_ = A.x[i + 32u]; ny_ = A.y[i + 32u]; nz_ = A.z[i + 32u];
+                nx_ = A.x[i + 32u * Wp]; ny_ = A.y[i + 32u * Wp]; nz_ = A.z[i + 32u * Wp];
             }
 #if EMC_STAGE_REFILL
             asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -114,6 +114,7 @@ def main():
         for _ in range(args.warmup):
             cs.step()
         fl, dp = [], []
+        ctx.set_obs_phase(True)       # as bench.py's coupled loop: observables in the load phase -> the lean kernel
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         for s in range(args.steps):
             cs.mesh.zero_counts()
