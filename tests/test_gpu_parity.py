@@ -824,6 +824,66 @@ def test_timestep_chain_bit_identical_to_one_launch_per_timestep(ctx, torch_mod,
     assert len(rows) == 3
 
 
+def test_timestep_chain_split_and_unaligned_rows(ctx, torch_mod):
+    """Two corners of the timestep chains: a loop longer than one chain (CHAIN_MAX_STEPS = 1024 timesteps per
+    launch: 1030 -> 1024 + 6), and state rows that are only 8-byte aligned (no bulk-tensor refill: every batch is
+    read with plain L2 loads) -- both equal one launch per timestep bit for bit, state and rows."""
+    torch = torch_mod
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    g = helpers.golden_params()["phys"]
+    ctx.set_efield([0, 0, -30000.0])
+    seed = 77
+
+    def run(ptrs, n, K, chained):
+        rows = torch.zeros((K, 11), dtype=torch.int64, device=ctx.device)
+        ctx.set_obs_phase(True)
+        try:
+            before = ctx.launch_count()
+            if chained:
+                ctx.check(ctx.lib.emc_flight_scatter_steps(ctx.h, *ptrs, n, abi.FIELD_CONSTANT, None, None, None, seed, 3, 40, K,
+                                                           rows.data_ptr(), ctx.stream))
+            else:
+                for s in range(K):
+                    ctx.check(ctx.lib.emc_flight_scatter(ctx.h, *ptrs, n, abi.FIELD_CONSTANT, None, None, None, seed, 3, 40 + s,
+                                                         rows[s].data_ptr(), None, ctx.stream))
+            return rows, ctx.launch_count() - before
+        finally:
+            ctx.set_obs_phase(False)
+
+    # (1) 1030 timesteps: two chains
+    n, K = 4097, 1030
+    coords, v, dtau = hot_ensemble(n, 81, g)
+    a = engine.Ensemble(ctx, n, pid_offset=3).load(coords, v, dtau)
+    b = engine.Ensemble(ctx, n, pid_offset=3).load(coords, v, dtau)
+    rows_a, la = run(a._ptrs(), n, K, False)
+    rows_b, lb = run(b._ptrs(), n, K, True)
+    assert (la, lb) == (K, 2)
+    assert torch.equal(a.state, b.state) and torch.equal(a.valley, b.valley) and torch.equal(rows_a, rows_b)
+
+    # (2) rows at odd 8-byte offsets: (7, n + 2) storage, particles 1 .. n
+    n, K = 300_000, 5
+    coords, v, dtau = hot_ensemble(n, 82, g)
+    ref = engine.Ensemble(ctx, n, pid_offset=3).load(coords, v, dtau)
+    stores = []
+    for chained in (False, True):
+        st = torch.zeros((7, n + 2), dtype=torch.float64, device=ctx.device)
+        vs = torch.zeros(n + 3, dtype=torch.int32, device=ctx.device)
+        st[:, 1:n + 1] = ref.state[:, :n]
+        vs[1:n + 1] = ref.valley[:n]
+        ptrs = [st.data_ptr() + r * (n + 2) * 8 + 8 for r in range(7)] + [vs.data_ptr() + 4]
+        assert all(p % 16 == 8 for p in ptrs[:7])
+        rows, nl = run(ptrs, n, K, chained)
+        assert nl == (1 if chained else K)
+        stores.append((st, vs, rows))
+    for x, y in zip(stores[0], stores[1]):
+        assert torch.equal(x, y)
+    # ... and equal to the aligned layout
+    rows_r, _ = run(ref._ptrs(), n, K, True)
+    assert torch.equal(stores[1][0][:, 1:n + 1], ref.state[:, :n]) and torch.equal(stores[1][1][1:n + 1], ref.valley[:n])
+    assert torch.equal(rows_r, stores[1][2])
+    ctx.set_efield(g["efield"])
+
+
 @pytest.mark.parametrize("mode", ["constant", "groups"])
 def test_fused_timesteps_bit_identical_to_single_launches(ctx, torch_mod, mode):
     """emc_flight_scatter_steps without observable rows = ONE persistent launch that keeps the
