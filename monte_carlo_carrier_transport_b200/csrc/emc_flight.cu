@@ -161,6 +161,21 @@ __device__ __forceinline__ void deposit_ngp_particle(const DevConst &P, double x
                 add(((int64_t)hx[a] * P.seg[1] + hy[b]) * P.seg[2] + hz[c]);
 }
 
+#ifdef EMC_WARP_END_TIMES
+// Debug builds only (profiles/warp_end_times.py): when every warp of the last flight_scatter_kernel launch entered and
+// left its loop (%globaltimer, ns).  Not part of the C-ABI of the product library.
+__device__ unsigned long long g_warp_t0[8192], g_warp_t1[8192];
+}  // namespace emc
+extern "C" int emc_debug_warp_times(unsigned long long *t0, unsigned long long *t1, int n)
+{
+    if (n > 8192) n = 8192;
+    if (cudaMemcpyFromSymbol(t0, emc::g_warp_t0, sizeof(unsigned long long) * n) != cudaSuccess) return 1;
+    if (cudaMemcpyFromSymbol(t1, emc::g_warp_t1, sizeof(unsigned long long) * n) != cudaSuccess) return 1;
+    return 0;
+}
+namespace emc {
+#endif
+
 // ------------------------------------------------------------------------------------------
 // the timestep kernel
 //
@@ -854,6 +869,13 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
 #if EMC_STAGE_REFILL
     stage_batch(WQ, A, wstart + next + lane, wend, lane);
 #endif
+#ifdef EMC_WARP_END_TIMES
+    if (LEAN && lane == 0 && gw < 8192) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_warp_t0[gw] = t;
+    }
+#endif
     int qn = 0, qsc = 0;                          // lengths of the event / scatter queues (warp-uniform)
     // EMC_FIELD_MESH_PACKED: a refill pass gathers the field record of the FOLLOWING batch (whose
     // positions it loads early and turns into a cell after its own flight), so that a refill never
@@ -1288,6 +1310,13 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             if (v) atomicAdd(reinterpret_cast<unsigned long long *>(A.mesh) + t, (unsigned long long)v);
         }
     }
+#ifdef EMC_WARP_END_TIMES
+    if (LEAN && lane == 0 && gw < 8192) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_warp_t1[gw] = t;
+    }
+#endif
     if (LEAN) acc.derive_segments();
     if (obs_out) obs_block_reduce_and_finish(acc, obs_parts, obs_ticket, obs_out, bid, nblk, !CHAIN);
     if constexpr (!CHAIN) {
