@@ -249,7 +249,13 @@ int emc_flight_scatter(EmcCtx *ctx, double *kx, double *ky, double *kz, double *
  * libm composition, the reference's table layout -- all n_steps (2 .. 65535) timesteps run in ONE
  * persistent launch in which a particle stays in its warp's queues from timestep to timestep
  * (no reload / write-back per timestep); the final state is bit-identical to n_steps single launches.
- * EMC_FUSED_STEPS=0 in the environment keeps the launch loop. */
+ * EMC_FUSED_STEPS=0 in the environment keeps the launch loop.
+ * With obs_rows != NULL in the before-step observable phase (emc_set_obs_phase(ctx, 1)) and the same lean case,
+ * the timesteps run as timestep chains: up to 1024 timesteps and their rows per persistent launch, the blocks
+ * taking (slice, timestep) work items from a device-side queue -- a timestep of a slice waits only for the
+ * previous timestep of THAT slice.  State and rows are bit-identical to n_steps single launches.  One chain
+ * per context at a time (the queue lives in the context, like the observable partials: callers that drive
+ * one context from several streams serialise these calls).  EMC_CHAIN_STEPS=0 keeps the launch loop. */
 int emc_flight_scatter_steps(EmcCtx *ctx, double *kx, double *ky, double *kz, double *x,
                              double *y, double *z, double *dtau, int32_t *valley, int64_t n,
                              int32_t field_mode, const double *ex, const double *ey,
