@@ -768,7 +768,9 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
                 item = (unsigned long long)T;                     // timestep 0 of slice T: the state as the caller left it
             } else {
                 // item T is pushed by the block that finishes the timestep before it on that slice: a block with a
-                // smaller ticket, i.e. one that is running (all blocks are resident: one wave)
+                // smaller ticket, and a ticket is only ever held by a block that is running -- no deadlock, whatever
+                // part of the grid is resident.  The slot's tag (T + 1) tells this item from the one that used the
+                // slot CHAIN_RING items earlier; at most `slices` items are in flight at a time (<< CHAIN_RING).
                 const unsigned long long *slot = &C->ready[T % CHAIN_RING];
                 for (;;) {
                     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(item) : "l"(slot) : "memory");
