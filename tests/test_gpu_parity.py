@@ -321,6 +321,33 @@ def test_field_groups_mode_vs_oracle(ctx, torch_mod):
     compare_states(st, *ens.coords(), np.array(g["tot_dim"]))
 
 
+def test_field_groups_many_small_groups_interleaved_batches_vs_oracle(ctx, torch_mod):
+    """The lean group-field kernel with interleaved batches (a warp takes every W-th batch of the ensemble and
+    advances its group bookkeeping by a precomputed (quotient, remainder) per batch): 1300 groups of 300
+    particles -- a batch straddles groups, a warp's next batch is 252 groups further on -- a pid_offset that is
+    no multiple of anything, particles beyond the last group, against the oracle's per-particle division."""
+    from monte_carlo_carrier_transport_b200 import abi, engine
+    g = helpers.golden_params()["phys"]
+    n, gs, n_groups, off = 400_003, 300, 1300, 12_345      # groups 41 .. 1374: the last 74 clamp to group 1299
+    fields = np.zeros((n_groups, 3))
+    fields[:, 2] = -np.logspace(2, np.log10(5e4), n_groups)
+    coords, v, dtau = hot_ensemble(n, 38, g)
+    o = helpers.make_oracle()
+    o.set_field_groups(fields, gs)
+    ctx.set_field_groups(fields, gs)
+    assert ctx.describe()["zonly_groups"] == "1" and ctx.describe()["lean"] == "1"
+    st = helpers.state_from_coords(coords, v, dtau)
+    ens = engine.Ensemble(ctx, n, pid_offset=off).load(coords, v, dtau)
+    ctx.set_obs_phase(True)                      # observables in the load phase: the lean kernel
+    try:
+        for s in range(4):
+            ens.step(s, 19, field_mode=abi.FIELD_GROUPS)
+            o.timestep(st, orc.philox_stream(19, s, off), threads=8)
+    finally:
+        ctx.set_obs_phase(False)
+    compare_states(st, *ens.coords(), np.array(g["tot_dim"]))
+
+
 def test_cyclic_z_extension_vs_oracle(torch_mod):
     """z_cyclic = 1 (bulk runs): z wraps like x and y instead of reflecting; same flag in the oracle."""
     from monte_carlo_carrier_transport_b200 import engine
