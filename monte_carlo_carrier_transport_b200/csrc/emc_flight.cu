@@ -183,7 +183,8 @@ namespace emc {
 // particles need no scatter event, 36 % one, the tail is unbounded.  One thread per particle
 // therefore runs the (fp64-heavy, ~1400 instruction) event body with a third of the lanes
 // active (measured 10/32, profiles/r1a_baseline_flight_ncu.txt).  Instead each WARP owns a
-// contiguous slice of the ensemble and two small queues in shared memory, and every pass of its
+// run of 32-particle batches of the ensemble (a contiguous slice, or every W-th batch: ILV below) and two
+// small queues in shared memory, and every pass of its
 // loop runs ONE of three phases with (nearly) all 32 lanes busy:
 //   refill   load the next 32 particles (fully coalesced 256-B rows per state array), fly the
 //            first segment, retire the particles whose free flight outlasts the timestep and
