@@ -770,14 +770,16 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             } else {
                 // item T is pushed by the block that finishes the timestep before it on that slice: a block with a
                 // smaller ticket, and a ticket is only ever held by a block that is running -- no deadlock, whatever
-                // part of the grid is resident.  The slot's tag (T + 1) tells this item from the one that used the
-                // slot CHAIN_RING items earlier; at most `slices` items are in flight at a time (<< CHAIN_RING).
+                // part of the grid is resident.  The slot's tag (T + 1) tells this item from the ones that use the
+                // slot CHAIN_RING items earlier or later; at most `slices` items are in flight at a time (<< CHAIN_RING).
                 const unsigned long long *slot = &C->ready[T % CHAIN_RING];
                 for (;;) {
                     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(item) : "l"(slot) : "memory");
                     if ((unsigned int)(item >> 32) == T + 1u) break;
                     __nanosleep(64);
                 }
+                // the slot is free again (a pusher waits for an empty slot: tests/test_chain_protocol_model.py)
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(slot), "l"(0ull) : "memory");
                 item &= 0xffffffffull;
                 __threadfence();
             }
@@ -1333,7 +1335,16 @@ flight_scatter_kernel(const __grid_constant__ DevConst P, const __grid_constant_
             __threadfence();
             const unsigned int Pn = (unsigned int)A.chain_slices + atomicAdd(&C->pushed, 1u);
             const unsigned long long v = ((unsigned long long)(Pn + 1u) << 32) | ((unsigned long long)(chain_j + 1u) << 16) | bid;
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&C->ready[Pn % CHAIN_RING]), "l"(v) : "memory");
+            unsigned long long *slot = &C->ready[Pn % CHAIN_RING];
+            // wait for an EMPTY slot (its reader of CHAIN_RING items ago empties it): never taken in practice, but it makes
+            // the ring safe for every schedule instead of for every plausible one
+            for (;;) {
+                unsigned long long cur;
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(slot) : "memory");
+                if (cur == 0ull) break;
+                __nanosleep(64);
+            }
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(slot), "l"(v) : "memory");
         }
     }
     }   // work items
@@ -1513,7 +1524,7 @@ cudaError_t launch_flight_chain(Ctx *ctx, FlightArgs &A, int field_mode, int n_s
         !zonly || ctx->dc.n_layers != 1 || ctx->waves != 1 || !ctx->obs_before || !A.obs || A.mesh ||
         (field_mode != EMC_FIELD_CONSTANT && field_mode != EMC_FIELD_GROUPS) ||
         (field_mode == EMC_FIELD_GROUPS && !ctx->dc.field_groups) || n_steps < 2 || n_steps > CHAIN_MAX_STEPS ||
-        A.n < 1 || A.n >= ((int64_t)1 << 32) - 64 || ctx->max_grid > 65535)
+        A.n < 1 || A.n >= ((int64_t)1 << 32) - 64 || ctx->max_grid > 65535 || ctx->max_grid >= CHAIN_RING)
         return cudaErrorNotSupported;
     cudaError_t e;
     if (!ctx->d_chain && (e = cudaMalloc(&ctx->d_chain, sizeof(ChainCtl))) != cudaSuccess) return e;

@@ -23,8 +23,9 @@ struct ObsPartial {
 // device memory: a block pops one, runs the one-timestep body on that slice, and pushes (slice, timestep + 1) when
 // it has written the slice back -- no grid-wide barrier between timesteps (slices are independent: a timestep
 // only needs ITS slice of the previous one), so a slow SM never holds the others up and there is no launch gap.
-// ready[i]: (i + 1) << 32 | timestep << 16 | slice, written with release semantics; the first `slices` items
-// (timestep 0 of every slice) are implicit.  Zeroed by a memset before every chain launch.
+// ready[i % CHAIN_RING]: (i + 1) << 32 | timestep << 16 | slice, written with release semantics into an EMPTY slot
+// (0; the reader empties it again); the first `slices` items (timestep 0 of every slice) are implicit.  Zeroed by a
+// memset before every chain launch.  The protocol under random schedules: tests/test_chain_protocol_model.py.
 constexpr int CHAIN_RING = 4096;          // >> the number of items in flight (<= slices <= max_grid)
 constexpr int CHAIN_MAX_STEPS = 1024;     // timesteps per chain launch (longer loops are split)
 struct ChainCtl {
